@@ -1,0 +1,197 @@
+/*
+ * ntsm_b200.h -- C ABI of libntsm_b200.so: the B200-native counting hot path of ntsmCount.
+ *
+ * The reference (JustinChu/ntsm @663f9a5) has no FFI: the seam this library sits behind is
+ * the five-call sequence of src/ntSeqMatchCount.cpp:177-181
+ *     FingerPrint fp; fp.computeCounts(files); fp.printOptionalHeader();
+ *     fp.printCountsMax(); fp.printInfoSummary();
+ * plus the per-read consumer contract FingerPrint::insertCount(seq,len)
+ * (src/FingerPrint.hpp:89-103; `T::consume(kseq_t&)` in vendor/ProdConKseqRunner.hpp:93).
+ * Every entry point below names the reference member it replaces.  INTEGRATION.md shows
+ * the binding a maintainer of the reference would add.
+ *
+ * Conventions: plain C types, opaque handles, caller-owned outputs, no exceptions and no
+ * exit() across the boundary.  Every function that can fail returns 0 (NTSM_OK) or a negative
+ * NTSM_ERR_* code; ntsm_last_error() gives the text.  There is NO CPU fallback: without a
+ * CUDA device ntsm_ctx_create fails with NTSM_ERR_CUDA.
+ *
+ * Packed batch layout ("2-bit + N-mask"), the unit streamed to the GPU:
+ *   A batch is ONE stream of positions.  Position p holds a base code in bits
+ *   [2*(p%16), 2*(p%16)+2) of the little-endian uint32 word bases2[p/16]
+ *   (A=0 C=1 G=2 T/U=3, decoded with the reference table vendor/KseqHashIterator.hpp:114-127)
+ *   and an invalid flag in bit (p%32) of nmask[p/32] (1 = the byte decoded to 4, i.e. "N").
+ *   Reads are laid end to end with exactly one invalid separator position after each read,
+ *   so no k-mer window can span two reads.  read_off[r] is the position of read r's first
+ *   base (read_off[n_reads] = end).  The tail is padded with invalid positions up to
+ *   ntsm_padded_positions(n_pos).
+ */
+#ifndef NTSM_B200_H
+#define NTSM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NTSM_OK 0
+#define NTSM_ERR_ARG (-1)    /* bad argument / bad state                                  */
+#define NTSM_ERR_CUDA (-2)   /* CUDA runtime failure (incl. no device)                    */
+#define NTSM_ERR_NCCL (-3)   /* NCCL failure                                              */
+#define NTSM_ERR_IO (-5)     /* file cannot be opened / read                              */
+#define NTSM_ERR_NOKEY (-134) /* the reference would abort here with std::out_of_range:
+                                a duplicate k-mer erased from the table (no -d) is still in a
+                                site list, or the last site has no var record
+                                (src/FingerPrint.hpp:276,282)                             */
+
+typedef struct ntsm_ctx ntsm_ctx;     /* one per GPU: table, counts, streams, pinned buffers */
+typedef struct ntsm_batch ntsm_batch; /* one pinned packed batch, owned by its ctx           */
+typedef struct ntsm_sites ntsm_sites; /* host result of FingerPrint::initCountsHash          */
+typedef struct ntsm_reader ntsm_reader; /* FASTA/FASTQ(.gz) record reader (kseq semantics)   */
+
+typedef struct ntsm_cfg {
+	uint32_t k;           /* opt::k (src/Options.h:23); 1..31                              */
+	int32_t device;       /* CUDA device ordinal                                           */
+	uint32_t n_buffers;   /* pinned+device batch buffers, >=2 (0 = default 3)              */
+	uint32_t reserved;
+	uint64_t batch_bases; /* capacity of one batch in stream positions (0 = default 2^25)  */
+	uint64_t max_counts;  /* m_maxCounts (src/FingerPrint.hpp:41-43); 0 = no -m cap        */
+} ntsm_cfg;
+
+const char *ntsm_version(void);
+int ntsm_device_count(void); /* visible CUDA devices; 0 when there is none (nothing can be counted then) */
+/* text of the last error on this ctx, or (ctx == NULL) of the calling thread */
+const char *ntsm_last_error(const ntsm_ctx *ctx);
+
+/* ---------------- host arithmetic shared with the reference ---------------- */
+/* vendor/KseqHashIterator.hpp:114-127 */
+uint32_t ntsm_nt4(uint8_t c);
+/* vendor/KseqHashIterator.hpp:129-139 (mask = 4^k - 1) and its inverse (the hash is a bijection) */
+uint64_t ntsm_hash64(uint64_t key, uint32_t k);
+uint64_t ntsm_hash64_inv(uint64_t hash, uint32_t k);
+
+/* ---------------- site set: FingerPrint::initCountsHash (src/FingerPrint.hpp:490-564) ------ */
+/* Reads the interleaved ref/var FASTA (plain or gz), first occurrence of a k-mer wins, later
+ * occurrences produce the reference's warning text and, unless allow_dupes (-d), are erased
+ * from the table while staying in the first owner's list. */
+int ntsm_sites_load(ntsm_sites **out, const char *path, uint32_t k, int allow_dupes);
+void ntsm_sites_free(ntsm_sites *s);
+uint32_t ntsm_sites_k(const ntsm_sites *s);
+uint32_t ntsm_sites_n_sites(const ntsm_sites *s);        /* m_alleleIDs.size()                 */
+uint32_t ntsm_sites_n_kmers(const ntsm_sites *s);        /* listed k-mers = dense index space  */
+uint64_t ntsm_sites_table_size(const ntsm_sites *s);     /* m_counts.size() after dupe removal */
+const uint64_t *ntsm_sites_hashes(const ntsm_sites *s);  /* [n_kmers] hash64, list order: ref_0,var_0,ref_1,... */
+const uint32_t *ntsm_sites_allele_off(const ntsm_sites *s); /* [2*n_sites+1] CSR into the above   */
+const uint8_t *ntsm_sites_erased(const ntsm_sites *s);   /* [n_kmers] 1 = erased duplicate      */
+const char *ntsm_sites_name(const ntsm_sites *s, uint32_t i); /* m_alleleIDs[i]                 */
+uint32_t ntsm_sites_n_warnings(const ntsm_sites *s);
+const char *ntsm_sites_warning(const ntsm_sites *s, uint32_t i); /* "Warning: <name> of REF file has a k-mer collision at pos: <p>" */
+/* 0 if printCountsMax would complete, NTSM_ERR_NOKEY if the reference would abort */
+int ntsm_sites_printable(const ntsm_sites *s);
+/* m_maxCounts for -m <cov>: uint64((double)table_size * cov / 2); cov <= 0 -> 0 (off) */
+uint64_t ntsm_sites_max_counts(const ntsm_sites *s, double cov);
+
+/* ---------------- device context: FingerPrint object ---------------- */
+int ntsm_ctx_create(ntsm_ctx **out, const ntsm_cfg *cfg);          /* FingerPrint() :35-44 */
+void ntsm_ctx_destroy(ntsm_ctx *ctx);
+/* Builds the device table (open addressing, keyed by the reference hash64 value) and the
+ * orientation-free k-mer pre-filter; zeroes counts.  kmer_hash[i] is the hash of dense k-mer i;
+ * erased (nullable) marks entries that are listed but not in the table. */
+int ntsm_load_sites(ntsm_ctx *ctx, const uint64_t *kmer_hash, const uint8_t *erased, uint32_t n_kmers,
+                    const uint32_t *allele_off, uint32_t n_sites);  /* initCountsHash :490-564 */
+int ntsm_load_siteset(ntsm_ctx *ctx, const ntsm_sites *s);
+
+/* ---------------- packed batches: the ProdCon bulk buffers (vendor/ProdConKseqRunner.hpp:34-46) */
+uint64_t ntsm_padded_positions(uint64_t n_pos); /* allocation/padding contract of a packed stream */
+/* blocks until one of the ctx's pinned buffers is free; thread-safe */
+int ntsm_acquire_batch(ntsm_ctx *ctx, ntsm_batch **b);
+/* Packs read bases seq[*pos..len) into the batch (insertCount's input, :89).  *pos = bases of
+ * this read already consumed by earlier batches (0 for a new read); a read that does not fit is
+ * split and the k-1 overlapping bases are re-packed by the library so every k-mer is counted
+ * once.  Returns 1 = read complete, 0 = batch full (submit, acquire, call again), <0 error. */
+int ntsm_batch_append(ntsm_batch *b, const char *seq, uint64_t len, uint64_t *pos);
+uint64_t ntsm_batch_positions(const ntsm_batch *b);
+uint64_t ntsm_batch_bases(const ntsm_batch *b);
+uint64_t ntsm_batch_reads(const ntsm_batch *b);
+/* async: cudaMemcpyAsync of the packed arrays + count kernel; the buffer recycles itself */
+int ntsm_submit_batch(ntsm_ctx *ctx, ntsm_batch *b);
+/* gives an acquired batch back without counting it */
+int ntsm_release_batch(ntsm_ctx *ctx, ntsm_batch *b);
+
+/* standalone packer with the same layout (no ctx): packs n_reads reads buf[off[r]..off[r+1])
+ * into caller memory sized for ntsm_padded_positions(sum(len)+n_reads). Returns n_pos. */
+uint64_t ntsm_pack_reads(const char *buf, const uint64_t *off, uint64_t n_reads, uint32_t *bases2,
+                         uint32_t *nmask, uint64_t *read_off /*nullable, n_reads+1*/);
+
+/* Count a packed stream that is ALREADY in device memory (padding contract as above) on
+ * `cuda_stream` (a cudaStream_t; NULL = the ctx's compute stream).  Adds n_bases to the base tally. */
+int ntsm_count_packed_device(ntsm_ctx *ctx, const uint32_t *d_bases2, const uint32_t *d_nmask,
+                             uint64_t n_pos, uint64_t n_bases, void *cuda_stream);
+
+/* insertCount drop-in (src/FingerPrint.hpp:89): packs into the ctx's current batch and submits
+ * it when full.  Single producer; ntsm_flush submits the partial batch. */
+int ntsm_insert_count(ntsm_ctx *ctx, const char *seq, uint64_t len);
+int ntsm_flush(ntsm_ctx *ctx);
+
+/* m_totalKmers / m_totalCounts / m_totalBases / m_earlyTerm (:458-463) over COMPLETED batches;
+ * non-blocking.  cap_reached = hits > max_counts at a batch boundary. */
+int ntsm_poll_totals(ntsm_ctx *ctx, uint64_t *total_kmers, uint64_t *total_hits, uint64_t *total_bases,
+                     int *cap_reached);
+int ntsm_sync(ntsm_ctx *ctx);          /* drain every submitted batch */
+int ntsm_reset_counts(ntsm_ctx *ctx);  /* zero counts and tallies, keep the table */
+
+/* ---------------- multi-GPU: one ctx (process or thread) per GPU ---------------- */
+#define NTSM_NCCL_ID_BYTES 128
+int ntsm_nccl_unique_id(void *id_out);                         /* ncclGetUniqueId */
+int ntsm_comm_init(ntsm_ctx *ctx, const void *id, int rank, int n_ranks);
+/* sum counts (u32) and tallies (u64) over all ranks: ONE ncclAllReduce each, before the per-site max */
+int ntsm_allreduce(ntsm_ctx *ctx);
+
+/* ---------------- results: printOptionalHeader + printCountsMax (:261-311) ---------------- */
+/* drains, runs the per-site reduce kernel, copies out.  Arrays have n_sites entries;
+ * totals = {total_kmers (#@TK), total_hits, total_bases}.  Any pointer may be NULL. */
+int ntsm_finalize(ntsm_ctx *ctx, uint32_t *max_ref, uint32_t *max_var, uint32_t *sum_ref, uint32_t *sum_var,
+                  uint64_t totals[3]);
+int ntsm_get_counts(ntsm_ctx *ctx, uint32_t *counts /* [n_kmers] */);
+/* getSitesCoveredInSample (:389-413) from finalize()'s maxima */
+uint32_t ntsm_sites_covered(const uint32_t *max_ref, const uint32_t *max_var, uint32_t n_sites);
+/* writes "#@TK..#@KS..\n#locusID...\n" + rows exactly as the reference does; returns bytes written
+ * (call with buf == NULL to size), or NTSM_ERR_NOKEY */
+int64_t ntsm_format_counts(const ntsm_sites *s, const uint32_t *max_ref, const uint32_t *max_var,
+                           const uint32_t *sum_ref, const uint32_t *sum_var, uint64_t total_kmers, char *buf,
+                           size_t cap);
+/* printInfoSummary text (:313-333) */
+int64_t ntsm_format_summary(const ntsm_sites *s, const uint64_t totals[3], uint32_t covered, char *buf, size_t cap);
+
+/* introspection (bench/tests): kernels launched so far, pre-filter size (log2 bits), table slots */
+uint64_t ntsm_ctx_launches(const ntsm_ctx *ctx);
+uint32_t ntsm_ctx_filter_bits(const ntsm_ctx *ctx);
+uint32_t ntsm_ctx_table_capacity(const ntsm_ctx *ctx);
+
+/* ---------------- record reader: kseq_read (vendor/kseq.h:178-219) ---------------- */
+int ntsm_reader_open(ntsm_reader **out, const char *path);
+/* returns sequence length >= 0 and sets *seq (valid until the next call), or -1 end of file,
+ * -2 truncated/mismatched quality, -3 stream error -- the codes of kseq.h:171-176 */
+int64_t ntsm_reader_next(ntsm_reader *r, const char **seq);
+const char *ntsm_reader_name(const ntsm_reader *r);
+void ntsm_reader_close(ntsm_reader *r);
+
+/* ---------------- whole path: FingerPrint::computeCounts (src/FingerPrint.hpp:46-87) -------- */
+/* Reads every file with `threads` parser threads (one file per thread at a time, like the
+ * reference's omp parallel for over files), packs reads into pinned batches and streams batch i
+ * to ctxs[i % n_ctx].  With a -m cap (cfg.max_counts of ctxs[0]) the summed hit tally is checked
+ * after every submitted batch against the batches completed so far (batch granularity, one batch
+ * of lag); parsing stops once it is exceeded and *early (nullable) is set = m_earlyTerm.
+ * Every read parsed before the stop is counted.  Returns NTSM_ERR_IO (text in ntsm_last_error)
+ * if a file cannot be opened. */
+int ntsm_count_files(ntsm_ctx *const *ctxs, uint32_t n_ctx, const char *const *paths, uint32_t n_paths,
+                     uint32_t threads, int verbose, int *early);
+
+/* the ntsmCount command line (src/ntSeqMatchCount.cpp:53-184); returns the process exit code */
+int ntsm_main(int argc, char **argv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTSM_B200_H */

@@ -1,0 +1,111 @@
+"""ctypes binding of include/ntsm_b200.h.  Fails loudly if the library has not been built."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libntsm_b200.so")
+
+
+class NtsmError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("ntsm_b200 error %d: %s" % (code, text))
+        self.code = code
+
+
+class Cfg(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("device", C.c_int32), ("n_buffers", C.c_uint32), ("reserved", C.c_uint32),
+                ("batch_bases", C.c_uint64), ("max_counts", C.c_uint64)]
+
+
+_P = C.c_void_p
+_SIGS = {
+    # name: (restype, argtypes)
+    "ntsm_version": (C.c_char_p, []),
+    "ntsm_device_count": (C.c_int, []),
+    "ntsm_last_error": (C.c_char_p, [_P]),
+    "ntsm_nt4": (C.c_uint32, [C.c_uint8]),
+    "ntsm_hash64": (C.c_uint64, [C.c_uint64, C.c_uint32]),
+    "ntsm_hash64_inv": (C.c_uint64, [C.c_uint64, C.c_uint32]),
+    "ntsm_sites_load": (C.c_int, [C.POINTER(_P), C.c_char_p, C.c_uint32, C.c_int]),
+    "ntsm_sites_free": (None, [_P]),
+    "ntsm_sites_k": (C.c_uint32, [_P]),
+    "ntsm_sites_n_sites": (C.c_uint32, [_P]),
+    "ntsm_sites_n_kmers": (C.c_uint32, [_P]),
+    "ntsm_sites_table_size": (C.c_uint64, [_P]),
+    "ntsm_sites_hashes": (C.POINTER(C.c_uint64), [_P]),
+    "ntsm_sites_allele_off": (C.POINTER(C.c_uint32), [_P]),
+    "ntsm_sites_erased": (C.POINTER(C.c_uint8), [_P]),
+    "ntsm_sites_name": (C.c_char_p, [_P, C.c_uint32]),
+    "ntsm_sites_n_warnings": (C.c_uint32, [_P]),
+    "ntsm_sites_warning": (C.c_char_p, [_P, C.c_uint32]),
+    "ntsm_sites_printable": (C.c_int, [_P]),
+    "ntsm_sites_max_counts": (C.c_uint64, [_P, C.c_double]),
+    "ntsm_ctx_create": (C.c_int, [C.POINTER(_P), C.POINTER(Cfg)]),
+    "ntsm_ctx_destroy": (None, [_P]),
+    "ntsm_load_sites": (C.c_int, [_P, _P, _P, C.c_uint32, _P, C.c_uint32]),
+    "ntsm_load_siteset": (C.c_int, [_P, _P]),
+    "ntsm_padded_positions": (C.c_uint64, [C.c_uint64]),
+    "ntsm_acquire_batch": (C.c_int, [_P, C.POINTER(_P)]),
+    "ntsm_batch_append": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "ntsm_batch_positions": (C.c_uint64, [_P]),
+    "ntsm_batch_bases": (C.c_uint64, [_P]),
+    "ntsm_batch_reads": (C.c_uint64, [_P]),
+    "ntsm_submit_batch": (C.c_int, [_P, _P]),
+    "ntsm_release_batch": (C.c_int, [_P, _P]),
+    "ntsm_pack_reads": (C.c_uint64, [_P, _P, C.c_uint64, _P, _P, _P]),
+    "ntsm_count_packed_device": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, _P]),
+    "ntsm_insert_count": (C.c_int, [_P, C.c_char_p, C.c_uint64]),
+    "ntsm_flush": (C.c_int, [_P]),
+    "ntsm_poll_totals": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
+    "ntsm_sync": (C.c_int, [_P]),
+    "ntsm_reset_counts": (C.c_int, [_P]),
+    "ntsm_nccl_unique_id": (C.c_int, [_P]),
+    "ntsm_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "ntsm_allreduce": (C.c_int, [_P]),
+    "ntsm_finalize": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "ntsm_get_counts": (C.c_int, [_P, _P]),
+    "ntsm_sites_covered": (C.c_uint32, [_P, _P, C.c_uint32]),
+    "ntsm_format_counts": (C.c_int64, [_P, _P, _P, _P, _P, C.c_uint64, _P, C.c_size_t]),
+    "ntsm_format_summary": (C.c_int64, [_P, _P, C.c_uint32, _P, C.c_size_t]),
+    "ntsm_ctx_launches": (C.c_uint64, [_P]),
+    "ntsm_ctx_filter_bits": (C.c_uint32, [_P]),
+    "ntsm_ctx_table_capacity": (C.c_uint32, [_P]),
+    "ntsm_reader_open": (C.c_int, [C.POINTER(_P), C.c_char_p]),
+    "ntsm_reader_next": (C.c_int64, [_P, C.POINTER(C.c_char_p)]),
+    "ntsm_reader_name": (C.c_char_p, [_P]),
+    "ntsm_reader_close": (None, [_P]),
+    "ntsm_count_files": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_int)]),
+    "ntsm_main": (C.c_int, [C.c_int, _P]),
+}
+
+_lib = None
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def lib():
+    """The loaded library.  No fallback: a missing build is an error, not a slow path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise ImportError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "or `make -C ntsm_b200/csrc` (there is no CPU fallback)" % _LIB_PATH)
+        L = C.CDLL(_LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in _SIGS.items():
+            f = getattr(L, name)          # AttributeError here = header/library mismatch
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def check(rc, ctx=None):
+    if rc < 0:
+        raise NtsmError(rc, (lib().ntsm_last_error(ctx) or b"").decode(errors="replace"))
+    return rc

@@ -1,0 +1,564 @@
+// ctx.cu -- the C ABI over the device path: context, site table, pinned batch ring, streams,
+// NCCL combine, results.  Mirrors the FingerPrint object (src/FingerPrint.hpp:32-566) and the
+// bulk-buffer recycling of vendor/ProdConKseqRunner.hpp:34-46.
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ntsm_b200.h"
+#include "internal.h"
+#include "kernels.cuh"
+#include "pack.h"
+
+using namespace ntsm;
+
+static thread_local std::string t_last_error;
+
+struct ntsm_batch {
+	ntsm_ctx *ctx = nullptr;
+	uint64_t *h_bases = nullptr;      // pinned
+	uint32_t *h_mask = nullptr;       // pinned
+	uint64_t *h_snap = nullptr;       // pinned {TK, hits} snapshot taken after this batch's kernel
+	uint2 *d_bases = nullptr;
+	uint32_t *d_mask = nullptr;
+	cudaEvent_t copied = nullptr, done = nullptr;
+	Packer pk;
+	uint64_t cap_pos = 0;             // usable positions
+	uint64_t n_bases = 0, n_reads = 0;
+	int state = 0;                    // 0 free, 1 acquired, 2 in flight
+};
+
+struct ntsm_ctx {
+	ntsm_cfg cfg{};
+	int device = 0;
+	cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+	int sm_count = 148;
+	// site table
+	uint32_t n_kmers = 0, n_sites = 0;
+	uint32_t *d_filter = nullptr;
+	uint32_t filter_bits = 0;
+	TableSlot *d_table = nullptr;
+	uint32_t table_cap = 0;
+	uint32_t *d_counts = nullptr;
+	uint32_t *d_allele_off = nullptr;
+	uint32_t *d_rows = nullptr;             // 4 * n_sites
+	unsigned long long *d_totals = nullptr; // {TK, hits, bases}
+	// batches
+	std::vector<ntsm_batch *> batches;
+	std::deque<ntsm_batch *> inflight;
+	std::mutex mu;
+	std::condition_variable cv;
+	ntsm_batch *current = nullptr;          // ntsm_insert_count's open batch
+	// tallies
+	uint64_t done_kmers = 0, done_hits = 0, done_bases = 0;   // over completed batches
+	uint64_t submitted_bases = 0;
+	uint64_t launches = 0;
+	bool reduced = false;
+	ncclComm_t comm = nullptr;
+	int rank = 0, n_ranks = 1;
+	std::string err;
+};
+
+static int fail(ntsm_ctx *c, int code, const char *fmt, ...)
+{
+	char b[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(b, sizeof b, fmt, ap);
+	va_end(ap);
+	t_last_error = b;
+	if (c) c->err = b;
+	return code;
+}
+
+#define CU(c, call)                                                                                      \
+	do {                                                                                                 \
+		cudaError_t e_ = (call);                                                                         \
+		if (e_ != cudaSuccess) return fail(c, NTSM_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+#define NC(c, call)                                                                                      \
+	do {                                                                                                 \
+		ncclResult_t e_ = (call);                                                                        \
+		if (e_ != ncclSuccess) return fail(c, NTSM_ERR_NCCL, "%s: %s (%s:%d)", #call, ncclGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+extern "C" const char *ntsm_version(void) { return "ntsm_b200 0.1 (reference ntsm 663f9a5 v1.2.1 counting path, sm_100a)"; }
+
+extern "C" const char *ntsm_last_error(const ntsm_ctx *ctx) { return ctx ? ctx->err.c_str() : t_last_error.c_str(); }
+
+extern "C" int ntsm_device_count(void)
+{
+	int n = 0;
+	return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
+// ------------------------------------------------------------------ context
+extern "C" int ntsm_ctx_create(ntsm_ctx **out, const ntsm_cfg *cfg)
+{
+	if (!out || !cfg) return fail(nullptr, NTSM_ERR_ARG, "ntsm_ctx_create: null argument");
+	if (cfg->k < 1 || cfg->k > 31) return fail(nullptr, NTSM_ERR_ARG, "k must be in 1..31 (got %u)", cfg->k);
+	int n_dev = 0;
+	cudaError_t e = cudaGetDeviceCount(&n_dev);
+	if (e != cudaSuccess || n_dev == 0)
+		return fail(nullptr, NTSM_ERR_CUDA, "no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+	if (cfg->device < 0 || cfg->device >= n_dev) return fail(nullptr, NTSM_ERR_ARG, "device %d out of range (%d devices)", cfg->device, n_dev);
+	ntsm_ctx *c = new ntsm_ctx();
+	c->cfg = *cfg;
+	if (c->cfg.n_buffers == 0) c->cfg.n_buffers = 3;
+	if (c->cfg.n_buffers < 2) c->cfg.n_buffers = 2;
+	if (c->cfg.batch_bases == 0) c->cfg.batch_bases = 1ull << 25;
+	if (c->cfg.batch_bases < 4096) c->cfg.batch_bases = 4096;
+	c->device = cfg->device;
+	CU(c, cudaSetDevice(c->device));
+	CU(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+	CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	CU(c, cudaStreamCreateWithFlags(&c->compute_stream, cudaStreamNonBlocking));
+	CU(c, cudaMalloc(&c->d_totals, 3 * sizeof(unsigned long long)));
+	CU(c, cudaMemset(c->d_totals, 0, 3 * sizeof(unsigned long long)));
+	*out = c;
+	return NTSM_OK;
+}
+
+static void free_batch(ntsm_batch *b)
+{
+	if (!b) return;
+	cudaFreeHost(b->h_bases);
+	cudaFreeHost(b->h_mask);
+	cudaFreeHost(b->h_snap);
+	cudaFree(b->d_bases);
+	cudaFree(b->d_mask);
+	if (b->copied) cudaEventDestroy(b->copied);
+	if (b->done) cudaEventDestroy(b->done);
+	delete b;
+}
+
+extern "C" void ntsm_ctx_destroy(ntsm_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaDeviceSynchronize();
+	if (c->comm) ncclCommDestroy(c->comm);
+	for (ntsm_batch *b : c->batches) free_batch(b);
+	cudaFree(c->d_filter);
+	cudaFree(c->d_table);
+	cudaFree(c->d_counts);
+	cudaFree(c->d_allele_off);
+	cudaFree(c->d_rows);
+	cudaFree(c->d_totals);
+	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+	if (c->compute_stream) cudaStreamDestroy(c->compute_stream);
+	delete c;
+}
+
+// ------------------------------------------------------------------ site table
+extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uint8_t *erased, uint32_t n_kmers,
+                               const uint32_t *allele_off, uint32_t n_sites)
+{
+	if (!c || (!kmer_hash && n_kmers) || !allele_off) return fail(c, NTSM_ERR_ARG, "ntsm_load_sites: null argument");
+	CU(c, cudaSetDevice(c->device));
+	const uint32_t k = c->cfg.k;
+	const uint64_t m = kmer_mask(k);
+	uint64_t live = 0;
+	for (uint32_t i = 0; i < n_kmers; ++i) live += !(erased && erased[i]);
+
+	// exact table: capacity = power of two >= 2 * keys (load <= 0.5, like robin_map's default, robin_map.h:90)
+	uint64_t cap = 1024;
+	while (cap < 2 * live) cap <<= 1;
+	if (cap > (1ull << 31)) return fail(c, NTSM_ERR_ARG, "too many site k-mers (%llu)", (unsigned long long)live);
+	std::vector<TableSlot> table(cap, TableSlot{ kEmptyKey, 0, 0 });
+
+	// pre-filter bitmap holding both orientations of every live k-mer
+	uint32_t fbits = 16;
+	while (fbits < 30 && (1ull << fbits) < 40ull * 2ull * live) ++fbits;
+	if (const char *e = getenv("NTSM_FILTER_BITS")) fbits = (uint32_t)std::min(32, std::max(10, atoi(e)));
+	std::vector<uint32_t> filter((1ull << fbits) / 32, 0u);
+	const uint32_t fshift = 32 - fbits;
+
+	for (uint32_t i = 0; i < n_kmers; ++i) {
+		if (erased && erased[i]) continue;
+		const uint64_t h = kmer_hash[i];
+		if (h > m) return fail(c, NTSM_ERR_ARG, "k-mer hash %u out of range for k=%u", i, k);
+		uint32_t slot = (uint32_t)(h ^ (h >> 29)) & (uint32_t)(cap - 1);
+		while (table[slot].key != kEmptyKey) {
+			if (table[slot].key == h) return fail(c, NTSM_ERR_ARG, "duplicate k-mer hash at index %u", i);
+			slot = (slot + 1) & (uint32_t)(cap - 1);
+		}
+		table[slot].key = h;
+		table[slot].idx = i;
+		// the canonical k-mer (reference orientation) and the two stream-order spellings a read can show
+		const uint64_t canon = hash64_inv(h, m);
+		const uint64_t s1 = fw_to_stream(canon, k);   // read carries the canonical strand
+		const uint64_t s2 = ~canon & m;               // read carries the other strand (kmer_math.h)
+		const uint64_t ss[2] = { s1, s2 };
+		for (uint64_t s : ss) {
+			const uint32_t ix = filter_mix((uint32_t)s, (uint32_t)(s >> 32)) >> fshift;
+			filter[ix >> 5] |= 1u << (ix & 31);
+		}
+	}
+
+	cudaFree(c->d_filter); cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_allele_off); cudaFree(c->d_rows);
+	c->d_filter = nullptr; c->d_table = nullptr; c->d_counts = nullptr; c->d_allele_off = nullptr; c->d_rows = nullptr;
+	CU(c, cudaMalloc(&c->d_filter, filter.size() * 4));
+	CU(c, cudaMalloc(&c->d_table, cap * sizeof(TableSlot)));
+	CU(c, cudaMalloc(&c->d_counts, std::max<size_t>(1, n_kmers) * 4));
+	CU(c, cudaMalloc(&c->d_allele_off, (2 * (size_t)n_sites + 1) * 4));
+	CU(c, cudaMalloc(&c->d_rows, std::max<size_t>(1, n_sites) * 16));
+	CU(c, cudaMemcpy(c->d_filter, filter.data(), filter.size() * 4, cudaMemcpyHostToDevice));
+	CU(c, cudaMemcpy(c->d_table, table.data(), cap * sizeof(TableSlot), cudaMemcpyHostToDevice));
+	CU(c, cudaMemcpy(c->d_allele_off, allele_off, (2 * (size_t)n_sites + 1) * 4, cudaMemcpyHostToDevice));
+	c->n_kmers = n_kmers;
+	c->n_sites = n_sites;
+	c->filter_bits = fbits;
+	c->table_cap = (uint32_t)cap;
+	return ntsm_reset_counts(c);
+}
+
+extern "C" int ntsm_load_siteset(ntsm_ctx *c, const ntsm_sites *s)
+{
+	if (!c || !s) return fail(c, NTSM_ERR_ARG, "ntsm_load_siteset: null argument");
+	if (ntsm_sites_k(s) != c->cfg.k) return fail(c, NTSM_ERR_ARG, "site set k=%u but ctx k=%u", ntsm_sites_k(s), c->cfg.k);
+	return ntsm_load_sites(c, ntsm_sites_hashes(s), ntsm_sites_erased(s), ntsm_sites_n_kmers(s), ntsm_sites_allele_off(s),
+	                       ntsm_sites_n_sites(s));
+}
+
+extern "C" int ntsm_reset_counts(ntsm_ctx *c)
+{
+	if (!c) return NTSM_ERR_ARG;
+	CU(c, cudaSetDevice(c->device));
+	CU(c, cudaDeviceSynchronize());
+	std::lock_guard<std::mutex> g(c->mu);
+	for (ntsm_batch *b : c->inflight) b->state = 0;
+	c->inflight.clear();
+	if (c->d_counts) CU(c, cudaMemset(c->d_counts, 0, std::max<size_t>(1, c->n_kmers) * 4));
+	CU(c, cudaMemset(c->d_totals, 0, 3 * sizeof(unsigned long long)));
+	c->done_kmers = c->done_hits = c->done_bases = c->submitted_bases = 0;
+	c->reduced = false;
+	c->cv.notify_all();
+	return NTSM_OK;
+}
+
+// ------------------------------------------------------------------ kernel launch
+static int launch_count(ntsm_ctx *c, const uint2 *d_bases, const uint32_t *d_mask, uint64_t n_pos, cudaStream_t st)
+{
+	if (!c->d_table) return fail(c, NTSM_ERR_ARG, "no site table loaded");
+	if (c->reduced) return fail(c, NTSM_ERR_ARG, "counts were already all-reduced; ntsm_reset_counts first");
+	if (n_pos == 0) return NTSM_OK;
+	CountParams P;
+	P.bases = d_bases;
+	P.nmask = d_mask;
+	P.n_chunks = (n_pos + 31) / 32;
+	P.filter = c->d_filter;
+	P.filter_shift = 32 - c->filter_bits;
+	P.table = c->d_table;
+	P.table_mask = c->table_cap - 1;
+	P.k = c->cfg.k;
+	P.counts = c->d_counts;
+	P.totals = c->d_totals;
+	const uint64_t tiles = (P.n_chunks + kCountThreads - 1) / kCountThreads;
+	const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)c->sm_count * 16);
+	if (c->cfg.k == 19) count_kernel<19><<<grid, kCountThreads, 0, st>>>(P);
+	else count_kernel<0><<<grid, kCountThreads, 0, st>>>(P);
+	CU(c, cudaGetLastError());
+	c->launches++;
+	return NTSM_OK;
+}
+
+extern "C" int ntsm_count_packed_device(ntsm_ctx *c, const uint32_t *d_bases2, const uint32_t *d_nmask, uint64_t n_pos,
+                                        uint64_t n_bases, void *cuda_stream)
+{
+	if (!c || !d_bases2 || !d_nmask) return fail(c, NTSM_ERR_ARG, "ntsm_count_packed_device: null argument");
+	CU(c, cudaSetDevice(c->device));
+	cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->compute_stream;
+	const int rc = launch_count(c, reinterpret_cast<const uint2 *>(d_bases2), d_nmask, n_pos, st);
+	if (rc == NTSM_OK) {
+		std::lock_guard<std::mutex> g(c->mu);
+		c->submitted_bases += n_bases;
+	}
+	return rc;
+}
+
+// ------------------------------------------------------------------ batches
+static int make_batch(ntsm_ctx *c, ntsm_batch **out)
+{
+	ntsm_batch *b = new ntsm_batch();
+	b->ctx = c;
+	b->cap_pos = c->cfg.batch_bases;
+	const uint64_t padded = padded_positions(b->cap_pos);
+	CU(c, cudaMallocHost(&b->h_bases, padded / 32 * 8));
+	CU(c, cudaMallocHost(&b->h_mask, padded / 32 * 4));
+	CU(c, cudaMallocHost(&b->h_snap, 16));
+	CU(c, cudaMalloc(&b->d_bases, padded / 32 * 8));
+	CU(c, cudaMalloc(&b->d_mask, padded / 32 * 4));
+	CU(c, cudaEventCreateWithFlags(&b->copied, cudaEventDisableTiming));
+	CU(c, cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming));
+	*out = b;
+	return NTSM_OK;
+}
+
+// fold finished batches into the completed tallies; caller holds c->mu
+static void reap(ntsm_ctx *c, bool block_on_oldest)
+{
+	while (!c->inflight.empty()) {
+		ntsm_batch *b = c->inflight.front();
+		cudaError_t q = cudaEventQuery(b->done);
+		if (q == cudaErrorNotReady) {
+			if (!block_on_oldest) break;
+			cudaEventSynchronize(b->done);
+			block_on_oldest = false;
+		}
+		c->done_kmers = b->h_snap[0];      // d_totals is cumulative and kernels run in submit order
+		c->done_hits = b->h_snap[1];
+		c->done_bases += b->n_bases;
+		b->state = 0;
+		c->inflight.pop_front();
+	}
+}
+
+extern "C" int ntsm_acquire_batch(ntsm_ctx *c, ntsm_batch **out)
+{
+	if (!c || !out) return fail(c, NTSM_ERR_ARG, "ntsm_acquire_batch: null argument");
+	CU(c, cudaSetDevice(c->device));
+	std::unique_lock<std::mutex> g(c->mu);
+	for (;;) {
+		reap(c, false);
+		for (ntsm_batch *b : c->batches)
+			if (b->state == 0) {
+				b->state = 1;
+				b->pk.reset(b->h_bases, b->h_mask);
+				b->n_bases = b->n_reads = 0;
+				*out = b;
+				return NTSM_OK;
+			}
+		if (c->batches.size() < c->cfg.n_buffers) {
+			ntsm_batch *b = nullptr;
+			const int rc = make_batch(c, &b);
+			if (rc) { free_batch(b); return rc; }
+			c->batches.push_back(b);
+			continue;
+		}
+		if (!c->inflight.empty()) reap(c, true);        // wait for the oldest kernel
+		else c->cv.wait(g);                             // every buffer is held by another producer
+	}
+}
+
+extern "C" int ntsm_batch_append(ntsm_batch *b, const char *seq, uint64_t len, uint64_t *pos)
+{
+	if (!b || !pos || (!seq && len) || *pos > len) return fail(b ? b->ctx : nullptr, NTSM_ERR_ARG, "ntsm_batch_append: bad argument");
+	const uint32_t k = b->ctx->cfg.k;
+	// a continued read re-packs its last k-1 consumed bases so the windows that span the cut are seen once
+	const uint64_t from = *pos >= (uint64_t)(k - 1) ? *pos - (k - 1) : 0;
+	const uint64_t start = *pos == 0 ? 0 : from;
+	const uint64_t need = len - start;
+	const uint64_t room = b->cap_pos - b->pk.pos;       // positions left, including the separator
+	if (need + 1 <= room) {
+		b->pk.put_bases(seq + start, need);
+		b->pk.put_separator();
+		b->n_bases += len - *pos;
+		b->n_reads += (*pos == 0);
+		*pos = len;
+		return 1;
+	}
+	const uint64_t split_min = std::max<uint64_t>(2 * k, std::min<uint64_t>(4096, b->cap_pos / 4));
+	if (b->pk.pos != 0 && room < split_min + 1) return 0;   // full: submit and come back
+	const uint64_t take = room - 1;                          // >= 2k > k-1, so the read always advances
+	b->pk.put_bases(seq + start, take);
+	b->pk.put_separator();
+	b->n_bases += start + take - *pos;
+	b->n_reads += (*pos == 0);
+	*pos = start + take;
+	return 0;
+}
+
+extern "C" uint64_t ntsm_batch_positions(const ntsm_batch *b) { return b->pk.pos; }
+extern "C" uint64_t ntsm_batch_bases(const ntsm_batch *b) { return b->n_bases; }
+extern "C" uint64_t ntsm_batch_reads(const ntsm_batch *b) { return b->n_reads; }
+
+extern "C" int ntsm_submit_batch(ntsm_ctx *c, ntsm_batch *b)
+{
+	if (!c || !b || b->ctx != c || b->state != 1) return fail(c, NTSM_ERR_ARG, "ntsm_submit_batch: batch not acquired from this ctx");
+	CU(c, cudaSetDevice(c->device));
+	const uint64_t n_pos = b->pk.finish();
+	const uint64_t padded = padded_positions(n_pos);
+	std::lock_guard<std::mutex> g(c->mu);
+	if (n_pos == 0) {
+		b->state = 0;
+		c->cv.notify_one();
+		return NTSM_OK;
+	}
+	CU(c, cudaMemcpyAsync(b->d_bases, b->h_bases, padded / 32 * 8, cudaMemcpyHostToDevice, c->copy_stream));
+	CU(c, cudaMemcpyAsync(b->d_mask, b->h_mask, padded / 32 * 4, cudaMemcpyHostToDevice, c->copy_stream));
+	CU(c, cudaEventRecord(b->copied, c->copy_stream));
+	CU(c, cudaStreamWaitEvent(c->compute_stream, b->copied, 0));
+	const int rc = launch_count(c, b->d_bases, b->d_mask, n_pos, c->compute_stream);
+	if (rc) return rc;
+	CU(c, cudaMemcpyAsync(b->h_snap, c->d_totals, 16, cudaMemcpyDeviceToHost, c->compute_stream));
+	CU(c, cudaEventRecord(b->done, c->compute_stream));
+	b->state = 2;
+	c->submitted_bases += b->n_bases;
+	c->inflight.push_back(b);
+	c->cv.notify_all();
+	return NTSM_OK;
+}
+
+extern "C" int ntsm_release_batch(ntsm_ctx *c, ntsm_batch *b)
+{
+	if (!c || !b || b->ctx != c || b->state != 1) return fail(c, NTSM_ERR_ARG, "ntsm_release_batch: batch not acquired from this ctx");
+	std::lock_guard<std::mutex> g(c->mu);
+	b->state = 0;
+	c->cv.notify_one();
+	return NTSM_OK;
+}
+
+extern "C" int ntsm_insert_count(ntsm_ctx *c, const char *seq, uint64_t len)
+{
+	if (!c) return NTSM_ERR_ARG;
+	uint64_t pos = 0;
+	for (;;) {
+		if (!c->current) {
+			const int rc = ntsm_acquire_batch(c, &c->current);
+			if (rc) return rc;
+		}
+		const int r = ntsm_batch_append(c->current, seq, len, &pos);
+		if (r < 0) return r;
+		if (r == 1) return NTSM_OK;
+		ntsm_batch *b = c->current;
+		c->current = nullptr;
+		const int rc = ntsm_submit_batch(c, b);
+		if (rc) return rc;
+	}
+}
+
+extern "C" int ntsm_flush(ntsm_ctx *c)
+{
+	if (!c) return NTSM_ERR_ARG;
+	if (!c->current) return NTSM_OK;
+	ntsm_batch *b = c->current;
+	c->current = nullptr;
+	return ntsm_submit_batch(c, b);
+}
+
+extern "C" int ntsm_poll_totals(ntsm_ctx *c, uint64_t *total_kmers, uint64_t *total_hits, uint64_t *total_bases,
+                                int *cap_reached)
+{
+	if (!c) return NTSM_ERR_ARG;
+	CU(c, cudaSetDevice(c->device));
+	std::lock_guard<std::mutex> g(c->mu);
+	reap(c, false);
+	if (total_kmers) *total_kmers = c->done_kmers;
+	if (total_hits) *total_hits = c->done_hits;
+	if (total_bases) *total_bases = c->done_bases;
+	if (cap_reached) *cap_reached = c->cfg.max_counts != 0 && c->done_hits > c->cfg.max_counts;   // FingerPrint.hpp:476
+	return NTSM_OK;
+}
+
+extern "C" int ntsm_sync(ntsm_ctx *c)
+{
+	if (!c) return NTSM_ERR_ARG;
+	CU(c, cudaSetDevice(c->device));
+	CU(c, cudaDeviceSynchronize());
+	std::lock_guard<std::mutex> g(c->mu);
+	reap(c, false);
+	c->cv.notify_all();
+	return NTSM_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU
+extern "C" int ntsm_nccl_unique_id(void *id_out)
+{
+	static_assert(sizeof(ncclUniqueId) == NTSM_NCCL_ID_BYTES, "ncclUniqueId size");
+	if (!id_out) return NTSM_ERR_ARG;
+	ncclUniqueId id;
+	NC(nullptr, ncclGetUniqueId(&id));
+	memcpy(id_out, &id, sizeof id);
+	return NTSM_OK;
+}
+
+extern "C" int ntsm_comm_init(ntsm_ctx *c, const void *id, int rank, int n_ranks)
+{
+	if (!c || !id || rank < 0 || rank >= n_ranks) return fail(c, NTSM_ERR_ARG, "ntsm_comm_init: bad argument");
+	CU(c, cudaSetDevice(c->device));
+	ncclUniqueId uid;
+	memcpy(&uid, id, sizeof uid);
+	NC(c, ncclCommInitRank(&c->comm, n_ranks, uid, rank));
+	c->rank = rank;
+	c->n_ranks = n_ranks;
+	return NTSM_OK;
+}
+
+extern "C" int ntsm_allreduce(ntsm_ctx *c)
+{
+	if (!c) return NTSM_ERR_ARG;
+	int rc = ntsm_flush(c);
+	if (rc) return rc;
+	rc = ntsm_sync(c);
+	if (rc) return rc;
+	if (c->reduced) return NTSM_OK;
+	// private base tally joins the two device tallies so ONE u64 all-reduce covers TK/hits/bases
+	const unsigned long long bases = c->submitted_bases;
+	CU(c, cudaMemcpyAsync(c->d_totals + 2, &bases, 8, cudaMemcpyHostToDevice, c->compute_stream));
+	if (c->comm && c->n_ranks > 1) {
+		// sums first, per-site max afterwards: max of sums != sum of maxes
+		NC(c, ncclGroupStart());
+		NC(c, ncclAllReduce(c->d_counts, c->d_counts, c->n_kmers, ncclUint32, ncclSum, c->comm, c->compute_stream));
+		NC(c, ncclAllReduce(c->d_totals, c->d_totals, 3, ncclUint64, ncclSum, c->comm, c->compute_stream));
+		NC(c, ncclGroupEnd());
+	}
+	CU(c, cudaStreamSynchronize(c->compute_stream));
+	c->reduced = true;
+	return NTSM_OK;
+}
+
+// ------------------------------------------------------------------ results
+extern "C" int ntsm_finalize(ntsm_ctx *c, uint32_t *max_ref, uint32_t *max_var, uint32_t *sum_ref, uint32_t *sum_var,
+                             uint64_t totals[3])
+{
+	if (!c) return NTSM_ERR_ARG;
+	if (!c->d_table) return fail(c, NTSM_ERR_ARG, "no site table loaded");
+	int rc = ntsm_allreduce(c);
+	if (rc) return rc;
+	const uint32_t S = c->n_sites;
+	if (S) {
+		uint32_t *r = c->d_rows;
+		site_reduce_kernel<<<(S + 255) / 256, 256, 0, c->compute_stream>>>(c->d_counts, c->d_allele_off, S, r, r + S,
+		                                                                   r + 2 * (size_t)S, r + 3 * (size_t)S);
+		CU(c, cudaGetLastError());
+		c->launches++;
+		uint32_t *dst[4] = { max_ref, max_var, sum_ref, sum_var };
+		for (int i = 0; i < 4; ++i)
+			if (dst[i]) CU(c, cudaMemcpyAsync(dst[i], r + (size_t)i * S, (size_t)S * 4, cudaMemcpyDeviceToHost, c->compute_stream));
+	}
+	unsigned long long t[3] = { 0, 0, 0 };
+	CU(c, cudaMemcpyAsync(t, c->d_totals, sizeof t, cudaMemcpyDeviceToHost, c->compute_stream));
+	CU(c, cudaStreamSynchronize(c->compute_stream));
+	if (totals) { totals[0] = t[0]; totals[1] = t[1]; totals[2] = t[2]; }
+	return NTSM_OK;
+}
+
+extern "C" int ntsm_get_counts(ntsm_ctx *c, uint32_t *counts)
+{
+	if (!c || !counts) return NTSM_ERR_ARG;
+	int rc = ntsm_flush(c);
+	if (rc) return rc;
+	rc = ntsm_sync(c);
+	if (rc) return rc;
+	CU(c, cudaMemcpy(counts, c->d_counts, (size_t)c->n_kmers * 4, cudaMemcpyDeviceToHost));
+	return NTSM_OK;
+}
+
+// library-internal helpers (not part of the public header)
+uint64_t ntsm_ctx_max_counts(const ntsm_ctx *c) { return c->cfg.max_counts; }
+void ntsm_set_thread_error(const char *text) { t_last_error = text; }
+
+extern "C" uint64_t ntsm_ctx_launches(const ntsm_ctx *c) { return c ? c->launches : 0; }
+extern "C" uint32_t ntsm_ctx_filter_bits(const ntsm_ctx *c) { return c ? c->filter_bits : 0; }
+extern "C" uint32_t ntsm_ctx_table_capacity(const ntsm_ctx *c) { return c ? c->table_cap : 0; }

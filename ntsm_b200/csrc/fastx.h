@@ -1,0 +1,57 @@
+// fastx.h -- FASTA/FASTQ(.gz) record reader with the exact record grammar of kseq_read
+// (vendor/kseq.h:178-219) as FingerPrint::computeCounts drives it (src/FingerPrint.hpp:64-67).
+//
+// Same grammar, different machinery: a 1 MiB inflate window scanned with memchr instead of a
+// 16 KiB buffer walked byte by byte.  Behaviour that must match (all covered by tests/golden):
+//   * a record starts at the next '>' or '@' (anywhere, when hunting; at a line start otherwise);
+//   * name = header up to the first isspace(); rest of the header line is ignored;
+//   * sequence = concatenation of the following lines until a line STARTING with '>', '+' or '@';
+//     empty lines are skipped; after each appended line one trailing '\r' is dropped if the
+//     sequence so far is longer than 1 byte; every other byte is kept verbatim;
+//   * '+' starts the quality block: rest of that line skipped, then whole lines are appended
+//     (same '\r' rule) until qual is at least as long as seq; length mismatch -> -2;
+//   * end of input after the '+' line -> -2; a record cut off inside its sequence is returned
+//     as a FASTA-style record;
+//   * return codes: >=0 sequence length, -1 end of file, -2 bad quality, -3 read error.
+#pragma once
+#include <stdint.h>
+#include <zlib.h>
+
+#include <string>
+#include <vector>
+
+namespace ntsm {
+
+class FastxReader {
+public:
+	FastxReader() = default;
+	~FastxReader() { close(); }
+	FastxReader(const FastxReader &) = delete;
+	FastxReader &operator=(const FastxReader &) = delete;
+
+	bool open(const char *path);
+	void close();
+	// next record; sequence available through seq()/name() until the following call
+	int64_t next();
+	const char *seq() const { return seq_.data(); }
+	uint64_t seq_len() const { return seq_.size(); }
+	const char *name() const { return name_.c_str(); }
+
+private:
+	bool fill();                       // refill the window; false at end of input / error
+	int getc();                        // next byte, -1 end, -3 error
+	// append the rest of the current line to dst (without '\n'); returns false if nothing could
+	// be read because the input had already ended
+	bool take_line(std::vector<char> &dst);
+	bool skip_line();
+
+	gzFile f_ = nullptr;
+	std::vector<unsigned char> buf_;
+	size_t beg_ = 0, end_ = 0;
+	bool eof_ = false, err_ = false;
+	int last_ = 0;                     // header byte already consumed by the previous record
+	std::string name_;
+	std::vector<char> seq_, qual_;
+};
+
+}  // namespace ntsm

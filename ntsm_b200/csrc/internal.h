@@ -1,0 +1,8 @@
+// internal.h -- helpers shared between the library's translation units (not exported in the header)
+#pragma once
+#include <stdint.h>
+
+#include "../../include/ntsm_b200.h"
+
+uint64_t ntsm_ctx_max_counts(const ntsm_ctx *c);
+void ntsm_set_thread_error(const char *text);

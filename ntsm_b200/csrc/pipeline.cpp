@@ -1,0 +1,129 @@
+// pipeline.cpp -- FingerPrint::computeCounts (src/FingerPrint.hpp:46-87) as a host ingest pipeline:
+// parser threads (one file each at a time) -> pinned packed batches -> round-robin over the GPUs.
+// This is what the dead ProdConKseqRunner (vendor/ProdConKseqRunner.hpp:30-184) intended: file
+// readers produce bulks, buffers are recycled; the "workers" are now CUDA streams.
+#include <stdio.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/ntsm_b200.h"
+#include "fastx.h"
+#include "internal.h"
+
+namespace {
+
+struct Shared {
+	ntsm_ctx *const *ctxs;
+	uint32_t n_ctx;
+	const char *const *paths;
+	uint32_t n_paths;
+	int verbose;
+	uint64_t max_counts;
+	std::atomic<uint32_t> next_file{0};
+	std::atomic<uint64_t> next_batch{0};
+	std::atomic<bool> early{false};
+	std::atomic<int> error{0};
+	std::mutex err_mu;
+	std::string err_text;
+};
+
+// -m check (FingerPrint.hpp:476-487) at batch granularity: sum the hit tallies of all GPUs over
+// the batches that have completed.
+void check_cap(Shared &sh)
+{
+	if (!sh.max_counts || sh.early.load()) return;
+	uint64_t hits = 0;
+	for (uint32_t i = 0; i < sh.n_ctx; ++i) {
+		uint64_t h = 0;
+		ntsm_poll_totals(sh.ctxs[i], nullptr, &h, nullptr, nullptr);
+		hits += h;
+	}
+	if (hits > sh.max_counts) sh.early.store(true);
+}
+
+void worker(Shared &sh)
+{
+	ntsm::FastxReader rd;
+	ntsm_batch *b = nullptr;
+	ntsm_ctx *bctx = nullptr;
+	auto set_error = [&](int code, const std::string &text) {
+		std::lock_guard<std::mutex> g(sh.err_mu);
+		if (!sh.error.load()) { sh.error.store(code); sh.err_text = text; }
+	};
+	auto submit = [&]() -> bool {
+		if (!b) return true;
+		const int rc = ntsm_submit_batch(bctx, b);
+		b = nullptr;
+		if (rc) { set_error(rc, ntsm_last_error(bctx)); return false; }
+		if (sh.max_counts) {
+			// -m: wait for this batch so the stop decision does not depend on timing
+			// (deterministic for one parser thread, like the reference's -t 1)
+			ntsm_sync(bctx);
+			check_cap(sh);
+		}
+		return true;
+	};
+	for (;;) {
+		const uint32_t fi = sh.next_file.fetch_add(1);
+		if (fi >= sh.n_paths || sh.error.load()) break;
+		if (!rd.open(sh.paths[fi])) {                               // FingerPrint.hpp:51-57
+			set_error(NTSM_ERR_IO, std::string("file ") + sh.paths[fi] + " cannot be opened");
+			break;
+		}
+		if (sh.verbose) fprintf(stderr, "Opening %s\n", sh.paths[fi]);   // :58-62
+		int64_t l;
+		while (!sh.early.load() && !sh.error.load() && (l = rd.next()) >= 0) {   // :67 (any negative code ends the file)
+			uint64_t pos = 0;
+			for (;;) {
+				if (!b) {
+					bctx = sh.ctxs[sh.next_batch.fetch_add(1) % sh.n_ctx];
+					const int rc = ntsm_acquire_batch(bctx, &b);
+					if (rc) { set_error(rc, ntsm_last_error(bctx)); return; }
+				}
+				const int r = ntsm_batch_append(b, rd.seq(), (uint64_t)l, &pos);
+				if (r < 0) { set_error(r, ntsm_last_error(bctx)); return; }
+				if (r == 1) break;
+				if (!submit()) return;
+			}
+		}
+		rd.close();
+	}
+	submit();
+}
+
+}  // namespace
+
+extern "C" int ntsm_count_files(ntsm_ctx *const *ctxs, uint32_t n_ctx, const char *const *paths, uint32_t n_paths,
+                                uint32_t threads, int verbose, int *early)
+{
+	if (!ctxs || !n_ctx || (!paths && n_paths)) return NTSM_ERR_ARG;
+	Shared sh;
+	sh.ctxs = ctxs;
+	sh.n_ctx = n_ctx;
+	sh.paths = paths;
+	sh.n_paths = n_paths;
+	sh.verbose = verbose;
+	sh.max_counts = 0;
+	sh.max_counts = ntsm_ctx_max_counts(ctxs[0]);   // every ctx carries the same cap
+	uint32_t nt = threads ? threads : 1;
+	if (nt > n_paths) nt = n_paths ? n_paths : 1;                   // -t never uses more than #files (:47-48)
+	std::vector<std::thread> pool;
+	for (uint32_t t = 1; t < nt; ++t) pool.emplace_back(worker, std::ref(sh));
+	worker(sh);
+	for (auto &t : pool) t.join();
+	for (uint32_t i = 0; i < n_ctx; ++i) {
+		const int rc = ntsm_sync(ctxs[i]);
+		if (rc && !sh.error.load()) { sh.error.store(rc); sh.err_text = ntsm_last_error(ctxs[i]); }
+	}
+	check_cap(sh);
+	if (early) *early = sh.early.load() ? 1 : 0;
+	if (sh.error.load()) {
+		ntsm_set_thread_error(sh.err_text.c_str());
+		return sh.error.load();
+	}
+	return NTSM_OK;
+}

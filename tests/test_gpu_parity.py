@@ -1,0 +1,247 @@
+"""GPU parity: the CUDA path, called through the C ABI (libntsm_b200.so) and through the
+ntsmCount binary, against (a) the committed stdout/stderr of the real reference binary and
+(b) the CPU oracle on seeded inputs.  Bit-exact: everything on this path is integer work."""
+import json
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, golden_cases
+from test_host import _case_files
+from test_oracle import _filter_err
+
+import ntsm_b200
+
+pytestmark = pytest.mark.gpu
+
+NTSMCOUNT = os.path.join(ROOT, "ntsm_b200", "bin", "ntsmCount")
+PANEL = os.path.join(ROOT, "data", "human_sites_n10.fa.gz")
+COMP = bytes.maketrans(b"ACGTacgt", b"TGCAtgca")
+
+
+def revcomp(b):
+    return b.translate(COMP)[::-1]
+
+
+# ---------------------------------------------------------------- reference fixtures
+@pytest.mark.parametrize("name", golden_cases())
+def test_cli_matches_reference_fixture(name):
+    """Our ntsmCount binary vs what the reference binary printed for the same argv."""
+    d, opts, files = _case_files(name)
+    argv = json.load(open(os.path.join(d, "cmd.json")))["argv"]
+    if opts["m"] > 0:
+        argv = ["--batch-bases", "4096"] + argv      # -m is checked per batch: make batches read-sized
+    p = subprocess.run([NTSMCOUNT] + argv, cwd=d, capture_output=True)
+    ref_rc = int(open(os.path.join(d, "rc.txt")).read())
+    ref_out = open(os.path.join(d, "stdout.txt"), "rb").read()
+    ref_err = open(os.path.join(d, "stderr.txt")).read()
+    if ref_rc != 0:
+        assert p.returncode == 134
+        assert [l for l in _filter_err(p.stderr.decode()) if "collision" in l] == [l for l in _filter_err(ref_err) if "collision" in l]
+        return
+    assert p.returncode == 0, p.stderr.decode()
+    if opts["m"] > 0 and "Reached desired" in ref_err:
+        # early stop is batch-granular here: the prefix property is tested below
+        assert "Reached desired (-m) threshold" in p.stderr.decode()
+        return
+    assert p.stdout == ref_out
+    keep = lambda t: [l for l in t.splitlines() if l.startswith(("Warning", "Reached", "Total ", "Distinct ", "Sites Covered"))]
+    assert keep(p.stderr.decode()) == keep(ref_err)
+
+
+@pytest.mark.parametrize("name", [n for n in golden_cases() if not n.startswith(("dupes_abort", "odd_sites"))])
+def test_abi_files_match_reference_fixture(name):
+    """FingerPrint mirror over the C ABI (computeCounts on the same files)."""
+    d, opts, files = _case_files(name)
+    if opts["m"] > 0 and "Reached desired" in open(os.path.join(d, "stderr.txt")).read():
+        pytest.skip("-m early stop: covered by the prefix-property test")
+    fp = ntsm_b200.FingerPrint(opts["sites"], k=opts["k"], dupes=opts["dupes"], cov_thresh=opts["m"], batch_bases=1 << 14)
+    fp.computeCounts(files, threads=opts["t"])
+    assert fp.counts_text().encode() == open(os.path.join(d, "stdout.txt"), "rb").read()
+    assert fp.printInfoSummary() in open(os.path.join(d, "stderr.txt")).read()
+    fp.close()
+
+
+# ---------------------------------------------------------------- oracle, seeded inputs
+def _windows(sites_path, limit=None):
+    import gzip
+    op = gzip.open if sites_path.endswith(".gz") else open
+    wins = []
+    with op(sites_path, "rt") as fh:
+        for i, line in enumerate(fh):
+            if limit and i >= limit:
+                break
+            if not line.startswith(">"):
+                wins.extend(line.strip().split("N"))
+    return wins
+
+
+def _reads(rng, wins, n, alphabet="ACGT", maxflank=80):
+    out = []
+    for i in range(n):
+        r = "".join(rng.choice(alphabet) for _ in range(rng.randrange(0, maxflank))) + rng.choice(wins) + \
+            "".join(rng.choice(alphabet) for _ in range(rng.randrange(0, maxflank)))
+        if rng.random() < 0.3:
+            p = rng.randrange(len(r)); r = r[:p] + rng.choice("ACGT") + r[p + 1:]
+        r = r.encode()
+        out.append(revcomp(r) if rng.random() < 0.5 else r)
+    return out
+
+
+def _check_against_oracle(oracle, sites, reads, k=19, dupes=False, **kw):
+    fp = ntsm_b200.FingerPrint(sites, k=k, dupes=dupes, **kw)
+    ofp = oracle.fingerprint(sites, k, dupes)
+    for r in reads:
+        fp.insertCount(r)
+        ofp.insert(r)
+    _, _, ocnt = ofp.lists()
+    gcnt = fp.kmer_counts()
+    live = ocnt != 0xFFFFFFFF
+    assert np.array_equal(gcnt[live], ocnt[live])            # every k-mer's counter, not just the per-site rows
+    mr, mv, sr, sv, t = fp.finalize()
+    assert (int(t[0]), int(t[1]), int(t[2])) == (ofp.total_kmers, ofp.total_counts, ofp.total_bases)
+    if fp.sites.printable():
+        assert fp.counts_text() == ofp.counts_text()
+        assert fp.printInfoSummary() == ofp.summary()
+    fp.close()
+    return ofp
+
+
+def test_insert_count_vs_oracle_k19(oracle):
+    sites = os.path.join(GOLDEN, "shared", "sites300.fa")
+    rng = random.Random(42)
+    reads = _reads(rng, _windows(sites), 3000, "ACGTN")
+    ofp = _check_against_oracle(oracle, sites, reads)
+    assert ofp.total_counts > 3000
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 11, 15, 16, 17, 25, 31])
+def test_other_k_vs_oracle(oracle, k):
+    name = "k%d" % k if os.path.isdir(os.path.join(GOLDEN, "cases", "k%d" % k)) else "k11"
+    sites = os.path.join(GOLDEN, "cases", name, "sites.fa")
+    rng = random.Random(k)
+    wins = [w for w in _windows(sites)]
+    reads = _reads(rng, wins, 800, "ACGTN", maxflank=40)
+    _check_against_oracle(oracle, sites, reads, k=k, dupes=True)
+
+
+def test_alphabet_and_edge_reads_vs_oracle(oracle):
+    sites = os.path.join(GOLDEN, "shared", "sites300.fa")
+    w = _windows(sites)
+    reads = [b"", b"A", w[0][:18].encode(), w[0][:19].encode(), w[0].lower().encode(), w[1].replace("T", "U").encode(),
+             w[2].replace("T", "u").encode(), bytes("ACGT".index(c) for c in w[3]), w[4][:10].encode() + b"\xff" + w[4][10:].encode(),
+             b"N" * 100, (w[5] + "N" + w[6] + "R" + w[7]).encode(), b"ACGT" * 5000 + w[8].encode() + b"TTTT" * 5000]
+    _check_against_oracle(oracle, sites, reads)
+
+
+def test_long_reads_split_across_batches(oracle):
+    """Reads far longer than a batch are cut with a k-1 overlap: every k-mer still counted once."""
+    sites = os.path.join(GOLDEN, "shared", "sites300.fa")
+    rng = random.Random(7)
+    wins = _windows(sites)
+    reads = []
+    for _ in range(30):
+        parts = []
+        for _ in range(rng.randrange(5, 60)):
+            parts.append("".join(rng.choice("ACGT") for _ in range(rng.randrange(0, 2500))))
+            parts.append(rng.choice(wins))
+            if rng.random() < 0.2:
+                parts.append("N" * rng.randrange(1, 60))
+        r = "".join(parts).encode()
+        reads.append(revcomp(r) if rng.random() < 0.5 else r)
+    assert max(len(r) for r in reads) > 20000
+    for bb in (4096, 5000, 1 << 14):
+        _check_against_oracle(oracle, sites, reads, batch_bases=bb, n_buffers=2)
+
+
+def test_full_panel_vs_oracle(oracle):
+    """The real 96 287-site panel, reads planted on panel windows (first 20k records) + random ones."""
+    rng = random.Random(2026)
+    wins = _windows(PANEL, limit=20000)
+    reads = _reads(rng, wins, 20000) + [bytes(rng.choice(b"ACGT") for _ in range(150)) for _ in range(5000)]
+    ofp = _check_against_oracle(oracle, PANEL, reads)
+    assert ofp.n_sites == 96287 and ofp.table_size == 1270317
+
+
+# ---------------------------------------------------------------- size-independent properties
+def _device_pack(reads):
+    import torch
+    b2, mk, n_pos, _ = ntsm_b200.pack_reads(reads)
+    return torch.from_numpy(b2.view(np.int32)).cuda(), torch.from_numpy(mk.view(np.int32)).cuda(), n_pos
+
+
+def test_properties_linearity_strand_and_reset(oracle):
+    """counts(A+B) = counts(A) + counts(B); reverse-complementing every read changes nothing;
+    reset gives zeros; the device-resident entry point agrees with the pinned-batch path."""
+    import torch
+    rng = random.Random(5)
+    wins = _windows(PANEL, limit=40000)
+    A = _reads(rng, wins, 30000)
+    B = _reads(rng, wins, 30000)
+    fp = ntsm_b200.FingerPrint(PANEL)
+
+    def run(reads):
+        fp.reset()
+        db, dm, n = _device_pack(reads)
+        fp.count_packed_device(db.data_ptr(), dm.data_ptr(), n, sum(map(len, reads)), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        c = fp.kmer_counts().astype(np.uint64)
+        t = fp.finalize()[4].copy()
+        return c, t
+
+    ca, ta = run(A)
+    cb, tb = run(B)
+    cab, tab = run(A + B)
+    assert np.array_equal(ca + cb, cab) and np.array_equal(ta + tb, tab)
+    crc, trc = run([revcomp(r) for r in A])
+    assert np.array_equal(crc, ca) and np.array_equal(trc, ta)
+    fp.reset()
+    assert fp.kmer_counts().sum() == 0 and fp.finalize()[4].sum() == 0
+    # pinned-batch path == device-resident path
+    fp.reset()
+    for r in A:
+        fp.insertCount(r)
+    assert np.array_equal(fp.kmer_counts().astype(np.uint64), ca)
+    assert np.array_equal(fp.finalize()[4], ta)
+    # and both equal the oracle
+    ofp = oracle.fingerprint(PANEL, 19)
+    buf = np.frombuffer(b"".join(A), np.uint8)
+    off = np.zeros(len(A) + 1, np.uint64); np.cumsum([len(r) for r in A], out=off[1:])
+    ofp.insert_many(buf, off, threads=8)
+    _, _, oc = ofp.lists()
+    assert np.array_equal(oc.astype(np.uint64), ca)
+    assert (ofp.total_kmers, ofp.total_counts, ofp.total_bases) == tuple(int(x) for x in ta)
+    fp.close()
+
+
+def test_m_cap_prefix_property(oracle, tmp_path):
+    """-m: we stop at a batch boundary.  Whatever prefix of the file was consumed, the counts must
+    equal the oracle's counts on exactly that prefix, the cap must have been exceeded by it, and
+    not exceeded one batch earlier."""
+    sites = os.path.join(GOLDEN, "shared", "sites300.fa")
+    rng = random.Random(9)
+    reads = _reads(rng, _windows(sites), 4000)
+    f = tmp_path / "reads.fa"
+    f.write_bytes(b"".join(b">r%d\n%s\n" % (i, r) for i, r in enumerate(reads)))
+    fp = ntsm_b200.FingerPrint(sites, cov_thresh=1.0, batch_bases=8192)
+    fp.computeCounts([str(f)], threads=1)
+    assert fp.early_term
+    mr, mv, sr, sv, t = fp.finalize()
+    ofp = oracle.fingerprint(sites, 19)
+    n = 0
+    prev_hits = 0
+    while ofp.total_bases < int(t[2]):
+        prev_hits = ofp.total_counts
+        ofp.insert(reads[n]); n += 1
+    assert ofp.total_bases == int(t[2]) and n < len(reads)         # a strict prefix of whole reads
+    assert fp.counts_text() == ofp.counts_text()
+    assert ofp.total_counts > fp.max_counts                         # cap exceeded ...
+    assert int(t[2]) - 0 <= (ofp.total_bases)                       # ... by this prefix
+    # the reference (read-granular) would have stopped within the last batch we consumed
+    o2 = oracle.fingerprint(sites, 19, False, 1.0)
+    o2.count_file(str(f))
+    assert o2.total_bases <= int(t[2]) <= o2.total_bases + 2 * 8192
+    fp.close()

@@ -1,0 +1,185 @@
+"""Host-side logic of libntsm_b200.so checked on CPU against the oracle and the reference
+fixtures: ABI surface, hash64 and its inverse, the kseq-grammar reader, the site-table builder
+(FingerPrint::initCountsHash), the 2-bit/N-mask packer and the counts-file formatter.
+No CUDA call is made here."""
+import ctypes as C
+import json
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, golden_cases
+
+import ntsm_b200
+from ntsm_b200 import _lib
+
+
+@pytest.fixture(scope="module")
+def L():
+    return ntsm_b200.lib()
+
+
+def test_library_exports_every_declared_symbol(L):
+    hdr = open(os.path.join(ROOT, "include", "ntsm_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(ntsm_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) > 50
+    for name in sorted(declared):
+        assert hasattr(L, name), "declared in include/ntsm_b200.h but not exported: " + name
+    assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
+
+
+def test_no_cpu_fallback(L):
+    """Without a device the context cannot be created -- the product never counts on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    ctx = C.c_void_p()
+    cfg = _lib.Cfg(k=19, device=0)
+    assert L.ntsm_ctx_create(C.byref(ctx), C.byref(cfg)) == -2
+    assert b"no CUDA device" in L.ntsm_last_error(None)
+
+
+def test_hash64_matches_oracle_and_inverts(L, oracle):
+    rng = random.Random(3)
+    for k in (1, 2, 5, 11, 15, 16, 17, 19, 25, 31):
+        for x in [0, 1, (1 << (2 * k)) - 1] + [rng.getrandbits(2 * k) for _ in range(500)]:
+            h = L.ntsm_hash64(x, k)
+            assert h == oracle.hash64(x, k)
+            assert L.ntsm_hash64_inv(h, k) == x
+
+
+def test_nt4(L, oracle):
+    for b in range(256):
+        assert L.ntsm_nt4(b) == oracle.nt4(b)
+
+
+def _lib_records(L, path):
+    r = C.c_void_p()
+    assert L.ntsm_reader_open(C.byref(r), os.fsencode(path)) == 0
+    out = []
+    s = C.c_char_p()
+    while True:
+        l = L.ntsm_reader_next(r, C.byref(s))
+        if l < 0:
+            break
+        out.append((L.ntsm_reader_name(r), C.string_at(s, l) if l else b""))
+    L.ntsm_reader_close(r)
+    return out, l
+
+
+def _case_files(name):
+    d = os.path.join(GOLDEN, "cases", name)
+    argv = json.load(open(os.path.join(d, "cmd.json")))["argv"]
+    files, i = [], 0
+    opts = {"k": 19, "dupes": False, "m": 0.0, "t": 1, "sites": None}
+    while i < len(argv):
+        a = argv[i]
+        if a == "-d":
+            opts["dupes"] = True
+        elif a in ("-s", "-k", "-m", "-t"):
+            v = argv[i + 1]; i += 1
+            if a == "-s": opts["sites"] = os.path.join(d, v)
+            elif a == "-k": opts["k"] = int(v)
+            elif a == "-m": opts["m"] = float(v)
+            else: opts["t"] = int(v)
+        else:
+            files.append(os.path.join(d, a))
+        i += 1
+    return d, opts, files
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_reader_matches_oracle_reader(L, oracle, name):
+    d, opts, files = _case_files(name)
+    for f in files + [opts["sites"]]:
+        assert _lib_records(L, f) == oracle.read_records(f), f
+
+
+def test_reader_fuzz(L, oracle, tmp_path):
+    from test_oracle import _rand_fastx
+    rng = random.Random(5)
+    wins = ["ACGTTGCATGCATGCAAGCTT", "CCACGTAGCACTGCACCCCCAT"]
+    for i in range(300):
+        f = tmp_path / ("z%d" % i)
+        txt = _rand_fastx(rng, wins)
+        if rng.random() < 0.3:   # records larger than the reader's window boundaries do not matter; long lines do
+            txt += ">big\n" + "ACGT" * rng.randrange(1, 5000) + "\n"
+        f.write_text(txt, newline="")
+        assert _lib_records(L, str(f)) == oracle.read_records(str(f))
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_site_table_matches_oracle(L, oracle, name):
+    d, opts, files = _case_files(name)
+    s = ntsm_b200.SiteSet(opts["sites"], opts["k"], opts["dupes"])
+    fp = oracle.fingerprint(opts["sites"], opts["k"], opts["dupes"], opts["m"])
+    hs, off, cnt = fp.lists()
+    assert s.n_sites == fp.n_sites and s.table_size == fp.table_size
+    assert np.array_equal(s.hashes, hs) and np.array_equal(s.allele_off, off)
+    assert np.array_equal(s.erased.astype(bool), cnt == 0xFFFFFFFF)
+    assert s.names == fp.names()
+    assert s.max_counts(opts["m"]) == fp.max_counts
+    # warnings exactly as the reference printed them
+    want = [l for l in open(os.path.join(d, "stderr.txt")).read().splitlines() if "k-mer collision" in l]
+    assert s.warnings == want
+    ref_rc = int(open(os.path.join(d, "rc.txt")).read())
+    assert s.printable() == (ref_rc == 0)
+
+
+def _py_pack(reads, nt4):
+    """Independent restatement of the packed layout in include/ntsm_b200.h."""
+    codes = []
+    for r in reads:
+        codes.extend(nt4(b) for b in r)
+        codes.append(4)
+    n = len(codes)
+    padded = (n + 8191) // 8192 * 8192 + 64
+    codes += [4] * (padded - n)
+    c = np.array(codes, np.uint64)
+    b2 = ((c & 3) << (2 * (np.arange(padded, dtype=np.uint64) % 16))).reshape(-1, 16).sum(1).astype(np.uint32)
+    mk = ((c >> 2) << (np.arange(padded, dtype=np.uint64) % 32)).reshape(-1, 32).sum(1).astype(np.uint32)
+    return b2, mk, n
+
+
+def test_packer_layout(L, oracle):
+    rng = random.Random(11)
+    alphabet = b"ACGTacgtNnUuRY-\x00\x01\x02\x03\xff "
+    for trial in range(40):
+        reads = [bytes(rng.choice(alphabet) for _ in range(rng.choice([0, 1, 18, 19, 31, 32, 33, 63, 64, 65, 150, 151, 700])))
+                 for _ in range(rng.randrange(1, 30))]
+        b2, mk, n_pos, roff = ntsm_b200.pack_reads(reads)
+        wb, wm, wn = _py_pack(reads, oracle.nt4)
+        assert n_pos == wn == sum(len(r) + 1 for r in reads)
+        assert np.array_equal(b2[:len(wb)], wb) and np.array_equal(mk[:len(wm)], wm)
+        assert list(roff[:-1]) == list(np.cumsum([0] + [len(r) + 1 for r in reads])[:-1])
+
+
+def test_format_counts_matches_reference_fixture(L, oracle):
+    """printOptionalHeader/printCountsMax/printInfoSummary text from oracle rows == reference stdout."""
+    for name in ("mini", "panel300_fq", "dupes_allowed", "k31"):
+        d, opts, files = _case_files(name)
+        fp = oracle.fingerprint(opts["sites"], opts["k"], opts["dupes"], opts["m"])
+        for f in files:
+            fp.count_file(f)
+        mr, mv, sr, sv, _, _ = fp.rows()
+        s = ntsm_b200.SiteSet(opts["sites"], opts["k"], opts["dupes"])
+        n = L.ntsm_format_counts(s._h, mr.ctypes.data, mv.ctypes.data, sr.ctypes.data, sv.ctypes.data, fp.total_kmers, None, 0)
+        buf = C.create_string_buffer(n)
+        L.ntsm_format_counts(s._h, mr.ctypes.data, mv.ctypes.data, sr.ctypes.data, sv.ctypes.data, fp.total_kmers, buf, n)
+        assert buf.raw[:n] == open(os.path.join(d, "stdout.txt"), "rb").read()
+        t = np.array([fp.total_kmers, fp.total_counts, fp.total_bases], np.uint64)
+        cov = L.ntsm_sites_covered(mr.ctypes.data, mv.ctypes.data, s.n_sites)
+        sb = C.create_string_buffer(2048)
+        m = L.ntsm_format_summary(s._h, t.ctypes.data, cov, sb, 2048)
+        assert sb.raw[:m].decode() in open(os.path.join(d, "stderr.txt")).read()
+
+
+def test_format_counts_aborts_like_reference(L):
+    d, opts, files = _case_files("dupes_abort")
+    s = ntsm_b200.SiteSet(opts["sites"], 19, False)
+    z = np.zeros(s.n_sites, np.uint32)
+    assert L.ntsm_format_counts(s._h, z.ctypes.data, z.ctypes.data, z.ctypes.data, z.ctypes.data, 0, None, 0) == -134
