@@ -1,0 +1,370 @@
+#!/usr/bin/env python3
+"""bench.py -- ntsmCount counting hot path on B200: Gbases/s, % of HBM roofline, CPU reference beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): synthetic 30x human short reads -- 150 bp, 1 % substitution
+error, 0.5 % of reads with an N run -- sampled from a 3.1 Gb diploid genome with every window of
+data/human_sites_n10.fa.gz planted once per haplotype; ~100 Gbases per GPU, packed 2-bit + N-mask.
+One step = one whole counting job over the rank's shard: zero counts -> count kernel over the
+packed stream -> (N>1: one NCCL u32 all-reduce of counts + one u64 all-reduce of tallies) ->
+per-site max/sum kernel.  `value` times that with the packed shard resident in HBM (CUDA events,
+max over ranks); `e2e` times the same job fed from pinned HOST memory through
+ntsm_count_packed_host + ntsm_finalize (H2D copies and the D2H of the result rows inside the
+timed region, wall clock between device syncs, max over ranks).
+"""
+import argparse
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PANEL = os.path.join(ROOT, "data", "human_sites_n10.fa.gz")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ntsmCount")
+PORT_BIN = os.path.join(ROOT, "oracle", "_build", "ntsm_oracle")
+READ_LEN = 150
+METRIC = "ntsmCount Gbases/s (synthetic 30x human 150bp reads vs human_sites_n10, k=19)"
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """nvidia-smi-equivalent sampling (NVML) of SM clocks and throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksEventReasonSwPowerCap if hasattr(nv, "nvmlClocksEventReasonSwPowerCap") else 0x4: "sw_power_cap",
+                     0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.02)
+        except Exception as e:  # NVML missing: report that rather than inventing clocks
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------- CPU reference
+def write_fastq_files(codes, n_files, outdir):
+    """codes: uint8 CPU tensor [n, L] -> n_files FASTQ files (numpy-formatted, constant quality)."""
+    import numpy as np
+    c = codes.numpy()
+    n, L = c.shape
+    ascii_tab = np.frombuffer(b"ACGTN", np.uint8)
+    rec = np.empty((n, 2 + 8 + 1 + L + 3 + L + 1), np.uint8)
+    rec[:, 0] = ord("@"); rec[:, 1] = ord("r")
+    idx = np.arange(n, dtype=np.int64)
+    for d in range(8):
+        rec[:, 2 + d] = (idx // 10 ** (7 - d)) % 10 + 48
+    rec[:, 10] = 10
+    rec[:, 11:11 + L] = ascii_tab[c]
+    rec[:, 11 + L] = 10; rec[:, 12 + L] = ord("+"); rec[:, 13 + L] = 10
+    rec[:, 14 + L:14 + 2 * L] = ord("I")
+    rec[:, 14 + 2 * L] = 10
+    paths = []
+    per = (n + n_files - 1) // n_files
+    for i in range(n_files):
+        p = os.path.join(outdir, "sample_%02d.fq" % i)
+        rec[i * per:(i + 1) * per].tofile(p)
+        paths.append(p)
+    return paths
+
+
+def run_reference(paths, threads):
+    """One timed run of the CPU implementation on the sample files -> (seconds, bases, stdout bytes, kind)."""
+    if os.path.exists(REF_BIN):
+        exe, kind = REF_BIN, "reference"
+    else:
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+        exe, kind = PORT_BIN, "port"
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+    t0 = time.perf_counter()
+    p = subprocess.run([exe, "-t", str(threads), "-s", PANEL] + paths, capture_output=True, env=env)
+    dt = time.perf_counter() - t0
+    if p.returncode != 0:
+        raise RuntimeError("reference run failed: " + p.stderr.decode()[-400:])
+    err = p.stderr.decode()
+    m = re.search(r"Total Bases Considered: (\d+)", err)
+    tm = re.search(r"Time: ([0-9.eE+-]+) s", err)
+    secs = float(tm.group(1)) if tm else dt          # the tool's own Time: line, wall as fallback
+    return secs, int(m.group(1)), p.stdout, kind
+
+
+def make_sample(device, n_reads, seed, genome_mb):
+    """Bounded sample of the bench workload: same generator, same genome size (=> same hit density)."""
+    import torch
+    from ntsm_b200 import synth
+    wc, wl = synth.panel_windows(PANEL)
+    g = synth.Genome(genome_mb * 1_000_000, wc, wl, seed, device)
+    codes = synth.sample_reads(g, n_reads, READ_LEN, 0.01, seed + 1)
+    return codes.cpu()
+
+
+def config_dict(args, per_gpu_gbases):
+    return {"workload": "cfg2: synthetic 30x human short reads (150bp, 1% error, 0.5% reads with N run) vs human_sites_n10.fa (96287 sites, 1270317 k-mers), k=19",
+            "per_gpu_gbases": per_gpu_gbases, "genome_mb": args.genome_mb, "read_len": READ_LEN,
+            "l2": "inputs (%.1f GB packed per GPU) far exceed the 126 MB L2; no flush needed" % (per_gpu_gbases * 0.3775),
+            "parallelism": "reads sharded over %d GPU(s), table replicated, one NCCL all-reduce per job" % args.gpus}
+
+
+def reference_arm(args):
+    import torch
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    cores = min(os.cpu_count() or 1, 16)
+    n_reads = env_int("NTSM_BENCH_CPU_READS", 1_000_000)
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    codes = make_sample(dev, n_reads, 7, args.genome_mb)
+    tmp = tempfile.mkdtemp(prefix="ntsm_ref_")
+    try:
+        paths = write_fastq_files(codes, cores, tmp)
+        times, bases, kind = [], 0, "reference"
+        for i in range(args.warmup + args.steps):
+            secs, bases, _, kind = run_reference(paths, cores)
+            if i >= args.warmup:
+                times.append(secs)
+            log("reference step %d: %.2f s" % (i, secs))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    ms = 1000 * sum(times) / len(times)
+    v = bases / (ms / 1000) / 1e9
+    sample = "%d x %dbp reads of the bench workload in %d FASTQ files (-t only parallelises over files)" % (n_reads, READ_LEN, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "Gbases/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic", "config": config_dict(args, args.gbases),
+        "cpu_baseline": {"value": v, "unit": "Gbases/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+# ----------------------------------------------------------------------------- our arm
+def ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import ntsm_b200
+    from ntsm_b200 import synth
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the counting path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- FingerPrint object on this rank's GPU ------------------------------------------
+    t0 = time.time()
+    sites = ntsm_b200.SiteSet(PANEL, 19)
+    fp = ntsm_b200.FingerPrint(sites, device=local, batch_bases=1 << 26, n_buffers=3)
+    stream = torch.cuda.current_stream()
+    fp.set_stream(stream.cuda_stream)
+    if world > 1:
+        box = [ntsm_b200.FingerPrint.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        fp.comm_init(box[0], rank, world)
+    log("rank %d: panel + table ready in %.1f s (filter 2^%d bits)" % (rank, time.time() - t0, fp.filter_bits))
+
+    # ---- this rank's shard, generated on the device ----------------------------------------
+    t0 = time.time()
+    n_reads = int(args.gbases * 1e9 / READ_LEN) // 32 * 32
+    wc, wl = synth.panel_windows(PANEL)
+    genome = synth.Genome(args.genome_mb * 1_000_000, wc, wl, 2, dev)
+    bases, mask, n_pos, n_bases = synth.make_packed_shard(genome, n_reads, READ_LEN, 0.01, seed=1000 + rank)
+    del genome
+    torch.cuda.synchronize()
+    alg_bytes = (3 * n_bases + 7) // 8 + 8 * n_reads          # 2-bit + N-mask per base, one u64 offset per read
+    phys_bytes = bases.numel() * 4 + mask.numel() * 4           # what the kernel actually streams (separator instead of offsets)
+    log("rank %d: %d reads / %.2f Gbases packed into %.2f GB in %.1f s" % (rank, n_reads, n_bases / 1e9, phys_bytes / 1e9, time.time() - t0))
+
+    def job_resident(ev=None):
+        fp.reset_async()
+        if ev:
+            ev[0].record(stream)
+        fp.count_packed_device(bases.data_ptr(), mask.data_ptr(), n_pos, n_bases, stream.cuda_stream)
+        if ev:
+            ev[1].record(stream)
+        fp.reduce_async()
+
+    for _ in range(args.warmup):
+        job_resident()
+    barrier()
+    l0 = fp.launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        job_resident(kev[i])
+    e1.record(stream)
+    barrier()
+    clocks = sampler.result() if rank == 0 else None
+    launches = fp.launches - l0
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    ms_kernel = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    mr, mv, sr, sv, tot = fp.finalize()
+    check = {"TK": int(tot[0]), "hits": int(tot[1]), "bases": int(tot[2]), "sites_covered": int(fp.sites_covered())}
+    value = world * n_bases / (ms_step / 1000) / 1e9
+
+    # ---- e2e: the same job from pinned host memory through the C ABI -----------------------
+    avail = 0
+    for line in open("/proc/meminfo"):
+        if line.startswith("MemAvailable"):
+            avail = int(line.split()[1]) * 1024
+    local_world = env_int("LOCAL_WORLD_SIZE", world)
+    budget = min(phys_bytes, int(avail * 0.4 / max(1, local_world)), env_int("NTSM_BENCH_E2E_GB", 48) << 30)
+    e_reads = min(n_reads, int(budget / (0.375 * (READ_LEN + 1)))) // 32 * 32
+    e_pos, e_bases = e_reads * (READ_LEN + 1), e_reads * READ_LEN
+    e_pad = synth.padded_positions(e_pos)
+    hb = torch.zeros(e_pad // 16, dtype=torch.int32).pin_memory()
+    hm = torch.full((e_pad // 32,), -1, dtype=torch.int32).pin_memory()
+    hb[:e_pos // 16].copy_(bases[:e_pos // 16]); hm[:e_pos // 32].copy_(mask[:e_pos // 32])
+    torch.cuda.synchronize()
+    slice_pos = (1 << 26) // 8192 * 8192
+    n_slices = (e_pos + slice_pos - 1) // slice_pos
+    h2d = (e_pos // 32 + 2 * n_slices) * 12
+    d2h = 4 * 4 * sites.n_sites + 24 + 16 * n_slices
+
+    def job_host():
+        fp.reset_async()
+        fp.count_packed_host(hb.data_ptr(), hm.data_ptr(), e_pos, e_bases)
+        return fp.finalize()
+
+    for _ in range(max(1, args.warmup)):
+        job_host()
+    times = []
+    for _ in range(args.steps):
+        barrier()
+        t = time.perf_counter()
+        rows = job_host()
+        torch.cuda.synchronize()
+        times.append(max_over_ranks(time.perf_counter() - t))
+    e2e_ms = 1000 * sum(times) / len(times)
+    e2e_val = world * e_bases / (e2e_ms / 1000) / 1e9
+    e2e_check = int(rows[4][0])
+
+    # ---- rank 0, single GPU: CPU reference on a bounded sample + byte-for-byte parity on it ----
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = min(os.cpu_count() or 1, 16)
+        n_s = env_int("NTSM_BENCH_CPU_READS", 1_000_000)
+        codes = make_sample(dev, n_s, 7, args.genome_mb)
+        tmp = tempfile.mkdtemp(prefix="ntsm_cpu_")
+        try:
+            paths = write_fastq_files(codes, cores, tmp)
+            secs, cb, ref_stdout, kind = run_reference(paths, cores)
+            fp.set_stream(None)
+            fp.reset()
+            fp.computeCounts(paths, threads=cores)
+            parity = fp.counts_text().encode() == ref_stdout
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        cpu = {"value": cb / secs / 1e9, "unit": "Gbases/s", "cores": cores, "kind": kind,
+               "sample": "%d x %dbp reads of the same generator in %d FASTQ files, ntsmCount -t %d; %.1f s" % (n_s, READ_LEN, cores, cores, secs)}
+
+    if rank == 0:
+        peaks, peak_src = None, "fallback 6650 GB/s (B200_PROFILING.md)"
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            peak = 6650.0
+        achieved = alg_bytes / (ms_kernel / 1000) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except Exception:
+            pass
+        out = {
+            "metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": config_dict(args, n_bases / 1e9),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch_scaled"), "peak_source": peak_src,
+                         "kernel": "count_kernel<19>", "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": alg_bytes,
+                         "packed_bytes_per_launch": phys_bytes,
+                         "note": "HBM fraction as BASELINE asks; the kernel is bound by L1/L2 probe wavefronts, see DESIGN.md"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": "Gbases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "gbases_per_step_per_gpu": e_bases / 1e9,
+                    "api": "ntsm_count_packed_host + ntsm_finalize (pinned host packed stream)"},
+            "gpu_launches": int(launches), "clocks": clocks, "check": dict(check, e2e_TK=e2e_check),
+            "parity_vs_reference_on_cpu_sample": parity,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gbases", type=float, default=float(os.environ.get("NTSM_BENCH_GBASES", 100)), help="Gbases per GPU")
+    ap.add_argument("--genome-mb", type=int, default=int(os.environ.get("NTSM_BENCH_GENOME_MB", 3100)))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

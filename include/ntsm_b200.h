@@ -129,6 +129,11 @@ uint64_t ntsm_pack_reads(const char *buf, const uint64_t *off, uint64_t n_reads,
 int ntsm_count_packed_device(ntsm_ctx *ctx, const uint32_t *d_bases2, const uint32_t *d_nmask,
                              uint64_t n_pos, uint64_t n_bases, void *cuda_stream);
 
+/* Same, for a packed stream in HOST memory (pinned for full PCIe rate): sliced into the ctx's
+ * device buffers, each slice copied with cudaMemcpyAsync and counted while the next one copies. */
+int ntsm_count_packed_host(ntsm_ctx *ctx, const uint32_t *h_bases2, const uint32_t *h_nmask, uint64_t n_pos,
+                           uint64_t n_bases);
+
 /* insertCount drop-in (src/FingerPrint.hpp:89): packs into the ctx's current batch and submits
  * it when full.  Single producer; ntsm_flush submits the partial batch. */
 int ntsm_insert_count(ntsm_ctx *ctx, const char *seq, uint64_t len);
@@ -140,6 +145,9 @@ int ntsm_poll_totals(ntsm_ctx *ctx, uint64_t *total_kmers, uint64_t *total_hits,
                      int *cap_reached);
 int ntsm_sync(ntsm_ctx *ctx);          /* drain every submitted batch */
 int ntsm_reset_counts(ntsm_ctx *ctx);  /* zero counts and tallies, keep the table */
+int ntsm_reset_counts_async(ntsm_ctx *ctx); /* same, enqueued on the compute stream; needs no batch in flight */
+/* run every kernel / all-reduce of this ctx on the caller's cudaStream_t (NULL = the ctx's own) */
+int ntsm_set_stream(ntsm_ctx *ctx, void *cuda_stream);
 
 /* ---------------- multi-GPU: one ctx (process or thread) per GPU ---------------- */
 #define NTSM_NCCL_ID_BYTES 128
@@ -147,6 +155,9 @@ int ntsm_nccl_unique_id(void *id_out);                         /* ncclGetUniqueI
 int ntsm_comm_init(ntsm_ctx *ctx, const void *id, int rank, int n_ranks);
 /* sum counts (u32) and tallies (u64) over all ranks: ONE ncclAllReduce each, before the per-site max */
 int ntsm_allreduce(ntsm_ctx *ctx);
+/* enqueue (no host sync) on the compute stream: the all-reduces above if a communicator is attached,
+ * then the per-site max/sum kernel.  ntsm_finalize calls it if it has not run yet. */
+int ntsm_reduce_async(ntsm_ctx *ctx);
 
 /* ---------------- results: printOptionalHeader + printCountsMax (:261-311) ---------------- */
 /* drains, runs the per-site reduce kernel, copies out.  Arrays have n_sites entries;

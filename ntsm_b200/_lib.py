@@ -54,6 +54,10 @@ _SIGS = {
     "ntsm_release_batch": (C.c_int, [_P, _P]),
     "ntsm_pack_reads": (C.c_uint64, [_P, _P, C.c_uint64, _P, _P, _P]),
     "ntsm_count_packed_device": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, _P]),
+    "ntsm_count_packed_host": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64]),
+    "ntsm_reset_counts_async": (C.c_int, [_P]),
+    "ntsm_set_stream": (C.c_int, [_P, _P]),
+    "ntsm_reduce_async": (C.c_int, [_P]),
     "ntsm_insert_count": (C.c_int, [_P, C.c_char_p, C.c_uint64]),
     "ntsm_flush": (C.c_int, [_P]),
     "ntsm_poll_totals": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),

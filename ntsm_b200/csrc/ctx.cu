@@ -41,7 +41,7 @@ struct ntsm_batch {
 struct ntsm_ctx {
 	ntsm_cfg cfg{};
 	int device = 0;
-	cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+	cudaStream_t copy_stream = nullptr, compute_stream = nullptr, own_compute = nullptr;
 	int sm_count = 148;
 	// site table
 	uint32_t n_kmers = 0, n_sites = 0;
@@ -122,7 +122,8 @@ extern "C" int ntsm_ctx_create(ntsm_ctx **out, const ntsm_cfg *cfg)
 	CU(c, cudaSetDevice(c->device));
 	CU(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
 	CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-	CU(c, cudaStreamCreateWithFlags(&c->compute_stream, cudaStreamNonBlocking));
+	CU(c, cudaStreamCreateWithFlags(&c->own_compute, cudaStreamNonBlocking));
+	c->compute_stream = c->own_compute;
 	CU(c, cudaMalloc(&c->d_totals, 3 * sizeof(unsigned long long)));
 	CU(c, cudaMemset(c->d_totals, 0, 3 * sizeof(unsigned long long)));
 	*out = c;
@@ -156,7 +157,7 @@ extern "C" void ntsm_ctx_destroy(ntsm_ctx *c)
 	cudaFree(c->d_rows);
 	cudaFree(c->d_totals);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-	if (c->compute_stream) cudaStreamDestroy(c->compute_stream);
+	if (c->own_compute) cudaStreamDestroy(c->own_compute);
 	delete c;
 }
 
@@ -231,19 +232,41 @@ extern "C" int ntsm_load_siteset(ntsm_ctx *c, const ntsm_sites *s)
 	                       ntsm_sites_n_sites(s));
 }
 
-extern "C" int ntsm_reset_counts(ntsm_ctx *c)
+static int reset_tallies(ntsm_ctx *c)
+{
+	std::lock_guard<std::mutex> g(c->mu);
+	if (!c->inflight.empty()) return fail(c, NTSM_ERR_ARG, "reset with batches in flight; ntsm_sync first");
+	if (c->d_counts) CU(c, cudaMemsetAsync(c->d_counts, 0, std::max<size_t>(1, c->n_kmers) * 4, c->compute_stream));
+	CU(c, cudaMemsetAsync(c->d_totals, 0, 3 * sizeof(unsigned long long), c->compute_stream));
+	c->done_kmers = c->done_hits = c->done_bases = c->submitted_bases = 0;
+	c->reduced = false;
+	return NTSM_OK;
+}
+
+extern "C" int ntsm_reset_counts_async(ntsm_ctx *c)
 {
 	if (!c) return NTSM_ERR_ARG;
 	CU(c, cudaSetDevice(c->device));
-	CU(c, cudaDeviceSynchronize());
-	std::lock_guard<std::mutex> g(c->mu);
-	for (ntsm_batch *b : c->inflight) b->state = 0;
-	c->inflight.clear();
-	if (c->d_counts) CU(c, cudaMemset(c->d_counts, 0, std::max<size_t>(1, c->n_kmers) * 4));
-	CU(c, cudaMemset(c->d_totals, 0, 3 * sizeof(unsigned long long)));
-	c->done_kmers = c->done_hits = c->done_bases = c->submitted_bases = 0;
-	c->reduced = false;
-	c->cv.notify_all();
+	return reset_tallies(c);
+}
+
+extern "C" int ntsm_reset_counts(ntsm_ctx *c)
+{
+	if (!c) return NTSM_ERR_ARG;
+	int rc = ntsm_sync(c);
+	if (rc) return rc;
+	rc = reset_tallies(c);
+	if (rc) return rc;
+	CU(c, cudaStreamSynchronize(c->compute_stream));
+	return NTSM_OK;
+}
+
+extern "C" int ntsm_set_stream(ntsm_ctx *c, void *cuda_stream)
+{
+	if (!c) return NTSM_ERR_ARG;
+	int rc = ntsm_sync(c);
+	if (rc) return rc;
+	c->compute_stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_compute;
 	return NTSM_OK;
 }
 
@@ -383,20 +406,19 @@ extern "C" uint64_t ntsm_batch_positions(const ntsm_batch *b) { return b->pk.pos
 extern "C" uint64_t ntsm_batch_bases(const ntsm_batch *b) { return b->n_bases; }
 extern "C" uint64_t ntsm_batch_reads(const ntsm_batch *b) { return b->n_reads; }
 
-extern "C" int ntsm_submit_batch(ntsm_ctx *c, ntsm_batch *b)
+// enqueue H2D of a packed stream (src_* = host memory holding at least padded/halo words) into the
+// batch's device buffers, the count kernel and the tally snapshot; caller holds no lock
+static int enqueue_batch(ntsm_ctx *c, ntsm_batch *b, const void *src_bases, const void *src_mask, uint64_t n_pos,
+                         uint64_t copy_pos, uint64_t n_bases)
 {
-	if (!c || !b || b->ctx != c || b->state != 1) return fail(c, NTSM_ERR_ARG, "ntsm_submit_batch: batch not acquired from this ctx");
-	CU(c, cudaSetDevice(c->device));
-	const uint64_t n_pos = b->pk.finish();
-	const uint64_t padded = padded_positions(n_pos);
 	std::lock_guard<std::mutex> g(c->mu);
 	if (n_pos == 0) {
 		b->state = 0;
-		c->cv.notify_one();
+		c->cv.notify_all();
 		return NTSM_OK;
 	}
-	CU(c, cudaMemcpyAsync(b->d_bases, b->h_bases, padded / 32 * 8, cudaMemcpyHostToDevice, c->copy_stream));
-	CU(c, cudaMemcpyAsync(b->d_mask, b->h_mask, padded / 32 * 4, cudaMemcpyHostToDevice, c->copy_stream));
+	CU(c, cudaMemcpyAsync(b->d_bases, src_bases, copy_pos / 32 * 8, cudaMemcpyHostToDevice, c->copy_stream));
+	CU(c, cudaMemcpyAsync(b->d_mask, src_mask, copy_pos / 32 * 4, cudaMemcpyHostToDevice, c->copy_stream));
 	CU(c, cudaEventRecord(b->copied, c->copy_stream));
 	CU(c, cudaStreamWaitEvent(c->compute_stream, b->copied, 0));
 	const int rc = launch_count(c, b->d_bases, b->d_mask, n_pos, c->compute_stream);
@@ -404,9 +426,38 @@ extern "C" int ntsm_submit_batch(ntsm_ctx *c, ntsm_batch *b)
 	CU(c, cudaMemcpyAsync(b->h_snap, c->d_totals, 16, cudaMemcpyDeviceToHost, c->compute_stream));
 	CU(c, cudaEventRecord(b->done, c->compute_stream));
 	b->state = 2;
-	c->submitted_bases += b->n_bases;
+	b->n_bases = n_bases;
+	c->submitted_bases += n_bases;
 	c->inflight.push_back(b);
 	c->cv.notify_all();
+	return NTSM_OK;
+}
+
+extern "C" int ntsm_submit_batch(ntsm_ctx *c, ntsm_batch *b)
+{
+	if (!c || !b || b->ctx != c || b->state != 1) return fail(c, NTSM_ERR_ARG, "ntsm_submit_batch: batch not acquired from this ctx");
+	CU(c, cudaSetDevice(c->device));
+	const uint64_t n_pos = b->pk.finish();
+	return enqueue_batch(c, b, b->h_bases, b->h_mask, n_pos, padded_positions(n_pos), b->n_bases);
+}
+
+extern "C" int ntsm_count_packed_host(ntsm_ctx *c, const uint32_t *h_bases2, const uint32_t *h_nmask, uint64_t n_pos,
+                                      uint64_t n_bases)
+{
+	if (!c || !h_bases2 || !h_nmask) return fail(c, NTSM_ERR_ARG, "ntsm_count_packed_host: null argument");
+	CU(c, cudaSetDevice(c->device));
+	const uint64_t cap = c->cfg.batch_bases / kTilePositions * kTilePositions;   // slice length, a multiple of 32
+	if (cap == 0) return fail(c, NTSM_ERR_ARG, "batch_bases too small");
+	for (uint64_t off = 0; off < n_pos; off += cap) {
+		const uint64_t len = std::min(cap, n_pos - off);
+		ntsm_batch *b = nullptr;
+		int rc = ntsm_acquire_batch(c, &b);
+		if (rc) return rc;
+		// a slice needs the 64 positions after it (windows that start inside and end outside)
+		const uint64_t copy_pos = (len + 31) / 32 * 32 + kHaloPositions;
+		rc = enqueue_batch(c, b, h_bases2 + off / 16, h_nmask + off / 32, len, copy_pos, off == 0 ? n_bases : 0);
+		if (rc) return rc;
+	}
 	return NTSM_OK;
 }
 
@@ -495,17 +546,20 @@ extern "C" int ntsm_comm_init(ntsm_ctx *c, const void *id, int rank, int n_ranks
 	return NTSM_OK;
 }
 
-extern "C" int ntsm_allreduce(ntsm_ctx *c)
+__global__ void set_u64_kernel(unsigned long long *p, unsigned long long v) { *p = v; }
+
+// enqueue on the compute stream: base tally -> device, the two all-reduces (if a communicator is
+// attached), the per-site reduce.  No host synchronisation.
+extern "C" int ntsm_reduce_async(ntsm_ctx *c)
 {
 	if (!c) return NTSM_ERR_ARG;
-	int rc = ntsm_flush(c);
-	if (rc) return rc;
-	rc = ntsm_sync(c);
-	if (rc) return rc;
+	if (!c->d_table) return fail(c, NTSM_ERR_ARG, "no site table loaded");
 	if (c->reduced) return NTSM_OK;
-	// private base tally joins the two device tallies so ONE u64 all-reduce covers TK/hits/bases
-	const unsigned long long bases = c->submitted_bases;
-	CU(c, cudaMemcpyAsync(c->d_totals + 2, &bases, 8, cudaMemcpyHostToDevice, c->compute_stream));
+	CU(c, cudaSetDevice(c->device));
+	// the private base tally joins the two device tallies so ONE u64 all-reduce covers TK/hits/bases
+	set_u64_kernel<<<1, 1, 0, c->compute_stream>>>(c->d_totals + 2, (unsigned long long)c->submitted_bases);
+	CU(c, cudaGetLastError());
+	c->launches++;
 	if (c->comm && c->n_ranks > 1) {
 		// sums first, per-site max afterwards: max of sums != sum of maxes
 		NC(c, ncclGroupStart());
@@ -513,8 +567,28 @@ extern "C" int ntsm_allreduce(ntsm_ctx *c)
 		NC(c, ncclAllReduce(c->d_totals, c->d_totals, 3, ncclUint64, ncclSum, c->comm, c->compute_stream));
 		NC(c, ncclGroupEnd());
 	}
-	CU(c, cudaStreamSynchronize(c->compute_stream));
+	const uint32_t S = c->n_sites;
+	if (S) {
+		uint32_t *r = c->d_rows;
+		site_reduce_kernel<<<(S + 255) / 256, 256, 0, c->compute_stream>>>(c->d_counts, c->d_allele_off, S, r, r + S,
+		                                                                   r + 2 * (size_t)S, r + 3 * (size_t)S);
+		CU(c, cudaGetLastError());
+		c->launches++;
+	}
 	c->reduced = true;
+	return NTSM_OK;
+}
+
+extern "C" int ntsm_allreduce(ntsm_ctx *c)
+{
+	if (!c) return NTSM_ERR_ARG;
+	int rc = ntsm_flush(c);
+	if (rc) return rc;
+	rc = ntsm_sync(c);
+	if (rc) return rc;
+	rc = ntsm_reduce_async(c);
+	if (rc) return rc;
+	CU(c, cudaStreamSynchronize(c->compute_stream));
 	return NTSM_OK;
 }
 
@@ -523,20 +597,19 @@ extern "C" int ntsm_finalize(ntsm_ctx *c, uint32_t *max_ref, uint32_t *max_var, 
                              uint64_t totals[3])
 {
 	if (!c) return NTSM_ERR_ARG;
-	if (!c->d_table) return fail(c, NTSM_ERR_ARG, "no site table loaded");
-	int rc = ntsm_allreduce(c);
+	int rc = ntsm_flush(c);
+	if (rc) return rc;
+	{   // drain the batch ring without a device-wide sync (other streams may be busy)
+		std::unique_lock<std::mutex> g(c->mu);
+		while (!c->inflight.empty()) reap(c, true);
+		c->cv.notify_all();
+	}
+	rc = ntsm_reduce_async(c);
 	if (rc) return rc;
 	const uint32_t S = c->n_sites;
-	if (S) {
-		uint32_t *r = c->d_rows;
-		site_reduce_kernel<<<(S + 255) / 256, 256, 0, c->compute_stream>>>(c->d_counts, c->d_allele_off, S, r, r + S,
-		                                                                   r + 2 * (size_t)S, r + 3 * (size_t)S);
-		CU(c, cudaGetLastError());
-		c->launches++;
-		uint32_t *dst[4] = { max_ref, max_var, sum_ref, sum_var };
-		for (int i = 0; i < 4; ++i)
-			if (dst[i]) CU(c, cudaMemcpyAsync(dst[i], r + (size_t)i * S, (size_t)S * 4, cudaMemcpyDeviceToHost, c->compute_stream));
-	}
+	uint32_t *dst[4] = { max_ref, max_var, sum_ref, sum_var };
+	for (int i = 0; i < 4 && S; ++i)
+		if (dst[i]) CU(c, cudaMemcpyAsync(dst[i], c->d_rows + (size_t)i * S, (size_t)S * 4, cudaMemcpyDeviceToHost, c->compute_stream));
 	unsigned long long t[3] = { 0, 0, 0 };
 	CU(c, cudaMemcpyAsync(t, c->d_totals, sizeof t, cudaMemcpyDeviceToHost, c->compute_stream));
 	CU(c, cudaStreamSynchronize(c->compute_stream));

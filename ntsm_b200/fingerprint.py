@@ -129,6 +129,20 @@ class FingerPrint:
         """Count a packed stream already resident in device memory (see ntsm_count_packed_device)."""
         check(_lib.lib().ntsm_count_packed_device(self._ctx, d_bases_ptr, d_mask_ptr, n_pos, n_bases, stream), self._ctx)
 
+    def count_packed_host(self, h_bases_ptr, h_mask_ptr, n_pos, n_bases):
+        """Count a packed stream in (pinned) host memory: H2D slices overlap the kernel (ntsm_count_packed_host)."""
+        check(_lib.lib().ntsm_count_packed_host(self._ctx, h_bases_ptr, h_mask_ptr, n_pos, n_bases), self._ctx)
+
+    def set_stream(self, stream):
+        check(_lib.lib().ntsm_set_stream(self._ctx, stream), self._ctx)
+
+    def reset_async(self):
+        check(_lib.lib().ntsm_reset_counts_async(self._ctx), self._ctx)
+        self._rows = None
+
+    def reduce_async(self):
+        check(_lib.lib().ntsm_reduce_async(self._ctx), self._ctx)
+
     def flush(self):
         check(_lib.lib().ntsm_flush(self._ctx), self._ctx)
 
