@@ -206,7 +206,10 @@ def ours(args):
     t0 = time.time()
     sites = ntsm_b200.SiteSet(PANEL, 19)
     fp = ntsm_b200.FingerPrint(sites, device=local, batch_bases=1 << 26, n_buffers=3)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) torch stream: the ABI reads a NULL handle as "use the ctx's own stream",
+    # and torch.cuda.Event only sees the stream it is recorded on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     fp.set_stream(stream.cuda_stream)
     if world > 1:
         box = [ntsm_b200.FingerPrint.nccl_unique_id() if rank == 0 else None]

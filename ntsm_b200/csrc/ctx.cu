@@ -46,6 +46,8 @@ struct ntsm_ctx {
 	// site table
 	uint32_t n_kmers = 0, n_sites = 0;
 	uint32_t *d_filter = nullptr;
+	uint32_t *d_minimizer = nullptr;        // level-1 bitmap (k = 19 only)
+	int kernel_variant = 1;                 // 0 = plain, 1 = minimizer-gated where available
 	uint32_t filter_bits = 0;
 	TableSlot *d_table = nullptr;
 	uint32_t table_cap = 0;
@@ -151,6 +153,7 @@ extern "C" void ntsm_ctx_destroy(ntsm_ctx *c)
 	if (c->comm) ncclCommDestroy(c->comm);
 	for (ntsm_batch *b : c->batches) free_batch(b);
 	cudaFree(c->d_filter);
+	cudaFree(c->d_minimizer);
 	cudaFree(c->d_table);
 	cudaFree(c->d_counts);
 	cudaFree(c->d_allele_off);
@@ -184,6 +187,9 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 	if (const char *e = getenv("NTSM_FILTER_BITS")) fbits = (uint32_t)std::min(32, std::max(10, atoi(e)));
 	std::vector<uint32_t> filter((1ull << fbits) / 32, 0u);
 	const uint32_t fshift = 32 - fbits;
+	// level-1 bitmap over M-mers: the minimizer of every spelling of every live k-mer (k = 19 kernel)
+	const bool use_min = (k == 19);
+	std::vector<uint32_t> minim(use_min ? (1ull << (2 * kMinimizerM)) / 32 : 0, 0u);
 
 	for (uint32_t i = 0; i < n_kmers; ++i) {
 		if (erased && erased[i]) continue;
@@ -204,17 +210,26 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 		for (uint64_t s : ss) {
 			const uint32_t ix = filter_mix((uint32_t)s, (uint32_t)(s >> 32)) >> fshift;
 			filter[ix >> 5] |= 1u << (ix & 31);
+			if (use_min) {
+				const uint32_t mm = minimizer_of(s, (int)k, kMinimizerM);
+				minim[mm >> 5] |= 1u << (mm & 31);
+			}
 		}
 	}
 
-	cudaFree(c->d_filter); cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_allele_off); cudaFree(c->d_rows);
-	c->d_filter = nullptr; c->d_table = nullptr; c->d_counts = nullptr; c->d_allele_off = nullptr; c->d_rows = nullptr;
+	cudaFree(c->d_filter); cudaFree(c->d_minimizer); cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_allele_off); cudaFree(c->d_rows);
+	c->d_minimizer = nullptr; c->d_filter = nullptr; c->d_table = nullptr; c->d_counts = nullptr; c->d_allele_off = nullptr; c->d_rows = nullptr;
 	CU(c, cudaMalloc(&c->d_filter, filter.size() * 4));
 	CU(c, cudaMalloc(&c->d_table, cap * sizeof(TableSlot)));
 	CU(c, cudaMalloc(&c->d_counts, std::max<size_t>(1, n_kmers) * 4));
 	CU(c, cudaMalloc(&c->d_allele_off, (2 * (size_t)n_sites + 1) * 4));
 	CU(c, cudaMalloc(&c->d_rows, std::max<size_t>(1, n_sites) * 16));
 	CU(c, cudaMemcpy(c->d_filter, filter.data(), filter.size() * 4, cudaMemcpyHostToDevice));
+	if (use_min) {
+		CU(c, cudaMalloc(&c->d_minimizer, minim.size() * 4));
+		CU(c, cudaMemcpy(c->d_minimizer, minim.data(), minim.size() * 4, cudaMemcpyHostToDevice));
+	}
+	if (const char *e = getenv("NTSM_KERNEL")) c->kernel_variant = atoi(e);
 	CU(c, cudaMemcpy(c->d_table, table.data(), cap * sizeof(TableSlot), cudaMemcpyHostToDevice));
 	CU(c, cudaMemcpy(c->d_allele_off, allele_off, (2 * (size_t)n_sites + 1) * 4, cudaMemcpyHostToDevice));
 	c->n_kmers = n_kmers;
@@ -280,6 +295,7 @@ static int launch_count(ntsm_ctx *c, const uint2 *d_bases, const uint32_t *d_mas
 	P.bases = d_bases;
 	P.nmask = d_mask;
 	P.n_chunks = (n_pos + 31) / 32;
+	P.minimizer = c->d_minimizer;
 	P.filter = c->d_filter;
 	P.filter_shift = 32 - c->filter_bits;
 	P.table = c->d_table;
@@ -289,7 +305,8 @@ static int launch_count(ntsm_ctx *c, const uint2 *d_bases, const uint32_t *d_mas
 	P.totals = c->d_totals;
 	const uint64_t tiles = (P.n_chunks + kCountThreads - 1) / kCountThreads;
 	const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)c->sm_count * 16);
-	if (c->cfg.k == 19) count_kernel<19><<<grid, kCountThreads, 0, st>>>(P);
+	if (c->cfg.k == 19 && c->kernel_variant == 1) count_kernel_min<19, kMinimizerM><<<grid, kCountThreads, 0, st>>>(P);
+	else if (c->cfg.k == 19) count_kernel<19><<<grid, kCountThreads, 0, st>>>(P);
 	else count_kernel<0><<<grid, kCountThreads, 0, st>>>(P);
 	CU(c, cudaGetLastError());
 	c->launches++;
@@ -546,7 +563,9 @@ extern "C" int ntsm_comm_init(ntsm_ctx *c, const void *id, int rank, int n_ranks
 	return NTSM_OK;
 }
 
+namespace ntsm {
 __global__ void set_u64_kernel(unsigned long long *p, unsigned long long v) { *p = v; }
+}  // namespace ntsm
 
 // enqueue on the compute stream: base tally -> device, the two all-reduces (if a communicator is
 // attached), the per-site reduce.  No host synchronisation.

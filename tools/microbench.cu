@@ -129,7 +129,10 @@ int main(int argc, char **argv)
 			CK(cudaMemcpy(d_b, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice));
 			CK(cudaMemcpy(d_m, hm.data(), hm.size() * 4, cudaMemcpyHostToDevice));
 		}
-		for (const char *fb : {"22", "24", "26", "27", "28", "29", "30"}) {
+		for (const char *cfgs : {"0:24", "0:27", "0:28", "1:24", "1:27", "1:28"}) {
+			char kv[2] = { cfgs[0], 0 };
+			const char *fb = cfgs + 2;
+			setenv("NTSM_KERNEL", kv, 1);
 			setenv("NTSM_FILTER_BITS", fb, 1);
 			ntsm_ctx *ctx; ntsm_cfg cfg; memset(&cfg, 0, sizeof cfg); cfg.k = 19;
 			if (ntsm_ctx_create(&ctx, &cfg)) { printf("ctx: %s\n", ntsm_last_error(NULL)); return 1; }
@@ -145,7 +148,7 @@ int main(int argc, char **argv)
 			}
 			uint64_t tot[3];
 			ntsm_finalize(ctx, NULL, NULL, NULL, NULL, tot);
-			printf("count kernel filter 2^%s bits: %8.3f ms per 2^30 positions = %7.1f Gpos/s  (TK=%llu hits=%llu)\n", fb, best,
+			printf("count kernel variant %s filter 2^%s bits: %8.3f ms per 2^30 positions = %7.1f Gpos/s  (TK=%llu hits=%llu)\n", kv, fb, best,
 			       (double)n_pos / best / 1e6, (unsigned long long)tot[0], (unsigned long long)tot[1]);
 			ntsm_ctx_destroy(ctx);
 		}
