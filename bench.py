@@ -212,9 +212,8 @@ def ours(args):
     torch.cuda.set_stream(stream)
     fp.set_stream(stream.cuda_stream)
     if world > 1:
-        box = [ntsm_b200.FingerPrint.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        fp.comm_init(box[0], rank, world)
+        from ntsm_b200 import dist as ndist
+        ndist.attach_comm(fp)          # rank 0's ncclUniqueId travels over torch.distributed; the all-reduce is the library's
     log("rank %d: panel + table ready in %.1f s (filter 2^%d bits)" % (rank, time.time() - t0, fp.filter_bits))
 
     # ---- this rank's shard, generated on the device ----------------------------------------
@@ -335,8 +334,9 @@ def ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic", "config": config_dict(args, n_bases / 1e9),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (traffic or {}).get("dram_bytes_per_launch_scaled"), "peak_source": peak_src,
-                         "kernel": "count_kernel<19>", "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": alg_bytes,
+                         "traffic": (traffic["dram_bytes_per_base"] * n_bases) if traffic else None,
+                         "traffic_source": (traffic or {}).get("source"), "peak_source": peak_src,
+                         "kernel": "count_kernel_gate<19>", "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": alg_bytes,
                          "packed_bytes_per_launch": phys_bytes,
                          "note": "HBM fraction as BASELINE asks; the kernel is bound by L1/L2 probe wavefronts, see DESIGN.md"},
             "cpu_baseline": cpu,

@@ -46,8 +46,11 @@ struct ntsm_ctx {
 	// site table
 	uint32_t n_kmers = 0, n_sites = 0;
 	uint32_t *d_filter = nullptr;
-	uint32_t *d_minimizer = nullptr;        // level-1 bitmap (k = 19 only)
-	int kernel_variant = 1;                 // 0 = plain, 1 = minimizer-gated where available
+	uint32_t *d_minimizer = nullptr;        // level-1 bitmap of count_kernel_min (k = 19 only)
+	uint32_t *d_minimizer2 = nullptr;       // level-1 bitmap of count_kernel_gate (hashed order)
+	uint32_t *d_level0 = nullptr;           // image of its shared-memory level-0 bitmap
+	uint32_t *d_filter2 = nullptr;          // two-bits-per-word k-mer bitmap of count_kernel_gate
+	int kernel_variant = 2;                 // k = 19: 0 plain, 1 minimizer, 2 smem-gated minimizer (default)
 	uint32_t filter_bits = 0;
 	TableSlot *d_table = nullptr;
 	uint32_t table_cap = 0;
@@ -153,7 +156,10 @@ extern "C" void ntsm_ctx_destroy(ntsm_ctx *c)
 	if (c->comm) ncclCommDestroy(c->comm);
 	for (ntsm_batch *b : c->batches) free_batch(b);
 	cudaFree(c->d_filter);
+	cudaFree(c->d_filter2);
 	cudaFree(c->d_minimizer);
+	cudaFree(c->d_minimizer2);
+	cudaFree(c->d_level0);
 	cudaFree(c->d_table);
 	cudaFree(c->d_counts);
 	cudaFree(c->d_allele_off);
@@ -190,6 +196,9 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 	// level-1 bitmap over M-mers: the minimizer of every spelling of every live k-mer (k = 19 kernel)
 	const bool use_min = (k == 19);
 	std::vector<uint32_t> minim(use_min ? (1ull << (2 * kMinimizerM)) / 32 : 0, 0u);
+	std::vector<uint32_t> minim2(use_min ? (1ull << (2 * kGateM)) / 32 : 0, 0u);
+	std::vector<uint32_t> level0(use_min ? kL0Words : 0, 0u);
+	std::vector<uint32_t> filter2(use_min ? filter.size() : 0, 0u);
 
 	for (uint32_t i = 0; i < n_kmers; ++i) {
 		if (erased && erased[i]) continue;
@@ -213,12 +222,20 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 			if (use_min) {
 				const uint32_t mm = minimizer_of(s, (int)k, kMinimizerM);
 				minim[mm >> 5] |= 1u << (mm & 31);
+				const uint32_t id = gate_minimizer_id(s, (int)k);
+				uint32_t l0w, l1w, gbit;
+				gate_slots(id, l0w, l1w, gbit);
+				minim2[l1w] |= 1u << gbit;
+				level0[l0w] |= 1u << gbit;
+				uint32_t fw2, fm2;
+				filter2_slots(filter_mix((uint32_t)s, (uint32_t)(s >> 32)), fshift, fw2, fm2);
+				filter2[fw2] |= fm2;
 			}
 		}
 	}
 
-	cudaFree(c->d_filter); cudaFree(c->d_minimizer); cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_allele_off); cudaFree(c->d_rows);
-	c->d_minimizer = nullptr; c->d_filter = nullptr; c->d_table = nullptr; c->d_counts = nullptr; c->d_allele_off = nullptr; c->d_rows = nullptr;
+	cudaFree(c->d_filter); cudaFree(c->d_filter2); cudaFree(c->d_minimizer); cudaFree(c->d_minimizer2); cudaFree(c->d_level0); cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_allele_off); cudaFree(c->d_rows);
+	c->d_minimizer = nullptr; c->d_minimizer2 = nullptr; c->d_level0 = nullptr; c->d_filter2 = nullptr; c->d_filter = nullptr; c->d_table = nullptr; c->d_counts = nullptr; c->d_allele_off = nullptr; c->d_rows = nullptr;
 	CU(c, cudaMalloc(&c->d_filter, filter.size() * 4));
 	CU(c, cudaMalloc(&c->d_table, cap * sizeof(TableSlot)));
 	CU(c, cudaMalloc(&c->d_counts, std::max<size_t>(1, n_kmers) * 4));
@@ -228,6 +245,13 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 	if (use_min) {
 		CU(c, cudaMalloc(&c->d_minimizer, minim.size() * 4));
 		CU(c, cudaMemcpy(c->d_minimizer, minim.data(), minim.size() * 4, cudaMemcpyHostToDevice));
+		CU(c, cudaMalloc(&c->d_minimizer2, minim2.size() * 4));
+		CU(c, cudaMemcpy(c->d_minimizer2, minim2.data(), minim2.size() * 4, cudaMemcpyHostToDevice));
+		CU(c, cudaMalloc(&c->d_level0, level0.size() * 4));
+		CU(c, cudaMemcpy(c->d_level0, level0.data(), level0.size() * 4, cudaMemcpyHostToDevice));
+		CU(c, cudaMalloc(&c->d_filter2, filter2.size() * 4));
+		CU(c, cudaMemcpy(c->d_filter2, filter2.data(), filter2.size() * 4, cudaMemcpyHostToDevice));
+		CU(c, cudaFuncSetAttribute(count_kernel_gate<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
 	}
 	if (const char *e = getenv("NTSM_KERNEL")) c->kernel_variant = atoi(e);
 	CU(c, cudaMemcpy(c->d_table, table.data(), cap * sizeof(TableSlot), cudaMemcpyHostToDevice));
@@ -296,16 +320,23 @@ static int launch_count(ntsm_ctx *c, const uint2 *d_bases, const uint32_t *d_mas
 	P.nmask = d_mask;
 	P.n_chunks = (n_pos + 31) / 32;
 	P.minimizer = c->d_minimizer;
+	P.minimizer2 = c->d_minimizer2;
+	P.level0 = c->d_level0;
 	P.filter = c->d_filter;
 	P.filter_shift = 32 - c->filter_bits;
 	P.table = c->d_table;
 	P.table_mask = c->table_cap - 1;
 	P.k = c->cfg.k;
+	P.four = 4;
 	P.counts = c->d_counts;
 	P.totals = c->d_totals;
 	const uint64_t tiles = (P.n_chunks + kCountThreads - 1) / kCountThreads;
 	const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)c->sm_count * 16);
-	if (c->cfg.k == 19 && c->kernel_variant == 1) count_kernel_min<19, kMinimizerM><<<grid, kCountThreads, 0, st>>>(P);
+	if (c->cfg.k == 19 && c->kernel_variant == 2) {
+		P.filter = c->d_filter2;
+		const unsigned g2 = (unsigned)std::min<uint64_t>((P.n_chunks + kGateThreads - 1) / kGateThreads, (uint64_t)c->sm_count);
+		count_kernel_gate<19><<<g2, kGateThreads, kL0Words * 4, st>>>(P);
+	} else if (c->cfg.k == 19 && c->kernel_variant == 1) count_kernel_min<19, kMinimizerM><<<grid, kCountThreads, 0, st>>>(P);
 	else if (c->cfg.k == 19) count_kernel<19><<<grid, kCountThreads, 0, st>>>(P);
 	else count_kernel<0><<<grid, kCountThreads, 0, st>>>(P);
 	CU(c, cudaGetLastError());

@@ -129,7 +129,7 @@ int main(int argc, char **argv)
 			CK(cudaMemcpy(d_b, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice));
 			CK(cudaMemcpy(d_m, hm.data(), hm.size() * 4, cudaMemcpyHostToDevice));
 		}
-		for (const char *cfgs : {"0:24", "0:27", "0:28", "1:24", "1:27", "1:28"}) {
+		for (const char *cfgs : {"0:27", "1:27", "2:27", "2:28"}) {
 			char kv[2] = { cfgs[0], 0 };
 			const char *fb = cfgs + 2;
 			setenv("NTSM_KERNEL", kv, 1);
