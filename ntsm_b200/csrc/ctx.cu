@@ -577,6 +577,7 @@ extern "C" int ntsm_nccl_unique_id(void *id_out)
 	static_assert(sizeof(ncclUniqueId) == NTSM_NCCL_ID_BYTES, "ncclUniqueId size");
 	if (!id_out) return NTSM_ERR_ARG;
 	ncclUniqueId id;
+	setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
 	NC(nullptr, ncclGetUniqueId(&id));
 	memcpy(id_out, &id, sizeof id);
 	return NTSM_OK;
@@ -588,6 +589,8 @@ extern "C" int ntsm_comm_init(ntsm_ctx *c, const void *id, int rank, int n_ranks
 	CU(c, cudaSetDevice(c->device));
 	ncclUniqueId uid;
 	memcpy(&uid, id, sizeof uid);
+	// stdout is the counts file: NCCL's version/debug banner (NCCL_DEBUG=VERSION on some hosts) goes to stderr
+	setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
 	NC(c, ncclCommInitRank(&c->comm, n_ranks, uid, rank));
 	c->rank = rank;
 	c->n_ranks = n_ranks;
