@@ -245,3 +245,75 @@ def test_m_cap_prefix_property(oracle, tmp_path):
     o2.count_file(str(f))
     assert o2.total_bases <= int(t[2]) <= o2.total_bases + 2 * 8192
     fp.close()
+
+
+# ---------------------------------------------------------------- BASELINE configs 3 and 5, scaled
+def _synthetic_panel(path, n_sites, seed):
+    """cfg5-style panel: random 31-mers, centre base A/T vs C/G, all 13 k-mers per allele joined by N;
+    sites whose k-mers collide with earlier ones are rejected (the reference aborts on duplicates)."""
+    rng = np.random.default_rng(seed)
+    seen = set()
+    out = []
+    wins = []
+    n = 0
+    comp = str.maketrans("ACGT", "TGCA")
+    while n < n_sites:
+        w = "".join("ACGT"[c] for c in rng.integers(0, 4, 31))
+        at, cg = ("A" if rng.random() < 0.5 else "T"), ("C" if rng.random() < 0.5 else "G")
+        alleles = [w[:15] + at + w[16:], w[:15] + cg + w[16:]]
+        kms = [[a[j:j + 19] for j in range(13)] for a in alleles]
+        canon = {min(k, k.translate(comp)[::-1]) for ks in kms for k in ks}
+        if len(canon) != 26 or canon & seen:
+            continue
+        seen |= canon
+        out.append(">s%d ref\n%s\n>s%d var\n%s\n" % (n, "N".join(kms[0]), n, "N".join(kms[1])))
+        wins.extend(alleles)
+        n += 1
+    with open(path, "w") as fh:
+        fh.write("".join(out))
+    return wins
+
+
+def test_cfg5_large_synthetic_panel_vs_oracle(oracle, tmp_path):
+    """A 60 000-site synthetic panel (1.56 M k-mers, more than the human panel) built the cfg5 way."""
+    sites = str(tmp_path / "sites.fa")
+    wins = _synthetic_panel(sites, 60000, 5)
+    rng = random.Random(55)
+    reads = []
+    for _ in range(30000):
+        r = "".join(rng.choice("ACGT") for _ in range(rng.randrange(0, 60))) + rng.choice(wins) + \
+            "".join(rng.choice("ACGT") for _ in range(rng.randrange(0, 60)))
+        if rng.random() < 0.3:
+            p = rng.randrange(len(r)); r = r[:p] + rng.choice("ACGTN") + r[p + 1:]
+        reads.append(revcomp(r.encode()) if rng.random() < 0.5 else r.encode())
+    ofp = _check_against_oracle(oracle, sites, reads)
+    assert ofp.table_size == 60000 * 26 and ofp.total_counts > 300000
+
+
+def test_cfg3_ont_like_long_reads_vs_oracle(oracle):
+    """ONT-like: log-normal lengths (N50 ~ 20 kb), 5-10 % errors split sub/ins/del, N runs."""
+    rng = np.random.default_rng(3)
+    prng = random.Random(3)
+    wins = _windows(PANEL, limit=4000)
+    reads = []
+    for _ in range(150):
+        L = int(np.clip(rng.lognormal(9.6, 0.8), 200, 200000))
+        s = []
+        while sum(map(len, s)) < L:
+            s.append("".join("ACGT"[c] for c in rng.integers(0, 4, int(rng.integers(20, 800)))))
+            s.append(prng.choice(wins))
+        seq = np.frombuffer("".join(s)[:L].encode(), np.uint8).copy()
+        err = rng.uniform(0.05, 0.10)
+        u = rng.random(len(seq))
+        sub = u < err / 3
+        seq[sub] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(sub.sum()))]
+        keep = ~((u >= 2 * err / 3) & (u < err))                 # deletions
+        ins = (u >= err / 3) & (u < 2 * err / 3)                # insertion after the base
+        pieces = np.stack([seq, np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, len(seq))]], 1)
+        mask = np.stack([keep, ins & keep], 1)
+        r = pieces[mask].tobytes().decode()
+        if rng.random() < 0.1:
+            p = int(rng.integers(0, len(r))); r = r[:p] + "N" * int(rng.geometric(1 / 50)) + r[p:]
+        reads.append(revcomp(r.encode()) if rng.random() < 0.5 else r.encode())
+    assert max(map(len, reads)) > 50000
+    _check_against_oracle(oracle, PANEL, reads, batch_bases=1 << 16)
