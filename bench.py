@@ -10,9 +10,12 @@ data/human_sites_n10.fa.gz planted once per haplotype; ~100 Gbases per GPU, pack
 One step = one whole counting job over the rank's shard: zero counts -> count kernel over the
 packed stream -> (N>1: one NCCL u32 all-reduce of counts + one u64 all-reduce of tallies) ->
 per-site max/sum kernel.  `value` times that with the packed shard resident in HBM (CUDA events,
-max over ranks); `e2e` times the same job fed from pinned HOST memory through
-ntsm_count_packed_host + ntsm_finalize (H2D copies and the D2H of the result rows inside the
-timed region, wall clock between device syncs, max over ranks).
+max over ranks).  `e2e` times the same job through the call a user of the reference makes --
+insertCount over ASCII reads in HOST memory (ntsm_insert_reads_fixed: decode + 2-bit/N-mask pack
+on the host cores into pinned batches, H2D, count) + ntsm_finalize (all-reduce, per-site reduce,
+D2H of the rows) -- wall clock between device syncs, max over ranks.  `e2e_packed` is the same
+job from an already packed pinned host stream (PCIe-bound), `e2e_files` the whole
+FingerPrint::computeCounts path from FASTQ files (parse + pack + count), for context.
 """
 import argparse
 import json
@@ -211,8 +214,8 @@ def ours(args):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     fp.set_stream(stream.cuda_stream)
+    from ntsm_b200 import dist as ndist
     if world > 1:
-        from ntsm_b200 import dist as ndist
         ndist.attach_comm(fp)          # rank 0's ncclUniqueId travels over torch.distributed; the all-reduce is the library's
     log("rank %d: panel + table ready in %.1f s (filter 2^%d bits)" % (rank, time.time() - t0, fp.filter_bits))
 
@@ -259,13 +262,61 @@ def ours(args):
     check = {"TK": int(tot[0]), "hits": int(tot[1]), "bases": int(tot[2]), "sites_covered": int(fp.sites_covered())}
     value = world * n_bases / (ms_step / 1000) / 1e9
 
-    # ---- e2e: the same job from pinned host memory through the C ABI -----------------------
+    # ---- e2e legs ---------------------------------------------------------------------------
     avail = 0
     for line in open("/proc/meminfo"):
         if line.startswith("MemAvailable"):
             avail = int(line.split()[1]) * 1024
     local_world = env_int("LOCAL_WORLD_SIZE", world)
-    budget = min(phys_bytes, int(avail * 0.4 / max(1, local_world)), env_int("NTSM_BENCH_E2E_GB", 48) << 30)
+    host_threads = max(1, env_int("NTSM_BENCH_THREADS", (os.cpu_count() or 1) // max(1, local_world)))
+
+    def timed_host_job(job):
+        for _ in range(max(1, args.warmup)):
+            job()
+        times, rows = [], None
+        for _ in range(args.steps):
+            barrier()
+            t = time.perf_counter()
+            rows = job()
+            torch.cuda.synchronize()
+            times.append(max_over_ranks(time.perf_counter() - t))
+        return 1000 * sum(times) / len(times), rows
+
+    # (a) headline: ASCII reads in host memory -> ntsm_insert_reads_fixed -> ntsm_finalize.
+    #     The sample is the first a_reads reads of this rank's shard (same generator, same seeds).
+    chunk = 1 << 20
+    a_budget = min(int(avail * 0.25 / max(1, local_world)), env_int("NTSM_BENCH_E2E_ASCII_GB", 24) << 30)
+    a_reads = max(chunk, min(n_reads, a_budget // READ_LEN) // chunk * chunk)
+    ascii_lut = torch.tensor(list(b"ACGTN"), dtype=torch.uint8, device=dev)
+    genome = synth.Genome(args.genome_mb * 1_000_000, wc, wl, 2, dev)
+    host_ascii = torch.empty((a_reads, READ_LEN), dtype=torch.uint8)
+    for ci in range(a_reads // chunk):
+        codes = synth.sample_reads(genome, chunk, READ_LEN, 0.01, (1000 + rank) * 1000003 + ci)
+        host_ascii[ci * chunk:(ci + 1) * chunk].copy_(ascii_lut[codes.long()])
+    del genome, codes
+    torch.cuda.synchronize()
+    a_bases = a_reads * READ_LEN
+    a_pos = a_reads * (READ_LEN + 1)
+    fp_a = ntsm_b200.FingerPrint(sites, device=local, batch_bases=1 << 24, n_buffers=host_threads + 4)
+    if world > 1:
+        ndist.attach_comm(fp_a)
+
+    def job_ascii():
+        fp_a.reset_async()
+        fp_a.insertReadsFixed(host_ascii.data_ptr(), READ_LEN, READ_LEN, a_reads, threads=host_threads)
+        return fp_a.finalize()
+
+    la = fp_a.launches
+    a_ms, a_rows = timed_host_job(job_ascii)
+    a_launches = (fp_a.launches - la) // (max(1, args.warmup) + args.steps)
+    a_val = world * a_bases / (a_ms / 1000) / 1e9
+    a_h2d = ((a_pos + 31) // 32 + 2 * a_launches) * 12          # packed words + per-batch halo
+    d2h = 4 * 4 * sites.n_sites + 24 + 16 * a_launches
+    log("rank %d: e2e ascii %.2f Gbases in %.1f ms with %d pack threads (%s)" %
+        (rank, a_bases / 1e9, a_ms, host_threads, ntsm_b200.lib().ntsm_pack_isa(None).decode()))
+
+    # (b) the same reads, already packed, in pinned host memory (what PCIe alone allows)
+    budget = min(phys_bytes, int(avail * 0.25 / max(1, local_world)), env_int("NTSM_BENCH_E2E_GB", 48) << 30)
     e_reads = min(n_reads, int(budget / (0.375 * (READ_LEN + 1)))) // 32 * 32
     e_pos, e_bases = e_reads * (READ_LEN + 1), e_reads * READ_LEN
     e_pad = synth.padded_positions(e_pos)
@@ -275,30 +326,33 @@ def ours(args):
     torch.cuda.synchronize()
     slice_pos = (1 << 26) // 8192 * 8192
     n_slices = (e_pos + slice_pos - 1) // slice_pos
-    h2d = (e_pos // 32 + 2 * n_slices) * 12
-    d2h = 4 * 4 * sites.n_sites + 24 + 16 * n_slices
+    p_h2d = (e_pos // 32 + 2 * n_slices) * 12
 
     def job_host():
         fp.reset_async()
         fp.count_packed_host(hb.data_ptr(), hm.data_ptr(), e_pos, e_bases)
         return fp.finalize()
 
-    for _ in range(max(1, args.warmup)):
-        job_host()
-    times = []
-    for _ in range(args.steps):
-        barrier()
-        t = time.perf_counter()
-        rows = job_host()
-        torch.cuda.synchronize()
-        times.append(max_over_ranks(time.perf_counter() - t))
-    e2e_ms = 1000 * sum(times) / len(times)
+    e2e_ms, rows = timed_host_job(job_host)
     e2e_val = world * e_bases / (e2e_ms / 1000) / 1e9
     e2e_check = int(rows[4][0])
+    # cross-check: the ASCII leg and the packed leg agree on their common prefix of reads
+    ascii_check = None
+    if world == 1:
+        c_reads = min(a_reads, e_reads) // 32 * 32
+        fp.reset_async()
+        fp.count_packed_host(hb.data_ptr(), hm.data_ptr(), c_reads * (READ_LEN + 1), c_reads * READ_LEN)
+        want = fp.finalize()
+        fp_a.reset_async()
+        fp_a.insertReadsFixed(host_ascii.data_ptr(), READ_LEN, READ_LEN, c_reads, threads=host_threads)
+        got = fp_a.finalize()
+        ascii_check = all(np.array_equal(x, y) for x, y in zip(want, got))
+    del hb, hm
 
     # ---- rank 0, single GPU: CPU reference on a bounded sample + byte-for-byte parity on it ----
     cpu = None
     parity = None
+    files = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = min(os.cpu_count() or 1, 16)
         n_s = env_int("NTSM_BENCH_CPU_READS", 1_000_000)
@@ -311,6 +365,25 @@ def ours(args):
             fp.reset()
             fp.computeCounts(paths, threads=cores)
             parity = fp.counts_text().encode() == ref_stdout
+            # the whole computeCounts path on a larger sample of the same generator: parse + pack + count
+            n_f = env_int("NTSM_BENCH_FILE_READS", 16_000_000)
+            fpaths = []
+            for part in range(0, n_f, 2_000_000):
+                c2 = make_sample(dev, min(2_000_000, n_f - part), 100 + part, args.genome_mb)
+                sub = os.path.join(tmp, "p%d" % part)
+                os.mkdir(sub)
+                fpaths += write_fastq_files(c2, max(1, host_threads * 2_000_000 // n_f), sub)
+            fbytes = sum(os.path.getsize(p) for p in fpaths)
+            ft = []
+            for _ in range(3):
+                fp.reset()
+                t = time.perf_counter()
+                fp.computeCounts(fpaths, threads=host_threads)
+                frows = fp.finalize()
+                ft.append(time.perf_counter() - t)
+            files = {"value": float(frows[4][2]) / min(ft) / 1e9, "unit": "Gbases/s", "seconds": min(ft), "files": len(fpaths),
+                     "threads": min(host_threads, len(fpaths)), "fastq_bytes": fbytes,
+                     "api": "ntsm_count_files (FingerPrint::computeCounts): plain FASTQ files -> parse -> pack -> H2D -> count -> rows"}
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
         cpu = {"value": cb / secs / 1e9, "unit": "Gbases/s", "cores": cores, "kind": kind,
@@ -340,10 +413,16 @@ def ours(args):
                          "packed_bytes_per_launch": phys_bytes,
                          "note": "HBM fraction as BASELINE asks; the kernel is bound by L1/L2 probe wavefronts, see DESIGN.md"},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_val, "unit": "Gbases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "gbases_per_step_per_gpu": e_bases / 1e9,
-                    "api": "ntsm_count_packed_host + ntsm_finalize (pinned host packed stream)"},
-            "gpu_launches": int(launches), "clocks": clocks, "check": dict(check, e2e_TK=e2e_check),
+            "e2e": {"value": a_val, "unit": "Gbases/s", "h2d_bytes_per_step": a_h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": a_ms, "gbases_per_step_per_gpu": a_bases / 1e9, "host_threads": host_threads,
+                    "pack_isa": ntsm_b200.lib().ntsm_pack_isa(None).decode(), "launches_per_step": int(a_launches),
+                    "api": "ntsm_insert_reads_fixed + ntsm_finalize (ASCII reads in host memory: decode + pack on host cores -> pinned batches -> H2D -> count)"},
+            "e2e_packed": {"value": e2e_val, "unit": "Gbases/s", "h2d_bytes_per_step": p_h2d, "d2h_bytes_per_step": d2h,
+                           "ms_per_step": e2e_ms, "gbases_per_step_per_gpu": e_bases / 1e9,
+                           "api": "ntsm_count_packed_host + ntsm_finalize (pinned host stream already packed)"},
+            "e2e_files": files,
+            "gpu_launches": int(launches), "clocks": clocks,
+            "check": dict(check, e2e_TK=int(a_rows[4][0]), e2e_packed_TK=e2e_check, ascii_equals_packed=ascii_check),
             "parity_vs_reference_on_cpu_sample": parity,
         }
         print(json.dumps(out))

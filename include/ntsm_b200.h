@@ -121,6 +121,9 @@ int ntsm_release_batch(ntsm_ctx *ctx, ntsm_batch *b);
 
 /* standalone packer with the same layout (no ctx): packs n_reads reads buf[off[r]..off[r+1])
  * into caller memory sized for ntsm_padded_positions(sum(len)+n_reads). Returns n_pos. */
+/* which decode+pack implementation the host uses: "avx512vbmi", "avx2" or "scalar" (picked from the
+ * CPU at load time).  force: NULL = just ask; "" = back to automatic; a name = use it if the CPU can. */
+const char *ntsm_pack_isa(const char *force);
 uint64_t ntsm_pack_reads(const char *buf, const uint64_t *off, uint64_t n_reads, uint32_t *bases2,
                          uint32_t *nmask, uint64_t *read_off /*nullable, n_reads+1*/);
 
@@ -138,6 +141,19 @@ int ntsm_count_packed_host(ntsm_ctx *ctx, const uint32_t *h_bases2, const uint32
  * it when full.  Single producer; ntsm_flush submits the partial batch. */
 int ntsm_insert_count(ntsm_ctx *ctx, const char *seq, uint64_t len);
 int ntsm_flush(ntsm_ctx *ctx);
+
+/* insertCount for a whole bulk of reads already in host memory -- what a consumer of the
+ * ProdConKseqRunner bulk queue receives (vendor/ProdConKseqRunner.hpp:34-46: records travel 256
+ * at a time).  Read r is buf[off[r] .. off[r+1]) (ASCII, decoded with the reference table).
+ * `threads` producer threads take contiguous ranges of reads, pack them into pinned batches and
+ * submit batch i to ctxs[i % n_ctx]; returns when every read has been submitted (the GPUs may
+ * still be counting: ntsm_finalize / ntsm_sync drain).  The -m cap is not looked at inside one
+ * call; callers poll ntsm_poll_totals between bulks. */
+int ntsm_insert_reads(ntsm_ctx *const *ctxs, uint32_t n_ctx, const char *buf, const uint64_t *off, uint64_t n_reads,
+                      uint32_t threads);
+/* same for a dense matrix: read r = buf[r*stride .. r*stride + read_len) */
+int ntsm_insert_reads_fixed(ntsm_ctx *const *ctxs, uint32_t n_ctx, const char *buf, uint64_t read_len, uint64_t stride,
+                            uint64_t n_reads, uint32_t threads);
 
 /* m_totalKmers / m_totalCounts / m_totalBases / m_earlyTerm (:458-463) over COMPLETED batches;
  * non-blocking.  cap_reached = hits > max_counts at a batch boundary. */

@@ -52,6 +52,7 @@ _SIGS = {
     "ntsm_batch_reads": (C.c_uint64, [_P]),
     "ntsm_submit_batch": (C.c_int, [_P, _P]),
     "ntsm_release_batch": (C.c_int, [_P, _P]),
+    "ntsm_pack_isa": (C.c_char_p, [C.c_char_p]),
     "ntsm_pack_reads": (C.c_uint64, [_P, _P, C.c_uint64, _P, _P, _P]),
     "ntsm_count_packed_device": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, _P]),
     "ntsm_count_packed_host": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64]),
@@ -60,6 +61,8 @@ _SIGS = {
     "ntsm_reduce_async": (C.c_int, [_P]),
     "ntsm_insert_count": (C.c_int, [_P, C.c_char_p, C.c_uint64]),
     "ntsm_flush": (C.c_int, [_P]),
+    "ntsm_insert_reads": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_uint64, C.c_uint32]),
+    "ntsm_insert_reads_fixed": (C.c_int, [_P, C.c_uint32, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]),
     "ntsm_poll_totals": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "ntsm_sync": (C.c_int, [_P]),
     "ntsm_reset_counts": (C.c_int, [_P]),

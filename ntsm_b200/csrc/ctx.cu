@@ -432,8 +432,7 @@ extern "C" int ntsm_batch_append(ntsm_batch *b, const char *seq, uint64_t len, u
 	const uint64_t need = len - start;
 	const uint64_t room = b->cap_pos - b->pk.pos;       // positions left, including the separator
 	if (need + 1 <= room) {
-		b->pk.put_bases(seq + start, need);
-		b->pk.put_separator();
+		b->pk.put_read(seq + start, need);
 		b->n_bases += len - *pos;
 		b->n_reads += (*pos == 0);
 		*pos = len;
@@ -442,8 +441,7 @@ extern "C" int ntsm_batch_append(ntsm_batch *b, const char *seq, uint64_t len, u
 	const uint64_t split_min = std::max<uint64_t>(2 * k, std::min<uint64_t>(4096, b->cap_pos / 4));
 	if (b->pk.pos != 0 && room < split_min + 1) return 0;   // full: submit and come back
 	const uint64_t take = room - 1;                          // >= 2k > k-1, so the read always advances
-	b->pk.put_bases(seq + start, take);
-	b->pk.put_separator();
+	b->pk.put_read(seq + start, take);
 	b->n_bases += start + take - *pos;
 	b->n_reads += (*pos == 0);
 	*pos = start + take;
@@ -683,6 +681,7 @@ extern "C" int ntsm_get_counts(ntsm_ctx *c, uint32_t *counts)
 
 // library-internal helpers (not part of the public header)
 uint64_t ntsm_ctx_max_counts(const ntsm_ctx *c) { return c->cfg.max_counts; }
+uint64_t ntsm_ctx_batch_bases(const ntsm_ctx *c) { return c->cfg.batch_bases; }
 void ntsm_set_thread_error(const char *text) { t_last_error = text; }
 
 extern "C" uint64_t ntsm_ctx_launches(const ntsm_ctx *c) { return c ? c->launches : 0; }

@@ -5,4 +5,5 @@
 #include "../../include/ntsm_b200.h"
 
 uint64_t ntsm_ctx_max_counts(const ntsm_ctx *c);
+uint64_t ntsm_ctx_batch_bases(const ntsm_ctx *c);
 void ntsm_set_thread_error(const char *text);

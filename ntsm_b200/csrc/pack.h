@@ -17,7 +17,9 @@ inline uint64_t padded_positions(uint64_t n_pos)
 	return (n_pos + kTilePositions - 1) / kTilePositions * kTilePositions + kHaloPositions;
 }
 
-const uint8_t *code_table();                 // byte -> 0..3, or 4 for "not a base" (256 entries)
+const uint8_t *code_table();
+const char *pack_isa();                      // "avx512vbmi" | "avx2" | "scalar": the packer picked at start-up
+void pack_reselect();                        // re-read NTSM_PACK_ISA (tests)                 // byte -> 0..3, or 4 for "not a base" (256 entries)
 
 // Streaming bit packer over caller-owned word arrays.
 struct Packer {
@@ -43,7 +45,24 @@ struct Packer {
 		++pos;
 	}
 
+	// n positions (1..32) at once: b = their 2-bit codes (low 2n bits, rest zero), m = invalid flags
+	inline void put_group(uint64_t b, uint32_t m, unsigned n)
+	{
+		const unsigned sh = (unsigned)pos & 31;
+		bacc |= b << (2 * sh);
+		macc |= m << sh;
+		if (sh + n >= 32) {
+			bases[pos >> 5] = bacc;
+			mask[pos >> 5] = macc;
+			const unsigned used = 32 - sh;               // positions of this group that went into the flushed word
+			bacc = used < 32 ? b >> (2 * used) : 0;
+			macc = used < 32 ? m >> used : 0;
+		}
+		pos += n;
+	}
+
 	void put_bases(const char *s, uint64_t n);          // decode + pack n bytes
+	void put_read(const char *s, uint64_t n);           // n bytes + the separator position
 	inline void put_separator() { put_code(4); }
 
 	// pad with invalid positions up to padded_positions(pos); returns the data length (pos before padding)

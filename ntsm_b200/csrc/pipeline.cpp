@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/ntsm_b200.h"
+#include "batch_writer.h"
 #include "fastx.h"
 #include "internal.h"
 
@@ -48,24 +49,17 @@ void check_cap(Shared &sh)
 void worker(Shared &sh)
 {
 	ntsm::FastxReader rd;
-	ntsm_batch *b = nullptr;
-	ntsm_ctx *bctx = nullptr;
+	ntsm::BatchWriter bw(sh.ctxs, sh.n_ctx, &sh.next_batch);
 	auto set_error = [&](int code, const std::string &text) {
 		std::lock_guard<std::mutex> g(sh.err_mu);
 		if (!sh.error.load()) { sh.error.store(code); sh.err_text = text; }
 	};
-	auto submit = [&]() -> bool {
-		if (!b) return true;
-		const int rc = ntsm_submit_batch(bctx, b);
-		b = nullptr;
-		if (rc) { set_error(rc, ntsm_last_error(bctx)); return false; }
-		if (sh.max_counts) {
-			// -m: wait for this batch so the stop decision does not depend on timing
-			// (deterministic for one parser thread, like the reference's -t 1)
-			ntsm_sync(bctx);
-			check_cap(sh);
-		}
-		return true;
+	// -m: wait for the batch just submitted so the stop decision does not depend on timing
+	// (deterministic for one parser thread, like the reference's -t 1)
+	auto after_submit = [&](ntsm_ctx *went) {
+		if (!sh.max_counts || !went) return;
+		ntsm_sync(went);
+		check_cap(sh);
 	};
 	for (;;) {
 		const uint32_t fi = sh.next_file.fetch_add(1);
@@ -77,22 +71,13 @@ void worker(Shared &sh)
 		if (sh.verbose) fprintf(stderr, "Opening %s\n", sh.paths[fi]);   // :58-62
 		int64_t l;
 		while (!sh.early.load() && !sh.error.load() && (l = rd.next()) >= 0) {   // :67 (any negative code ends the file)
-			uint64_t pos = 0;
-			for (;;) {
-				if (!b) {
-					bctx = sh.ctxs[sh.next_batch.fetch_add(1) % sh.n_ctx];
-					const int rc = ntsm_acquire_batch(bctx, &b);
-					if (rc) { set_error(rc, ntsm_last_error(bctx)); return; }
-				}
-				const int r = ntsm_batch_append(b, rd.seq(), (uint64_t)l, &pos);
-				if (r < 0) { set_error(r, ntsm_last_error(bctx)); return; }
-				if (r == 1) break;
-				if (!submit()) return;
-			}
+			if (!bw.append(rd.seq(), (uint64_t)l, after_submit)) { set_error(bw.error, bw.error_text); return; }
 		}
 		rd.close();
 	}
-	submit();
+	ntsm_ctx *went = nullptr;
+	if (!bw.submit(&went)) { set_error(bw.error, bw.error_text); return; }
+	after_submit(went);
 }
 
 }  // namespace

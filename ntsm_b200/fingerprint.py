@@ -113,6 +113,19 @@ class FingerPrint:
         """FingerPrint::insertCount(seq, len) -- src/FingerPrint.hpp:89."""
         check(_lib.lib().ntsm_insert_count(self._ctx, seq, len(seq)), self._ctx)
 
+    def insertReads(self, buf, off, threads=1):
+        """Bulk insertCount: read r = buf[off[r]:off[r+1]] (ntsm_insert_reads).  buf: bytes / uint8 array, off: uint64 array."""
+        b = np.frombuffer(buf, np.uint8) if isinstance(buf, (bytes, bytearray)) else buf
+        off = np.ascontiguousarray(off, np.uint64)
+        ctxs = (C.c_void_p * 1)(self._ctx)
+        rc = _lib.lib().ntsm_insert_reads(ctxs, 1, b.ctypes.data if len(b) else None, off.ctypes.data, len(off) - 1, threads)
+        check(rc, self._ctx if rc != -1 else None)
+
+    def insertReadsFixed(self, ptr, read_len, stride, n_reads, threads=1):
+        """Bulk insertCount over a dense host matrix of n_reads x read_len ASCII bytes at address `ptr`."""
+        ctxs = (C.c_void_p * 1)(self._ctx)
+        check(_lib.lib().ntsm_insert_reads_fixed(ctxs, 1, ptr, read_len, stride, n_reads, threads), self._ctx)
+
     def computeCounts(self, filenames, threads=1, verbose=0):
         """FingerPrint::computeCounts -- src/FingerPrint.hpp:46; `threads` is opt::threads."""
         L = _lib.lib()

@@ -157,6 +157,39 @@ def test_long_reads_split_across_batches(oracle):
         _check_against_oracle(oracle, sites, reads, batch_bases=bb, n_buffers=2)
 
 
+def test_bulk_insert_reads_vs_oracle(oracle):
+    """ntsm_insert_reads / ntsm_insert_reads_fixed (multi-threaded pack into the pinned ring) ==
+    one insertCount per read == the oracle, for ragged and fixed-length bulks."""
+    sites = os.path.join(GOLDEN, "shared", "sites300.fa")
+    rng = random.Random(99)
+    wins = _windows(sites)
+    reads = _reads(rng, wins, 6000, "ACGTN") + [b"", b"A", b"N" * 40, wins[0].encode() * 300]
+    ofp = oracle.fingerprint(sites, 19, False)
+    for r in reads:
+        ofp.insert(r)
+    buf = np.frombuffer(b"".join(reads), np.uint8)
+    off = np.zeros(len(reads) + 1, np.uint64)
+    np.cumsum([len(r) for r in reads], out=off[1:])
+    for threads, bb in ((1, 1 << 14), (4, 1 << 13), (7, 5000)):
+        fp = ntsm_b200.FingerPrint(sites, batch_bases=bb, n_buffers=threads + 2)
+        fp.insertReads(buf, off, threads=threads)
+        assert fp.counts_text() == ofp.counts_text() and fp.printInfoSummary() == ofp.summary()
+        fp.close()
+    # dense matrix form: fixed-length reads with a row stride
+    L_, stride, n = 151, 160, 4000
+    mat = np.full((n, stride), ord("N"), np.uint8)
+    ofp2 = oracle.fingerprint(sites, 19, False)
+    for i in range(n):
+        w = rng.choice(wins).encode()
+        r = (bytes(rng.choice(b"ACGT") for _ in range(L_)) + w)[-L_:] if i % 3 else bytes(rng.choice(b"ACGTN") for _ in range(L_))
+        mat[i, :L_] = np.frombuffer(r, np.uint8)
+        ofp2.insert(r)
+    fp = ntsm_b200.FingerPrint(sites, batch_bases=1 << 15, n_buffers=5)
+    fp.insertReadsFixed(mat.ctypes.data, L_, stride, n, threads=3)
+    assert fp.counts_text() == ofp2.counts_text() and fp.printInfoSummary() == ofp2.summary()
+    fp.close()
+
+
 def test_full_panel_vs_oracle(oracle):
     """The real 96 287-site panel, reads planted on panel windows (first 20k records) + random ones."""
     rng = random.Random(2026)

@@ -158,6 +158,53 @@ def test_packer_layout(L, oracle):
         assert list(roff[:-1]) == list(np.cumsum([0] + [len(r) + 1 for r in reads])[:-1])
 
 
+def test_packer_isa_variants_agree(L):
+    """scalar, AVX2 and AVX-512 VBMI packers write the same words (whichever this CPU has)."""
+    rng = random.Random(5)
+    alphabet = bytes(range(256))
+    reads = [bytes(rng.choice(alphabet) if rng.random() < 0.2 else rng.choice(b"ACGTacgtNU") for _ in range(rng.choice([0, 1, 31, 32, 33, 63, 64, 65, 127, 128, 129, 150, 1000])))
+             for _ in range(300)]
+    outs = {}
+    try:
+        for isa in (b"scalar", b"avx2", b"avx512"):
+            got = L.ntsm_pack_isa(isa)
+            outs[got] = ntsm_b200.pack_reads(reads)
+    finally:
+        L.ntsm_pack_isa(b"")
+    assert b"scalar" in outs
+    ref = outs[b"scalar"]
+    for name, o in outs.items():
+        assert o[2] == ref[2] and np.array_equal(o[0], ref[0]) and np.array_equal(o[1], ref[1]), name
+
+
+def test_packer_reads_nothing_past_a_page_edge(L):
+    """A read that ends on the last byte before an unmapped page is packed without touching that page."""
+    import mmap
+    libc = C.CDLL(None, use_errno=True)
+    libc.mmap.restype = C.c_void_p
+    libc.mmap.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_long]
+    libc.mprotect.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+    base = libc.mmap(None, 2 * 4096, mmap.PROT_READ | mmap.PROT_WRITE, mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS, -1, 0)
+    assert base not in (None, C.c_void_p(-1).value)
+    assert libc.mprotect(base + 4096, 4096, 0) == 0                 # PROT_NONE
+    try:
+        for isa in (b"scalar", b"avx2", b"avx512"):
+            L.ntsm_pack_isa(isa)
+            for n in (1, 7, 22, 31, 32, 33, 63, 64, 65, 150):
+                read = bytes(b"ACGTN"[i % 5] for i in range(n))
+                C.memmove(base + 4096 - n, read, n)
+                off = np.array([0, n], np.uint64)
+                padded = L.ntsm_padded_positions(n + 1)
+                b2 = np.zeros(padded // 16, np.uint32)
+                mk = np.zeros(padded // 32, np.uint32)
+                assert L.ntsm_pack_reads(base + 4096 - n, off.ctypes.data, 1, b2.ctypes.data, mk.ctypes.data, None) == n + 1
+                wb, wm, _, _ = ntsm_b200.pack_reads([read])
+                assert np.array_equal(b2, wb) and np.array_equal(mk, wm), (isa, n)
+    finally:
+        L.ntsm_pack_isa(b"")
+        libc.munmap(C.c_void_p(base), 2 * 4096)
+
+
 def test_format_counts_matches_reference_fixture(L, oracle):
     """printOptionalHeader/printCountsMax/printInfoSummary text from oracle rows == reference stdout."""
     for name in ("mini", "panel300_fq", "dupes_allowed", "k31"):
