@@ -262,6 +262,16 @@ def ours(args):
     check = {"TK": int(tot[0]), "hits": int(tot[1]), "bases": int(tot[2]), "sites_covered": int(fp.sites_covered())}
     value = world * n_bases / (ms_step / 1000) / 1e9
 
+    if args.kernel_only:       # variant sweeps: device-resident number only, not a bench line for the driver
+        if rank == 0:
+            print(json.dumps({"kernel_only": True, "value": value, "unit": "Gbases/s", "kernel_ms": ms_kernel, "ms_per_step": ms_step,
+                              "n_gpus": world, "gbases_per_gpu": n_bases / 1e9, "check": check,
+                              "env": {k: v for k, v in os.environ.items() if k.startswith("NTSM_")}}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
     # ---- e2e legs ---------------------------------------------------------------------------
     avail = 0
     for line in open("/proc/meminfo"):
@@ -376,10 +386,10 @@ def ours(args):
             fbytes = sum(os.path.getsize(p) for p in fpaths)
             ft = []
             for _ in range(3):
-                fp.reset()
+                fp_a.reset()                       # the context with one pinned buffer per parser thread (+4)
                 t = time.perf_counter()
-                fp.computeCounts(fpaths, threads=host_threads)
-                frows = fp.finalize()
+                fp_a.computeCounts(fpaths, threads=host_threads)
+                frows = fp_a.finalize()
                 ft.append(time.perf_counter() - t)
             files = {"value": float(frows[4][2]) / min(ft) / 1e9, "unit": "Gbases/s", "seconds": min(ft), "files": len(fpaths),
                      "threads": min(host_threads, len(fpaths)), "fastq_bytes": fbytes,
@@ -409,7 +419,7 @@ def ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic["dram_bytes_per_base"] * n_bases) if traffic else None,
                          "traffic_source": (traffic or {}).get("source"), "peak_source": peak_src,
-                         "kernel": "count_kernel_gate<19>", "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel": fp.kernel_name, "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": alg_bytes,
                          "packed_bytes_per_launch": phys_bytes,
                          "note": "HBM fraction as BASELINE asks; the kernel is bound by L1/L2 probe wavefronts, see DESIGN.md"},
             "cpu_baseline": cpu,
@@ -440,6 +450,7 @@ def main():
     ap.add_argument("--gbases", type=float, default=float(os.environ.get("NTSM_BENCH_GBASES", 100)), help="Gbases per GPU")
     ap.add_argument("--genome-mb", type=int, default=int(os.environ.get("NTSM_BENCH_GENOME_MB", 3100)))
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--kernel-only", action="store_true", help="device-resident leg only (kernel variant sweeps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -193,6 +193,7 @@ int64_t ntsm_format_summary(const ntsm_sites *s, const uint64_t totals[3], uint3
 
 /* introspection (bench/tests): kernels launched so far, pre-filter size (log2 bits), table slots */
 uint64_t ntsm_ctx_launches(const ntsm_ctx *ctx);
+const char *ntsm_ctx_kernel_name(const ntsm_ctx *ctx);   /* the count kernel this ctx launches, as a profiler lists it */
 uint32_t ntsm_ctx_filter_bits(const ntsm_ctx *ctx);
 uint32_t ntsm_ctx_table_capacity(const ntsm_ctx *ctx);
 

@@ -75,6 +75,7 @@ _SIGS = {
     "ntsm_format_counts": (C.c_int64, [_P, _P, _P, _P, _P, C.c_uint64, _P, C.c_size_t]),
     "ntsm_format_summary": (C.c_int64, [_P, _P, C.c_uint32, _P, C.c_size_t]),
     "ntsm_ctx_launches": (C.c_uint64, [_P]),
+    "ntsm_ctx_kernel_name": (C.c_char_p, [_P]),
     "ntsm_ctx_filter_bits": (C.c_uint32, [_P]),
     "ntsm_ctx_table_capacity": (C.c_uint32, [_P]),
     "ntsm_reader_open": (C.c_int, [C.POINTER(_P), C.c_char_p]),

@@ -18,6 +18,7 @@
 #include "../../include/ntsm_b200.h"
 #include "internal.h"
 #include "kernels.cuh"
+#include "gate2.cuh"
 #include "pack.h"
 
 using namespace ntsm;
@@ -46,11 +47,10 @@ struct ntsm_ctx {
 	// site table
 	uint32_t n_kmers = 0, n_sites = 0;
 	uint32_t *d_filter = nullptr;
-	uint32_t *d_minimizer = nullptr;        // level-1 bitmap of count_kernel_min (k = 19 only)
-	uint32_t *d_minimizer2 = nullptr;       // level-1 bitmap of count_kernel_gate (hashed order)
-	uint32_t *d_level0 = nullptr;           // image of its shared-memory level-0 bitmap
-	uint32_t *d_filter2 = nullptr;          // two-bits-per-word k-mer bitmap of count_kernel_gate
-	int kernel_variant = 2;                 // k = 19: 0 plain, 1 minimizer, 2 smem-gated minimizer (default)
+	uint32_t *d_level1 = nullptr;           // 4^M-bit minimizer bitmap of the k = 19 kernels (layout per variant)
+	uint32_t *d_level0 = nullptr;           // image of the gated kernels' shared-memory level-0 bitmap
+	int kernel_variant = 3;                 // k = 19: 0 plain, 1 minimizer, 2 smem-gated minimizer, 3 gate2 (default)
+	int gate_m = 14;                        // M-mer length of gate2 (12..14)
 	uint32_t filter_bits = 0;
 	TableSlot *d_table = nullptr;
 	uint32_t table_cap = 0;
@@ -156,9 +156,7 @@ extern "C" void ntsm_ctx_destroy(ntsm_ctx *c)
 	if (c->comm) ncclCommDestroy(c->comm);
 	for (ntsm_batch *b : c->batches) free_batch(b);
 	cudaFree(c->d_filter);
-	cudaFree(c->d_filter2);
-	cudaFree(c->d_minimizer);
-	cudaFree(c->d_minimizer2);
+	cudaFree(c->d_level1);
 	cudaFree(c->d_level0);
 	cudaFree(c->d_table);
 	cudaFree(c->d_counts);
@@ -187,18 +185,24 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 	if (cap > (1ull << 31)) return fail(c, NTSM_ERR_ARG, "too many site k-mers (%llu)", (unsigned long long)live);
 	std::vector<TableSlot> table(cap, TableSlot{ kEmptyKey, 0, 0 });
 
-	// pre-filter bitmap holding both orientations of every live k-mer
+	// which count kernel will run decides which pre-filter structures are built (NTSM_KERNEL / NTSM_GATE_M
+	// are measurement knobs: every variant gives the same counts)
+	int variant = k == 19 ? 3 : 0, gm = 14;
+	if (const char *e = getenv("NTSM_KERNEL")) variant = atoi(e);
+	if (const char *e = getenv("NTSM_GATE_M")) gm = atoi(e);
+	if (k != 19 || variant < 0 || variant > 3) variant = 0;
+	if (gm < 12 || gm > 14) gm = 14;
+
+	// k-mer bitmap holding both orientations of every live k-mer
 	uint32_t fbits = 16;
 	while (fbits < 30 && (1ull << fbits) < 40ull * 2ull * live) ++fbits;
 	if (const char *e = getenv("NTSM_FILTER_BITS")) fbits = (uint32_t)std::min(32, std::max(10, atoi(e)));
-	std::vector<uint32_t> filter((1ull << fbits) / 32, 0u);
 	const uint32_t fshift = 32 - fbits;
-	// level-1 bitmap over M-mers: the minimizer of every spelling of every live k-mer (k = 19 kernel)
-	const bool use_min = (k == 19);
-	std::vector<uint32_t> minim(use_min ? (1ull << (2 * kMinimizerM)) / 32 : 0, 0u);
-	std::vector<uint32_t> minim2(use_min ? (1ull << (2 * kGateM)) / 32 : 0, 0u);
-	std::vector<uint32_t> level0(use_min ? kL0Words : 0, 0u);
-	std::vector<uint32_t> filter2(use_min ? filter.size() : 0, 0u);
+	std::vector<uint32_t> filter((1ull << fbits) / 32, 0u);      // layout depends on the variant
+	// minimizer bitmaps: level 1 = 4^M bits in global memory, level 0 = image of the shared-memory bitmap
+	const int mm_len = variant == 1 ? kMinimizerM : variant == 2 ? kGateM : gm;
+	std::vector<uint32_t> level1(variant ? (1ull << (2 * mm_len)) / 32 : 0, 0u);
+	std::vector<uint32_t> level0(variant >= 2 ? kL0Words : 0, 0u);
 
 	for (uint32_t i = 0; i < n_kmers; ++i) {
 		if (erased && erased[i]) continue;
@@ -217,43 +221,75 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 		const uint64_t s2 = ~canon & m;               // read carries the other strand (kmer_math.h)
 		const uint64_t ss[2] = { s1, s2 };
 		for (uint64_t s : ss) {
-			const uint32_t ix = filter_mix((uint32_t)s, (uint32_t)(s >> 32)) >> fshift;
-			filter[ix >> 5] |= 1u << (ix & 31);
-			if (use_min) {
+			const uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
+			uint32_t l0w = 0, l1w = 0, gbit = 0, fw2, fm2;
+			switch (variant) {
+			case 0: {
+				const uint32_t ix = filter_mix(lo, hi) >> fshift;
+				filter[ix >> 5] |= 1u << (ix & 31);
+				break;
+			}
+			case 1: {
+				const uint32_t ix = filter_mix(lo, hi) >> fshift;
+				filter[ix >> 5] |= 1u << (ix & 31);
 				const uint32_t mm = minimizer_of(s, (int)k, kMinimizerM);
-				minim[mm >> 5] |= 1u << (mm & 31);
-				const uint32_t id = gate_minimizer_id(s, (int)k);
-				uint32_t l0w, l1w, gbit;
-				gate_slots(id, l0w, l1w, gbit);
-				minim2[l1w] |= 1u << gbit;
+				level1[mm >> 5] |= 1u << (mm & 31);
+				break;
+			}
+			case 2:
+				gate_slots(gate_minimizer_id(s, (int)k), l0w, l1w, gbit);
+				level1[l1w] |= 1u << gbit;
 				level0[l0w] |= 1u << gbit;
-				uint32_t fw2, fm2;
-				filter2_slots(filter_mix((uint32_t)s, (uint32_t)(s >> 32)), fshift, fw2, fm2);
-				filter2[fw2] |= fm2;
+				filter2_slots(filter_mix(lo, hi), fshift, fw2, fm2);
+				filter[fw2] |= fm2;
+				break;
+			default:
+				gate2_slots(gate2_minimizer_id(s, (int)k, gm), gm, l0w, l1w, gbit);
+				level1[l1w] |= 1u << gbit;
+				level0[l0w] |= 1u << gbit;
+				{
+					uint32_t ra, rb;
+					gate2_filter_slots(lo, hi, (int)k, fshift, fw2, ra, rb);
+					filter[fw2] |= (1u << ra) | (1u << rb);
+				}
+				break;
 			}
 		}
 	}
 
-	cudaFree(c->d_filter); cudaFree(c->d_filter2); cudaFree(c->d_minimizer); cudaFree(c->d_minimizer2); cudaFree(c->d_level0); cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_allele_off); cudaFree(c->d_rows);
-	c->d_minimizer = nullptr; c->d_minimizer2 = nullptr; c->d_level0 = nullptr; c->d_filter2 = nullptr; c->d_filter = nullptr; c->d_table = nullptr; c->d_counts = nullptr; c->d_allele_off = nullptr; c->d_rows = nullptr;
+	cudaFree(c->d_filter); cudaFree(c->d_level1); cudaFree(c->d_level0); cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_allele_off); cudaFree(c->d_rows);
+	c->d_level1 = nullptr; c->d_level0 = nullptr; c->d_filter = nullptr; c->d_table = nullptr; c->d_counts = nullptr; c->d_allele_off = nullptr; c->d_rows = nullptr;
 	CU(c, cudaMalloc(&c->d_filter, filter.size() * 4));
 	CU(c, cudaMalloc(&c->d_table, cap * sizeof(TableSlot)));
 	CU(c, cudaMalloc(&c->d_counts, std::max<size_t>(1, n_kmers) * 4));
 	CU(c, cudaMalloc(&c->d_allele_off, (2 * (size_t)n_sites + 1) * 4));
 	CU(c, cudaMalloc(&c->d_rows, std::max<size_t>(1, n_sites) * 16));
 	CU(c, cudaMemcpy(c->d_filter, filter.data(), filter.size() * 4, cudaMemcpyHostToDevice));
-	if (use_min) {
-		CU(c, cudaMalloc(&c->d_minimizer, minim.size() * 4));
-		CU(c, cudaMemcpy(c->d_minimizer, minim.data(), minim.size() * 4, cudaMemcpyHostToDevice));
-		CU(c, cudaMalloc(&c->d_minimizer2, minim2.size() * 4));
-		CU(c, cudaMemcpy(c->d_minimizer2, minim2.data(), minim2.size() * 4, cudaMemcpyHostToDevice));
+	if (!level1.empty()) {
+		// gate2 forms probe addresses as {lo32(base) + offset, hi32(base)}: the bitmap must not cross a
+		// 4 GiB line.  cudaMalloc hands out 2 MiB-aligned blocks, so a second try always fits.
+		std::vector<void *> rejected;
+		for (int attempt = 0; attempt < 8; ++attempt) {
+			CU(c, cudaMalloc(&c->d_level1, level1.size() * 4));
+			const uintptr_t a = (uintptr_t)c->d_level1, z = a + level1.size() * 4 - 1;
+			if ((a >> 32) == (z >> 32)) break;
+			rejected.push_back(c->d_level1);
+			c->d_level1 = nullptr;
+		}
+		for (void *r : rejected) cudaFree(r);
+		if (!c->d_level1) return fail(c, NTSM_ERR_CUDA, "could not place the minimizer bitmap inside one 4 GiB window");
+		CU(c, cudaMemcpy(c->d_level1, level1.data(), level1.size() * 4, cudaMemcpyHostToDevice));
+	}
+	if (!level0.empty()) {
 		CU(c, cudaMalloc(&c->d_level0, level0.size() * 4));
 		CU(c, cudaMemcpy(c->d_level0, level0.data(), level0.size() * 4, cudaMemcpyHostToDevice));
-		CU(c, cudaMalloc(&c->d_filter2, filter2.size() * 4));
-		CU(c, cudaMemcpy(c->d_filter2, filter2.data(), filter2.size() * 4, cudaMemcpyHostToDevice));
 		CU(c, cudaFuncSetAttribute(count_kernel_gate<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
+		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
+		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
+		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
 	}
-	if (const char *e = getenv("NTSM_KERNEL")) c->kernel_variant = atoi(e);
+	c->kernel_variant = variant;
+	c->gate_m = gm;
 	CU(c, cudaMemcpy(c->d_table, table.data(), cap * sizeof(TableSlot), cudaMemcpyHostToDevice));
 	CU(c, cudaMemcpy(c->d_allele_off, allele_off, (2 * (size_t)n_sites + 1) * 4, cudaMemcpyHostToDevice));
 	c->n_kmers = n_kmers;
@@ -319,8 +355,8 @@ static int launch_count(ntsm_ctx *c, const uint2 *d_bases, const uint32_t *d_mas
 	P.bases = d_bases;
 	P.nmask = d_mask;
 	P.n_chunks = (n_pos + 31) / 32;
-	P.minimizer = c->d_minimizer;
-	P.minimizer2 = c->d_minimizer2;
+	P.minimizer = c->d_level1;
+	P.minimizer2 = c->d_level1;
 	P.level0 = c->d_level0;
 	P.filter = c->d_filter;
 	P.filter_shift = 32 - c->filter_bits;
@@ -332,11 +368,13 @@ static int launch_count(ntsm_ctx *c, const uint2 *d_bases, const uint32_t *d_mas
 	P.totals = c->d_totals;
 	const uint64_t tiles = (P.n_chunks + kCountThreads - 1) / kCountThreads;
 	const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)c->sm_count * 16);
-	if (c->cfg.k == 19 && c->kernel_variant == 2) {
-		P.filter = c->d_filter2;
-		const unsigned g2 = (unsigned)std::min<uint64_t>((P.n_chunks + kGateThreads - 1) / kGateThreads, (uint64_t)c->sm_count);
-		count_kernel_gate<19><<<g2, kGateThreads, kL0Words * 4, st>>>(P);
-	} else if (c->cfg.k == 19 && c->kernel_variant == 1) count_kernel_min<19, kMinimizerM><<<grid, kCountThreads, 0, st>>>(P);
+	const unsigned g2 = (unsigned)std::min<uint64_t>((P.n_chunks + kGateThreads - 1) / kGateThreads, (uint64_t)c->sm_count);
+	if (c->cfg.k == 19 && c->kernel_variant == 3) {
+		if (c->gate_m == 12) count_kernel_gate2<19, 12><<<g2, kGateThreads, kL0Words * 4, st>>>(P);
+		else if (c->gate_m == 13) count_kernel_gate2<19, 13><<<g2, kGateThreads, kL0Words * 4, st>>>(P);
+		else count_kernel_gate2<19, 14><<<g2, kGateThreads, kL0Words * 4, st>>>(P);
+	} else if (c->cfg.k == 19 && c->kernel_variant == 2) count_kernel_gate<19><<<g2, kGateThreads, kL0Words * 4, st>>>(P);
+	else if (c->cfg.k == 19 && c->kernel_variant == 1) count_kernel_min<19, kMinimizerM><<<grid, kCountThreads, 0, st>>>(P);
 	else if (c->cfg.k == 19) count_kernel<19><<<grid, kCountThreads, 0, st>>>(P);
 	else count_kernel<0><<<grid, kCountThreads, 0, st>>>(P);
 	CU(c, cudaGetLastError());
@@ -685,5 +723,13 @@ uint64_t ntsm_ctx_batch_bases(const ntsm_ctx *c) { return c->cfg.batch_bases; }
 void ntsm_set_thread_error(const char *text) { t_last_error = text; }
 
 extern "C" uint64_t ntsm_ctx_launches(const ntsm_ctx *c) { return c ? c->launches : 0; }
+extern "C" const char *ntsm_ctx_kernel_name(const ntsm_ctx *c)
+{
+	if (!c) return "";
+	if (c->cfg.k != 19 || c->kernel_variant == 0) return c->cfg.k == 19 ? "count_kernel<19>" : "count_kernel<0>";
+	if (c->kernel_variant == 1) return "count_kernel_min<19,13>";
+	if (c->kernel_variant == 2) return "count_kernel_gate<19>";
+	return c->gate_m == 12 ? "count_kernel_gate2<19,12>" : c->gate_m == 13 ? "count_kernel_gate2<19,13>" : "count_kernel_gate2<19,14>";
+}
 extern "C" uint32_t ntsm_ctx_filter_bits(const ntsm_ctx *c) { return c ? c->filter_bits : 0; }
 extern "C" uint32_t ntsm_ctx_table_capacity(const ntsm_ctx *c) { return c ? c->table_cap : 0; }

@@ -17,8 +17,11 @@ bool FastxReader::open(const char *path)
 	gzbuffer(f_, 1u << 18);
 	buf_.resize(kWindow);
 	beg_ = end_ = 0;
-	eof_ = err_ = false;
+	eof_ = err_ = src_err_ = false;
 	last_ = 0;
+	fast_name_ = nullptr;
+	cur_seq_ = "";
+	cur_len_ = 0;
 	return true;
 }
 
@@ -31,7 +34,10 @@ void FastxReader::close()
 bool FastxReader::fill()
 {
 	if (beg_ < end_) return true;
-	if (eof_) return false;
+	if (eof_) {
+		if (src_err_) err_ = true;      // a read error met while topping the window up surfaces once the window is drained
+		return false;
+	}
 	beg_ = 0;
 	const int n = gzread(f_, buf_.data(), (unsigned)buf_.size());
 	if (n <= 0) {
@@ -81,7 +87,80 @@ bool FastxReader::skip_line()
 	}
 }
 
+const char *FastxReader::name()
+{
+	if (fast_name_) {                                      // name = header up to the first white-space byte
+		size_t i = 0;
+		while (i < fast_name_len_ && !(fast_name_[i] == ' ' || (fast_name_[i] >= '\t' && fast_name_[i] <= '\r'))) ++i;
+		name_.assign((const char *)fast_name_, i);
+		fast_name_ = nullptr;
+	}
+	return name_.c_str();
+}
+
+bool FastxReader::next_fast(int64_t *len)
+{
+	if (last_ != 0 || err_) return false;                  // only when the next record starts at the next byte
+	for (int attempt = 0; attempt < 2; ++attempt) {
+		if (beg_ >= end_) {
+			if (!fill()) return false;
+		}
+		const unsigned char *p = buf_.data() + beg_, *e = buf_.data() + end_;
+		if (*p != '@') return false;
+		const unsigned char *nl1, *nl2, *nl3, *nl4;
+		bool complete = false;
+		do {
+			if (!(nl1 = (const unsigned char *)memchr(p + 1, '\n', (size_t)(e - p - 1)))) break;
+			const unsigned char *s0 = nl1 + 1;
+			if (s0 >= e) break;
+			if (*s0 == '\n' || *s0 == '>' || *s0 == '+' || *s0 == '@') return false;
+			if (!(nl2 = (const unsigned char *)memchr(s0, '\n', (size_t)(e - s0)))) break;
+			if (nl2 + 1 >= e) break;
+			if (nl2[1] != '+') return false;                 // multi-line sequence, FASTA, ...
+			if (!(nl3 = (const unsigned char *)memchr(nl2 + 2, '\n', (size_t)(e - nl2 - 2)))) break;
+			const unsigned char *q0 = nl3 + 1;
+			if (!(nl4 = (const unsigned char *)memchr(q0, '\n', (size_t)(e - q0)))) break;
+			complete = true;
+			size_t sl = (size_t)(nl2 - s0), ql = (size_t)(nl4 - q0);
+			if (sl > 1 && s0[sl - 1] == '\r') --sl;          // kseq.h:141, applied per appended line
+			if (ql > 1 && q0[ql - 1] == '\r') --ql;
+			if (ql != sl) return false;                      // short (continues on the next line) or long (-2): general parser
+			cur_seq_ = (const char *)s0;
+			cur_len_ = sl;
+			fast_name_ = p + 1;
+			fast_name_len_ = (size_t)(nl1 - p - 1);
+			beg_ = (size_t)(nl4 - buf_.data()) + 1;
+			*len = (int64_t)sl;
+			return true;
+		} while (0);
+		if (complete || eof_ || attempt) return false;
+		// the record runs past the window: slide the unread tail to the front and top the window up
+		const size_t tail = end_ - beg_;
+		if (tail >= buf_.size() / 2) return false;         // a record longer than half the window is not the common case
+		memmove(buf_.data(), buf_.data() + beg_, tail);
+		beg_ = 0;
+		end_ = tail;
+		const int n = gzread(f_, buf_.data() + tail, (unsigned)(buf_.size() - tail));
+		if (n < 0) { src_err_ = true; eof_ = true; return false; }
+		if ((size_t)n < buf_.size() - tail) eof_ = true;   // gzread only comes back short at the end of the input
+		end_ = tail + (size_t)n;
+		if (n == 0) return false;
+	}
+	return false;
+}
+
 int64_t FastxReader::next()
+{
+	int64_t l;
+	if (next_fast(&l)) return l;
+	fast_name_ = nullptr;
+	l = next_general();
+	cur_seq_ = seq_.data();
+	cur_len_ = seq_.size();
+	return l;
+}
+
+int64_t FastxReader::next_general()
 {
 	int c;
 	if (last_ == 0) {                                     // hunt for the next header byte
@@ -159,6 +238,6 @@ extern "C" int64_t ntsm_reader_next(ntsm_reader *r, const char **seq)
 	return l;
 }
 
-extern "C" const char *ntsm_reader_name(const ntsm_reader *r) { return r->r.name(); }
+extern "C" const char *ntsm_reader_name(const ntsm_reader *r) { return const_cast<ntsm_reader *>(r)->r.name(); }
 
 extern "C" void ntsm_reader_close(ntsm_reader *r) { delete r; }

@@ -33,11 +33,17 @@ public:
 	void close();
 	// next record; sequence available through seq()/name() until the following call
 	int64_t next();
-	const char *seq() const { return seq_.data(); }
-	uint64_t seq_len() const { return seq_.size(); }
-	const char *name() const { return name_.c_str(); }
+	const char *seq() const { return cur_seq_; }
+	uint64_t seq_len() const { return cur_len_; }
+	const char *name();
 
 private:
+	// Fast path for the record shape every sequencer writes -- "@name\nSEQ\n+...\nQUAL\n" with one
+	// sequence line and a quality line of the same length, wholly inside the window: four memchr
+	// calls, nothing copied (seq() points into the window).  Returns false, with no state changed,
+	// for anything else; the byte-exact general parser below then handles the record.
+	bool next_fast(int64_t *len);
+	int64_t next_general();
 	bool fill();                       // refill the window; false at end of input / error
 	int getc();                        // next byte, -1 end, -3 error
 	// append the rest of the current line to dst (without '\n'); returns false if nothing could
@@ -48,10 +54,14 @@ private:
 	gzFile f_ = nullptr;
 	std::vector<unsigned char> buf_;
 	size_t beg_ = 0, end_ = 0;
-	bool eof_ = false, err_ = false;
+	bool eof_ = false, err_ = false, src_err_ = false;
 	int last_ = 0;                     // header byte already consumed by the previous record
 	std::string name_;
 	std::vector<char> seq_, qual_;
+	const char *cur_seq_ = "";         // sequence of the current record: in seq_ or inside the window
+	uint64_t cur_len_ = 0;
+	const unsigned char *fast_name_ = nullptr;   // header text of a fast-path record (name built on demand)
+	size_t fast_name_len_ = 0;
 };
 
 }  // namespace ntsm

@@ -230,5 +230,10 @@ class FingerPrint:
         return _lib.lib().ntsm_ctx_launches(self._ctx)
 
     @property
+    def kernel_name(self):
+        """Name of the count kernel this context launches (as ncu lists it)."""
+        return _lib.lib().ntsm_ctx_kernel_name(self._ctx).decode()
+
+    @property
     def filter_bits(self):
         return _lib.lib().ntsm_ctx_filter_bits(self._ctx)

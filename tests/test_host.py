@@ -112,6 +112,54 @@ def test_reader_fuzz(L, oracle, tmp_path):
         assert _lib_records(L, str(f)) == oracle.read_records(str(f))
 
 
+def test_reader_fast_path_across_window_refills(L, oracle, tmp_path):
+    """Several MiB of mostly regular 4-line FASTQ (the zero-copy fast path) with irregular records
+    mixed in (CRLF, multi-line, FASTA, short/long quality, '@' quality lines), in plain and gz
+    form: records that straddle the 1 MiB window and every hand-over between the fast path and the
+    general parser give the oracle's records."""
+    import gzip
+    rng = random.Random(17)
+    parts = []
+    for i in range(9000):
+        n = rng.choice([1, 2, 19, 75, 150, 151, 250, 1000])
+        seq = "".join(rng.choice("ACGTN") for _ in range(n))
+        x = rng.random()
+        if x < 0.90:
+            q = "".join(rng.choice("@+>I#5") for _ in range(n))
+            parts.append("@r%d some comment\n%s\n+\n%s\n" % (i, seq, q))
+        elif x < 0.92:
+            parts.append("@r%d\r\n%s\r\n+\r\n%s\r\n" % (i, seq, "I" * n))
+        elif x < 0.94:
+            h = n // 2
+            parts.append("@r%d\n%s\n%s\n+r%d\n%s\n%s\n" % (i, seq[:h], seq[h:], i, "I" * h, "I" * (n - h)))
+        elif x < 0.96:
+            parts.append(">f%d\n%s\n" % (i, seq))
+        elif x < 0.97:
+            parts.append("@r%d\n%s\n+\n%s\n" % (i, seq, "I" * (n + 3)))      # long quality: -2, file ends there
+        elif x < 0.98:
+            parts.append("@r%d\n\n%s\n+\n%s\n" % (i, seq, "I" * n))         # empty line before the sequence
+        else:
+            parts.append("\n\n@r%d\t x\n%s\n+\n%s\n\n" % (i, seq, "I" * n))
+    for cut in (len(parts), 4000):
+        txt = "".join(p for p in parts[:cut] if cut == len(parts) or "III" not in p[-6:] or len(p) < 40)
+        plain = tmp_path / ("w%d.fq" % cut)
+        plain.write_text(txt, newline="")
+        gz = tmp_path / ("w%d.fq.gz" % cut)
+        with gzip.open(gz, "wb") as fh:
+            fh.write(txt.encode())
+        want = oracle.read_records(str(plain))
+        assert len(want[0]) > 100
+        assert _lib_records(L, str(plain)) == want
+        assert _lib_records(L, str(gz)) == want
+    # a clean multi-MiB file never leaves the fast path; its last record has no trailing newline
+    clean = "".join("@c%d\n%s\n+\n%s\n" % (i, "ACGTTGCA" * 19, "I" * 152) for i in range(12000))[:-1]
+    f = tmp_path / "clean.fq"
+    f.write_text(clean, newline="")
+    want = oracle.read_records(str(f))
+    assert len(want[0]) == 12000
+    assert _lib_records(L, str(f)) == want
+
+
 @pytest.mark.parametrize("name", golden_cases())
 def test_site_table_matches_oracle(L, oracle, name):
     d, opts, files = _case_files(name)
