@@ -92,6 +92,41 @@ __device__ __forceinline__ void gate2_step(uint32_t cur, uint32_t prev, uint32_t
 	      "r"(1u << (32 - SH - 5)), "r"(four), "r"(base_hi));
 }
 
+// exact path for one candidate k-mer (stream order, lo = bases 0-15, hi = the rest): canonical value,
+// the reference's hash64, open-addressing probe, atomicAdd.  Returns 1 on a table hit.
+template <int K>
+__device__ __forceinline__ uint32_t resolve_one(const CountParams &P, uint32_t lo, uint32_t hi)
+{
+	const uint64_t kmask = kmer_mask(K);
+	const uint64_t s = (((uint64_t)hi << 32) | lo) & kmask;
+	const uint64_t fw = stream_to_fw(s, K), rv = stream_to_rv(s, kmask);
+	const uint64_t h = hash64(fw < rv ? fw : rv, kmask);         // KseqHashIterator.hpp:102
+	uint32_t slot = (uint32_t)(h ^ (h >> 29)) & P.table_mask;
+	for (;;) {
+		const TableSlot e = P.table[slot];
+		if (e.key == h) {
+			atomicAdd(P.counts + e.idx, 1u);                     // FingerPrint.hpp:93-94
+			return 1;
+		}
+		if (e.key == kEmptyKey) return 0;
+		slot = (slot + 1) & P.table_mask;
+	}
+}
+
+constexpr int kCandSlots = 32;      // candidates one warp hands round per pass of its tail
+
+// Work layout.  Every warp owns a CONTIGUOUS run of 32-chunk groups of the stream and walks it in
+// order, one group (1024 positions) per iteration, a lane per chunk.  The words of the next group
+// are loaded one iteration ahead (ncu: the streaming loads were the second largest stall), and
+// because the next group is also the next 32 chunks of the stream, lane 0's prefetched words ARE
+// the halo lane 31 needs -- no separate halo load.
+//
+// Tail (level 2 + exact path).  About 1.5 % of positions pass the minimizer levels, in runs of 3-4
+// inside few lanes; a per-lane loop walked them with ~2 lanes active and one L2 round trip per
+// step (ncu: 31 % of all long-scoreboard stalls on that one load).  Now the warp pools its
+// candidates: an inclusive scan gives every lane its slots, the owners write (lane, position)
+// into 32 shared-memory slots, and lane j takes candidate j -- fetching the owner's four words
+// by shuffle -- so all level-2 probes of a group are in flight together.
 template <int K, int M>
 __global__ void __launch_bounds__(kGateThreads, 1) count_kernel_gate2(const CountParams P)
 {
@@ -102,6 +137,7 @@ __global__ void __launch_bounds__(kGateThreads, 1) count_kernel_gate2(const Coun
 	static_assert(2 * K > 32 && K <= 31, "level 2 cuts the k-mer as one full word plus 2K-32 bits");
 	static_assert(M >= 11 && M <= 15 && W >= 2 && 2 * (NH - 1) + 32 <= 128, "window does not fit the 128-bit register view");
 	extern __shared__ uint32_t s_l0[];
+	__shared__ uint16_t s_cand[kGateThreads / 32][kCandSlots];
 	{
 		const uint4 *src = reinterpret_cast<const uint4 *>(P.level0);
 		uint4 *dst = reinterpret_cast<uint4 *>(s_l0);
@@ -110,85 +146,116 @@ __global__ void __launch_bounds__(kGateThreads, 1) count_kernel_gate2(const Coun
 	__syncthreads();
 	const uint32_t base_lo = (uint32_t)(uintptr_t)P.minimizer2, base_hi = (uint32_t)((uintptr_t)P.minimizer2 >> 32);
 	const uint32_t s_l0_addr = (uint32_t)__cvta_generic_to_shared(s_l0);
-	const uint64_t kmask = kmer_mask(K);
-	const int lane = threadIdx.x & 31;
+	const uint32_t wshift = P.filter_shift + 5;
+	const uint32_t lane = threadIdx.x & 31;
+	uint16_t *cand = s_cand[threadIdx.x >> 5];
 	uint32_t tk = 0, hits = 0;
-	const uint64_t stride = (uint64_t)gridDim.x * kGateThreads;
-	for (uint64_t base = (uint64_t)blockIdx.x * kGateThreads + (threadIdx.x & ~31u); base < P.n_chunks; base += stride) {
-		const uint64_t c = base + lane;
-		uint2 own = make_uint2(0, 0);
-		uint32_t m0 = 0xFFFFFFFFu;
-		if (c <= P.n_chunks) {                                   // chunk n_chunks is padding, always readable
-			own = __ldcs(P.bases + c);
-			m0 = __ldcs(P.nmask + c);
+
+	// this warp's run of groups: groups are dealt out as evenly as whole groups allow
+	const uint64_t n_groups = (P.n_chunks + 31) / 32;
+	const uint64_t n_warps = (uint64_t)gridDim.x * (kGateThreads / 32);
+	const uint64_t gw = (uint64_t)blockIdx.x * (kGateThreads / 32) + (threadIdx.x >> 5);
+	const uint64_t q = n_groups / n_warps, r = n_groups % n_warps;
+	const uint64_t g0 = gw * q + (gw < r ? gw : r), g1 = g0 + q + (gw < r ? 1 : 0);
+
+	// chunk n_chunks and n_chunks + 1 are padding and always readable (ntsm_padded_positions)
+	uint2 own_n = make_uint2(0, 0);
+	uint32_t m0_n = 0xFFFFFFFFu;
+	if (g0 < g1 && g0 * 32 + lane <= P.n_chunks) {
+		own_n = __ldcs(P.bases + g0 * 32 + lane);
+		m0_n = __ldcs(P.nmask + g0 * 32 + lane);
+	}
+	for (uint64_t g = g0; g < g1; ++g) {
+		const uint64_t c = g * 32 + lane;
+		const uint2 own = own_n;
+		uint32_t m0 = m0_n;
+		own_n = make_uint2(0, 0);
+		m0_n = 0xFFFFFFFFu;
+		if (c + 32 <= P.n_chunks) {                              // next group's words (the halo of this one among them)
+			own_n = __ldcs(P.bases + c + 32);
+			m0_n = __ldcs(P.nmask + c + 32);
 		}
 		uint2 nxt;
 		nxt.x = __shfl_down_sync(0xffffffffu, own.x, 1);
 		nxt.y = __shfl_down_sync(0xffffffffu, own.y, 1);
 		uint32_t m1 = __shfl_down_sync(0xffffffffu, m0, 1);
-		if (lane == 31) {
-			nxt = make_uint2(0, 0);
-			m1 = 0xFFFFFFFFu;
-			if (c + 1 <= P.n_chunks) {
-				nxt = __ldcs(P.bases + c + 1);
-				m1 = __ldcs(P.nmask + c + 1);
-			}
-		}
-		if (c >= P.n_chunks) m0 = 0xFFFFFFFFu;                  // nothing starts in the padding chunk
+		const uint32_t hx = __shfl_sync(0xffffffffu, own_n.x, 0), hy = __shfl_sync(0xffffffffu, own_n.y, 0);
+		const uint32_t hm = __shfl_sync(0xffffffffu, m0_n, 0);
+		if (lane == 31) { nxt.x = hx; nxt.y = hy; m1 = hm; }
+		if (c >= P.n_chunks) m0 = 0xFFFFFFFFu;                  // nothing starts in the padding chunks
 		const uint32_t w[4] = { own.x, own.y, nxt.x, nxt.y };
 		const uint32_t valid = valid_windows(m0, m1, K);
-		if (valid == 0) continue;
-		tk += __popc(valid);
-
-		// hash of the M-mer starting at each position: the multiplier's low SH zero bits push the
-		// bases beyond the M-mer out of the word, so no mask is needed
-		uint32_t h[NH];
+		uint32_t pass = 0;
+		if (valid) {
+			tk += __popc(valid);
+			// hash of the M-mer starting at each position: the multiplier's low SH zero bits push the
+			// bases beyond the M-mer out of the word, so no mask is needed
+			uint32_t h[NH];
 #pragma unroll
-		for (int j = 0; j < NH; ++j) {
-			const int a = j >> 4, sh = (2 * j) & 31;
-			h[j] = __funnelshift_r(w[a], w[a + 1 < 4 ? a + 1 : 3], sh) * kHashMul;
-		}
-		// sliding minimum over W consecutive hashes (van Herk / Gil-Werman)
-		uint32_t win[32];
-#pragma unroll
-		for (int i = 0; i < 32; ++i) {
-			const int b = i / W * W;
-			uint32_t sfx = h[b + W - 1];
-#pragma unroll
-			for (int t = b + W - 2; t >= i; --t) sfx = min(sfx, h[t]);
-			uint32_t v = sfx;
-			if (i != b) {
-				uint32_t pfx = h[b + W];
-#pragma unroll
-				for (int t = b + W + 1; t <= i + W - 1; ++t) pfx = min(pfx, h[t]);
-				v = min(sfx, pfx);
+			for (int j = 0; j < NH; ++j) {
+				const int a = j >> 4, sh = (2 * j) & 31;
+				h[j] = __funnelshift_r(w[a], w[a + 1 < 4 ? a + 1 : 3], sh) * kHashMul;
 			}
-			win[i] = v;
-		}
-		uint32_t pass = 0, bit = 0;
+			// sliding minimum over W consecutive hashes (van Herk / Gil-Werman)
+			uint32_t win[32];
 #pragma unroll
-		for (int i = 0; i < 32; ++i)
-			gate2_step<SH>(win[i], i ? win[i - 1] : ~win[0], s_l0_addr, base_lo, base_hi, P.four, bit, pass);
-		pass = __brev(pass);                 // steps pushed position 0 first, so it ended up at bit 31
-		pass &= valid;
-
-		// level 2: the k-mer bitmap, for the ~1.5 % of positions whose minimizer is a site minimizer
-		uint32_t pass2 = 0;
-		const uint32_t wshift = P.filter_shift + 5;
-		while (pass) {
-			uint32_t i;
-			asm("bfind.u32 %0, %1;" : "=r"(i) : "r"(pass));      // highest set bit (one FLO)
-			pass ^= 1u << i;
-			const bool up = i >= 16;
-			const uint32_t x0 = up ? w[1] : w[0], x1 = up ? w[2] : w[1], x2 = up ? w[3] : w[2];
-			const uint32_t lo = __funnelshift_r(x0, x1, 2 * i), hi = __funnelshift_r(x1, x2, 2 * i);
-			const uint32_t mix = lo * kG2MixA + hi * (kG2MixB << (64 - 2 * K));
-			const uint32_t v = __ldg(P.filter + (mix >> wshift));
-			const uint32_t t = mix * kG2MixC;
-			const uint32_t both = __funnelshift_r(v, v, t) & __funnelshift_r(v, v, t >> 5) & 1u;   // bits (t & 31) and (t >> 5 & 31)
-			pass2 |= both << i;
+			for (int i = 0; i < 32; ++i) {
+				const int b = i / W * W;
+				uint32_t sfx = h[b + W - 1];
+#pragma unroll
+				for (int t = b + W - 2; t >= i; --t) sfx = min(sfx, h[t]);
+				uint32_t v = sfx;
+				if (i != b) {
+					uint32_t pfx = h[b + W];
+#pragma unroll
+					for (int t = b + W + 1; t <= i + W - 1; ++t) pfx = min(pfx, h[t]);
+					v = min(sfx, pfx);
+				}
+				win[i] = v;
+			}
+			uint32_t bit = 0;
+#pragma unroll
+			for (int i = 0; i < 32; ++i)
+				gate2_step<SH>(win[i], i ? win[i - 1] : ~win[0], s_l0_addr, base_lo, base_hi, P.four, bit, pass);
+			pass = __brev(pass) & valid;         // steps pushed position 0 first, so it ended up at bit 31
 		}
-		if (pass2) hits += resolve_survivors<K>(P, w, pass2, K, kmask);
+
+		// ---- tail: pool the warp's candidates, one lane per candidate ----
+		const uint32_t cnt = __popc(pass);
+		uint32_t incl = cnt;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+			if (lane >= (uint32_t)d) incl += t;
+		}
+		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+		uint32_t idx = incl - cnt;                                // slot of this lane's next candidate
+		for (uint32_t r0 = 0; r0 < total; r0 += kCandSlots) {     // warp-uniform trip count, 1 almost always
+			while (pass && idx < r0 + kCandSlots) {
+				uint32_t i;
+				asm("bfind.u32 %0, %1;" : "=r"(i) : "r"(pass));  // highest set bit (one FLO)
+				pass ^= 1u << i;
+				cand[idx - r0] = (uint16_t)((lane << 5) | i);
+				++idx;
+			}
+			__syncwarp();
+			const bool mine = r0 + lane < total;
+			const uint32_t e = mine ? cand[lane] : (lane << 5);
+			const uint32_t src = e >> 5, i = e & 31;
+			const uint32_t y0 = __shfl_sync(0xffffffffu, w[0], src), y1 = __shfl_sync(0xffffffffu, w[1], src);
+			const uint32_t y2 = __shfl_sync(0xffffffffu, w[2], src), y3 = __shfl_sync(0xffffffffu, w[3], src);
+			if (mine) {
+				const bool up = i >= 16;
+				const uint32_t x0 = up ? y1 : y0, x1 = up ? y2 : y1, x2 = up ? y3 : y2;
+				const uint32_t lo = __funnelshift_r(x0, x1, 2 * i), hi = __funnelshift_r(x1, x2, 2 * i);
+				const uint32_t mix = lo * kG2MixA + hi * (kG2MixB << (64 - 2 * K));
+				const uint32_t v = __ldg(P.filter + (mix >> wshift));
+				const uint32_t t = mix * kG2MixC;
+				// level 2: bits (t & 31) and (t >> 5 & 31) of the word both set?
+				if (__funnelshift_r(v, v, t) & __funnelshift_r(v, v, t >> 5) & 1u) hits += resolve_one<K>(P, lo, hi);
+			}
+			__syncwarp();
+		}
 	}
 	flush_tallies(tk, hits, P.totals);
 }

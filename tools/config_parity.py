@@ -1,0 +1,211 @@
+#!/usr/bin/env python3
+"""Bit-exactness of the ntsmCount drop-in on the five BASELINE.json configs, through the CLI binary.
+
+    python tools/config_parity.py --make-expected      # build container: runs the UNMODIFIED reference
+    python tools/config_parity.py --check               # GPU box: runs ntsm_b200/bin/ntsmCount
+
+Both modes regenerate the same inputs from fixed seeds (ntsm_b200/synth_np.py, numpy PCG64), scaled
+so that the reference finishes in minutes on the build container's cores:
+
+  cfg1  1 M x 150 bp reads, 30 Mb genome, one FASTQ, -t 1                (full size)
+  cfg2  4 M x 150 bp reads, 300 Mb genome, 16 FASTQ files, -t 16         (scaled from 100 Gbases)
+  cfg3  0.3 Gbases of ONT-like reads (N50 ~20 kb, 5-10 % error, N runs)  (scaled from 20 Gbases)
+  cfg4  4 M paired-end reads of a 30 Mb genome as 8 .fq.gz, with and without -m 10
+  cfg5  10^6 synthetic sites (~26 M k-mers) vs 2 M reads                 (reads scaled from 50 Gbases)
+
+--make-expected stores sha256 / size / the reference's own summary numbers per config in
+tests/golden/configs.json.  --check compares the CLI's stdout byte count and sha256 with it (for
+the -m run: the documented batch-granular stop is checked instead) and writes the
+timings next to the reference's to gpurun_out/config_parity.json.
+/root/reference is never read here: the reference binary is oracle/_ref/ntsmCount (built by
+oracle/Makefile), and only --make-expected executes it.
+"""
+import argparse
+import hashlib
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+PANEL = os.path.join(ROOT, "data", "human_sites_n10.fa.gz")
+REF = os.path.join(ROOT, "oracle", "_ref", "ntsmCount")
+OURS = os.path.join(ROOT, "ntsm_b200", "bin", "ntsmCount")
+EXPECTED = os.path.join(ROOT, "tests", "golden", "configs.json")
+
+
+def log(*a):
+    print("[config_parity]", *a, file=sys.stderr, flush=True)
+
+
+def human_panel(tmp):
+    import gzip
+    p = os.path.join(tmp, "human_sites_n10.fa")
+    if not os.path.exists(p):
+        with gzip.open(PANEL, "rb") as src, open(p, "wb") as dst:
+            shutil.copyfileobj(src, dst)
+    return p
+
+
+def make_inputs(cfg, tmp, scale):
+    """-> (sites_path, [read files], extra argv, threads)"""
+    from ntsm_b200 import synth_np as S
+    d = os.path.join(tmp, cfg)
+    os.makedirs(d, exist_ok=True)
+    if cfg in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg4m"):
+        sites = human_panel(tmp)
+        wc, wl = S.read_panel_windows(PANEL)
+    if cfg == "cfg1":
+        g = S.Genome(30_000_000, wc, wl, 1)
+        codes = S.short_reads(g, int(1_000_000 * scale), 150, 0.01, 11)
+        return sites, [S.write_fastq_matrix(codes, os.path.join(d, "reads.fq"))], [], 1
+    if cfg == "cfg2":
+        g = S.Genome(300_000_000, wc, wl, 2)
+        n, files = int(4_000_000 * scale) // 16 * 16, []
+        for i in range(16):
+            codes = S.short_reads(g, n // 16, 150, 0.01, 200 + i)
+            files.append(S.write_fastq_matrix(codes, os.path.join(d, "part%02d.fq" % i), first_index=i * (n // 16)))
+        return sites, files, [], 16
+    if cfg == "cfg3":
+        g = S.Genome(300_000_000, wc, wl, 3)
+        files = []
+        for i in range(4):
+            reads = S.ont_reads(g, int(75_000_000 * scale), 300 + i)
+            files.append(S.write_fastq_ragged(reads, os.path.join(d, "ont%d.fq" % i)))
+        return sites, files, [], 4
+    if cfg in ("cfg4", "cfg4m"):
+        d = os.path.join(tmp, "cfg4")                       # both runs share the files
+        os.makedirs(d, exist_ok=True)
+        files = [os.path.join(d, "lane%d_R%d.fq.gz" % (l, r)) for l in range(4) for r in (1, 2)]
+        if not all(os.path.exists(f) for f in files):
+            g = S.Genome(30_000_000, wc, wl, 4)
+            plain = []
+            for lane in range(4):
+                r1, r2 = S.paired_reads(g, int(500_000 * scale), 150, 0.01, 400 + lane)
+                plain.append(S.write_fastq_matrix(r1, os.path.join(d, "lane%d_R1.fq" % lane), prefix=b"f"))
+                plain.append(S.write_fastq_matrix(r2, os.path.join(d, "lane%d_R2.fq" % lane), prefix=b"g"))
+            S.gzip_files(plain)
+        if cfg == "cfg4m":
+            return sites, files, ["-m", "10"], 1               # -t 1: the reference's stop point is deterministic
+        return sites, files, [], 8
+    if cfg == "cfg5":
+        sites = os.path.join(d, "sites_1e6.fa")
+        win, n = S.synthetic_panel(sites, int(1_000_000 * min(1.0, scale)), 5)
+        wc, wl = S.panel_alleles_from_windows(win)
+        g = S.Genome(max(100_000_000, 100 * n), wc, wl, 50)
+        files = []
+        for i in range(4):
+            codes = S.short_reads(g, int(500_000 * scale), 150, 0.01, 500 + i)
+            files.append(S.write_fastq_matrix(codes, os.path.join(d, "reads%d.fq" % i), first_index=i * 10_000_000))
+        return sites, files, [], 4
+    raise ValueError(cfg)
+
+
+def run(exe, sites, files, extra, threads, env=None):
+    argv = [exe, "-t", str(threads), "-s", sites] + extra + files
+    t0 = time.perf_counter()
+    p = subprocess.run(argv, capture_output=True, env=env)
+    dt = time.perf_counter() - t0
+    err = p.stderr.decode(errors="replace")
+    info = {"rc": p.returncode, "seconds": dt, "stdout_bytes": len(p.stdout), "sha256": hashlib.sha256(p.stdout).hexdigest()}
+    for key, pat in (("bases", r"Total Bases Considered: (\d+)"), ("kmers", r"Total k-mers Considered: (\d+)"),
+                     ("hits", r"Total k-mers Recorded: (\d+)"), ("tool_seconds", r"Time: ([0-9.eE+-]+) s")):
+        m = re.search(pat, err)
+        if m:
+            info[key] = float(m.group(1)) if key == "tool_seconds" else int(m.group(1))
+    info["early_stop"] = "Reached desired" in err or "threshold" in err
+    if p.returncode != 0:
+        info["stderr_tail"] = err[-400:]
+    return info, p.stdout
+
+
+def rows_of(stdout):
+    """counts file -> {locus: (countAT, countCG, sumAT, sumCG)}"""
+    out = {}
+    for line in stdout.decode().splitlines():
+        if line.startswith("#"):
+            continue
+        f = line.split("\t")
+        out[f[0]] = tuple(int(x) for x in f[1:5])
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--make-expected", action="store_true")
+    ap.add_argument("--check", action="store_true")
+    ap.add_argument("--configs", default="cfg1,cfg2,cfg3,cfg4,cfg4m,cfg5")
+    ap.add_argument("--scale", type=float, default=1.0, help="scale every read count (tests use < 1)")
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--tmp", default=None)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "config_parity.json"))
+    args = ap.parse_args()
+    tmp = args.tmp or tempfile.mkdtemp(prefix="ntsm_cfg_")
+    os.makedirs(tmp, exist_ok=True)
+    cfgs = args.configs.split(",")
+    expected = json.load(open(EXPECTED)) if os.path.exists(EXPECTED) else {}
+    key = "scale=%g" % args.scale
+    results, ok = {}, True
+    try:
+        for cfg in cfgs:
+            t0 = time.perf_counter()
+            sites, files, extra, threads = make_inputs(cfg, tmp, args.scale)
+            gen_s = time.perf_counter() - t0
+            in_bytes = sum(os.path.getsize(f) for f in files)
+            if args.make_expected:
+                info, _ = run(REF, sites, files, extra, threads, env=dict(os.environ, OMP_NUM_THREADS=str(threads)))
+                info.update(threads=threads, input_bytes=in_bytes, argv_extra=extra, n_files=len(files))
+                expected.setdefault(key, {})[cfg] = info
+                log(cfg, "reference: rc", info["rc"], "%.1f s" % info["seconds"], "bases", info.get("bases"), "sha", info["sha256"][:12], "(generated in %.1f s)" % gen_s)
+            if args.check:
+                want = expected.get(key, {}).get(cfg)
+                more = ["--gpus", str(args.gpus)] if args.gpus != 1 else []
+                info, out = run(OURS, sites, files, extra + more, threads)
+                info.update(threads=threads, input_bytes=in_bytes, generated_in_s=gen_s)
+                if info.get("bases") and info.get("tool_seconds"):
+                    info["gbases_per_s"] = info["bases"] / info["tool_seconds"] / 1e9
+                if want is None:
+                    info["verdict"] = "no expected entry"
+                    ok = False
+                elif cfg == "cfg4m":
+                    # -m: we stop at a batch boundary (2^22 positions per batch in the CLI), the reference after
+                    # the read that crosses the cap.  Same file order, so our reads are a superset prefix.
+                    nocap = expected[key].get("cfg4")
+                    slack = 2 * (1 << 22) * max(1, args.gpus)
+                    good = info["rc"] == 0 and info["early_stop"] and want["bases"] <= info["bases"] <= want["bases"] + slack
+                    good = good and info["hits"] >= want["hits"] and (nocap is None or info["bases"] < nocap["bases"])
+                    info["verdict"] = "ok (stopped %d bases after the reference's stop, slack %d)" % (info["bases"] - want["bases"], slack) if good else "MISMATCH"
+                    info["reference"] = {k: want.get(k) for k in ("bases", "hits", "seconds", "tool_seconds")}
+                    ok = ok and good
+                else:
+                    good = info["rc"] == want["rc"] and info["sha256"] == want["sha256"] and info["stdout_bytes"] == want["stdout_bytes"]
+                    info["verdict"] = "bit-exact" if good else "MISMATCH"
+                    info["reference"] = {k: want.get(k) for k in ("bases", "seconds", "tool_seconds", "threads")}
+                    if want.get("bases") and want.get("tool_seconds"):
+                        info["reference"]["gbases_per_s"] = want["bases"] / want["tool_seconds"] / 1e9
+                    ok = ok and good
+                results[cfg] = info
+                log(cfg, info["verdict"], "rc", info["rc"], "%.2f s" % info["seconds"], "bases", info.get("bases"), "(generated in %.1f s)" % gen_s)
+            if cfg not in ("cfg4",):                         # cfg4m reuses cfg4's files
+                shutil.rmtree(os.path.join(tmp, cfg), ignore_errors=True)
+    finally:
+        if not args.tmp:
+            shutil.rmtree(tmp, ignore_errors=True)
+    if args.make_expected:
+        os.makedirs(os.path.dirname(EXPECTED), exist_ok=True)
+        json.dump(expected, open(EXPECTED, "w"), indent=1, sort_keys=True)
+        log("wrote", EXPECTED)
+    if args.check:
+        os.makedirs(os.path.dirname(args.out), exist_ok=True)
+        json.dump({"scale": args.scale, "gpus": args.gpus, "all_ok": ok, "configs": results}, open(args.out, "w"), indent=1, sort_keys=True)
+        log("wrote", args.out, "all_ok =", ok)
+        sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
