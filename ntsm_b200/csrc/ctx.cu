@@ -50,7 +50,9 @@ struct ntsm_ctx {
 	uint32_t *d_level1 = nullptr;           // 4^M-bit minimizer bitmap of the k = 19 kernels (layout per variant)
 	uint32_t *d_level0 = nullptr;           // image of the gated kernels' shared-memory level-0 bitmap
 	int kernel_variant = 3;                 // k = 19: 0 plain, 1 minimizer, 2 smem-gated minimizer, 3 gate2 (default)
-	int gate_m = 14;                        // M-mer length of gate2 (12..14)
+	int gate_m = 14;                        // M-mer length of gate2 (13 or 14)
+	int gate_threads = 1024;                // gate2 CTA size (NTSM_GATE_THREADS: 512 / 768 / 1024)
+	bool pool_tail = true;                  // gate2: warp-pooled level-2/exact tail (NTSM_TAIL_POOL=0 -> per-lane loop)
 	uint32_t filter_bits = 0;
 	TableSlot *d_table = nullptr;
 	uint32_t table_cap = 0;
@@ -191,7 +193,9 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 	if (const char *e = getenv("NTSM_KERNEL")) variant = atoi(e);
 	if (const char *e = getenv("NTSM_GATE_M")) gm = atoi(e);
 	if (k != 19 || variant < 0 || variant > 3) variant = 0;
-	if (gm < 12 || gm > 14) gm = 14;
+	if (gm < 13 || gm > 14) gm = 14;
+	if (const char *e = getenv("NTSM_TAIL_POOL")) c->pool_tail = atoi(e) != 0;
+	if (const char *e = getenv("NTSM_GATE_THREADS")) c->gate_threads = atoi(e);
 
 	// k-mer bitmap holding both orientations of every live k-mer
 	uint32_t fbits = 16;
@@ -284,9 +288,11 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 		CU(c, cudaMalloc(&c->d_level0, level0.size() * 4));
 		CU(c, cudaMemcpy(c->d_level0, level0.data(), level0.size() * 4, cudaMemcpyHostToDevice));
 		CU(c, cudaFuncSetAttribute(count_kernel_gate<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
-		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
-		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
-		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
+		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 13, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
+		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 14, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
+		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 14, false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
+		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 14, true, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
+		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 14, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
 	}
 	c->kernel_variant = variant;
 	c->gate_m = gm;
@@ -370,9 +376,14 @@ static int launch_count(ntsm_ctx *c, const uint2 *d_bases, const uint32_t *d_mas
 	const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)c->sm_count * 16);
 	const unsigned g2 = (unsigned)std::min<uint64_t>((P.n_chunks + kGateThreads - 1) / kGateThreads, (uint64_t)c->sm_count);
 	if (c->cfg.k == 19 && c->kernel_variant == 3) {
-		if (c->gate_m == 12) count_kernel_gate2<19, 12><<<g2, kGateThreads, kL0Words * 4, st>>>(P);
-		else if (c->gate_m == 13) count_kernel_gate2<19, 13><<<g2, kGateThreads, kL0Words * 4, st>>>(P);
-		else count_kernel_gate2<19, 14><<<g2, kGateThreads, kL0Words * 4, st>>>(P);
+		// one persistent CTA per SM (fewer when the batch has fewer 31-chunk groups than that many CTAs have warps)
+		const uint64_t groups = (P.n_chunks + kGroupChunks - 1) / kGroupChunks, wpc = (uint64_t)(c->gate_threads == 768 || c->gate_threads == 512 ? c->gate_threads : 1024) / 32;
+		const unsigned g3 = (unsigned)std::min<uint64_t>((groups + wpc - 1) / wpc, (uint64_t)c->sm_count);
+		if (c->gate_m == 13) count_kernel_gate2<19, 13, true, 1024><<<g3, 1024, kL0Words * 4, st>>>(P);
+		else if (!c->pool_tail) count_kernel_gate2<19, 14, false, 1024><<<g3, 1024, kL0Words * 4, st>>>(P);
+		else if (c->gate_threads == 768) count_kernel_gate2<19, 14, true, 768><<<g3, 768, kL0Words * 4, st>>>(P);
+		else if (c->gate_threads == 512) count_kernel_gate2<19, 14, true, 512><<<g3, 512, kL0Words * 4, st>>>(P);
+		else count_kernel_gate2<19, 14, true, 1024><<<g3, 1024, kL0Words * 4, st>>>(P);
 	} else if (c->cfg.k == 19 && c->kernel_variant == 2) count_kernel_gate<19><<<g2, kGateThreads, kL0Words * 4, st>>>(P);
 	else if (c->cfg.k == 19 && c->kernel_variant == 1) count_kernel_min<19, kMinimizerM><<<grid, kCountThreads, 0, st>>>(P);
 	else if (c->cfg.k == 19) count_kernel<19><<<grid, kCountThreads, 0, st>>>(P);
@@ -729,7 +740,7 @@ extern "C" const char *ntsm_ctx_kernel_name(const ntsm_ctx *c)
 	if (c->cfg.k != 19 || c->kernel_variant == 0) return c->cfg.k == 19 ? "count_kernel<19>" : "count_kernel<0>";
 	if (c->kernel_variant == 1) return "count_kernel_min<19,13>";
 	if (c->kernel_variant == 2) return "count_kernel_gate<19>";
-	return c->gate_m == 12 ? "count_kernel_gate2<19,12>" : c->gate_m == 13 ? "count_kernel_gate2<19,13>" : "count_kernel_gate2<19,14>";
+	return c->gate_m == 13 ? "count_kernel_gate2<19,13,1>" : c->pool_tail ? "count_kernel_gate2<19,14,1>" : "count_kernel_gate2<19,14,0>";
 }
 extern "C" uint32_t ntsm_ctx_filter_bits(const ntsm_ctx *c) { return c ? c->filter_bits : 0; }
 extern "C" uint32_t ntsm_ctx_table_capacity(const ntsm_ctx *c) { return c ? c->table_cap : 0; }

@@ -115,33 +115,36 @@ __device__ __forceinline__ uint32_t resolve_one(const CountParams &P, uint32_t l
 
 constexpr int kCandSlots = 32;      // candidates one warp hands round per pass of its tail
 
-// Work layout.  Every warp owns a CONTIGUOUS run of 32-chunk groups of the stream and walks it in
-// order, one group (1024 positions) per iteration, a lane per chunk.  The words of the next group
-// are loaded one iteration ahead (ncu: the streaming loads were the second largest stall), and
-// because the next group is also the next 32 chunks of the stream, lane 0's prefetched words ARE
-// the halo lane 31 needs -- no separate halo load.
+// Work layout.  A group is 31 chunks (992 positions) handled by lanes 0-30; lane 31 holds the chunk after them,
+// which is only the halo of lane 30 (a window reaches K-1 <= 30 positions past its start).  That
+// costs one idle lane (no extra issue slots: the warp executes the same instructions) and buys a
+// loop with no dependence between a group and the next one's data, so every lane loads its words
+// a whole iteration before they are used (ncu on the first version: the streaming loads, used
+// right after they were issued, were 32 % of all long-scoreboard stalls).
 //
 // Tail (level 2 + exact path).  About 1.5 % of positions pass the minimizer levels, in runs of 3-4
-// inside few lanes; a per-lane loop walked them with ~2 lanes active and one L2 round trip per
-// step (ncu: 31 % of all long-scoreboard stalls on that one load).  Now the warp pools its
-// candidates: an inclusive scan gives every lane its slots, the owners write (lane, position)
-// into 32 shared-memory slots, and lane j takes candidate j -- fetching the owner's four words
-// by shuffle -- so all level-2 probes of a group are in flight together.
-template <int K, int M>
-__global__ void __launch_bounds__(kGateThreads, 1) count_kernel_gate2(const CountParams P)
+// inside few lanes; a per-lane loop walks them with ~2 lanes active and one L2 round trip per
+// step (ncu: 36 % of the long-scoreboard stalls on that one load).  With POOL the warp pools its
+// candidates instead: an inclusive scan gives every lane its slots, the owners write
+// (lane, position) into 32 shared-memory slots, and lane j takes candidate j -- fetching the
+// owner's four words by shuffle -- so all level-2 probes of a group are in flight together.
+constexpr uint32_t kGroupChunks = 31;
+
+template <int K, int M, bool POOL, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) count_kernel_gate2(const CountParams P)
 {
 	constexpr int W = K - M + 1;
 	constexpr int NH = 32 + W - 1;
 	constexpr int SH = 32 - 2 * M;
 	constexpr uint32_t kHashMul = kMinHashMul << SH;
 	static_assert(2 * K > 32 && K <= 31, "level 2 cuts the k-mer as one full word plus 2K-32 bits");
-	static_assert(M >= 11 && M <= 15 && W >= 2 && 2 * (NH - 1) + 32 <= 128, "window does not fit the 128-bit register view");
+	static_assert(M >= 11 && M <= 15 && W >= 2 && W <= 17 && 2 * (NH - 1) + 32 <= 128, "window does not fit the 128-bit register view");
 	extern __shared__ uint32_t s_l0[];
-	__shared__ uint16_t s_cand[kGateThreads / 32][kCandSlots];
+	__shared__ uint16_t s_cand[THREADS / 32][kCandSlots];
 	{
 		const uint4 *src = reinterpret_cast<const uint4 *>(P.level0);
 		uint4 *dst = reinterpret_cast<uint4 *>(s_l0);
-		for (uint32_t i = threadIdx.x; i < kL0Words / 4; i += kGateThreads) dst[i] = __ldg(src + i);
+		for (uint32_t i = threadIdx.x; i < kL0Words / 4; i += THREADS) dst[i] = __ldg(src + i);
 	}
 	__syncthreads();
 	const uint32_t base_lo = (uint32_t)(uintptr_t)P.minimizer2, base_hi = (uint32_t)((uintptr_t)P.minimizer2 >> 32);
@@ -151,75 +154,99 @@ __global__ void __launch_bounds__(kGateThreads, 1) count_kernel_gate2(const Coun
 	uint16_t *cand = s_cand[threadIdx.x >> 5];
 	uint32_t tk = 0, hits = 0;
 
-	// this warp's run of groups: groups are dealt out as evenly as whole groups allow
-	const uint64_t n_groups = (P.n_chunks + 31) / 32;
-	const uint64_t n_warps = (uint64_t)gridDim.x * (kGateThreads / 32);
-	const uint64_t gw = (uint64_t)blockIdx.x * (kGateThreads / 32) + (threadIdx.x >> 5);
-	const uint64_t q = n_groups / n_warps, r = n_groups % n_warps;
-	const uint64_t g0 = gw * q + (gw < r ? gw : r), g1 = g0 + q + (gw < r ? 1 : 0);
+	// groups are dealt round-robin over all warps of the grid: at any moment the whole grid reads one
+	// narrow band of the stream (contiguous per-warp runs were 15 % slower -- thousands of separate
+	// streams cost TLB reach and DRAM page locality)
+	const uint64_t n_groups = (P.n_chunks + kGroupChunks - 1) / kGroupChunks;
+	const uint64_t n_warps = (uint64_t)gridDim.x * (THREADS / 32);
+	const uint64_t gw = (uint64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
 
-	// chunk n_chunks and n_chunks + 1 are padding and always readable (ntsm_padded_positions)
+	// chunk n_chunks is padding and always readable (ntsm_padded_positions); anything later reads as invalid
 	uint2 own_n = make_uint2(0, 0);
 	uint32_t m0_n = 0xFFFFFFFFu;
-	if (g0 < g1 && g0 * 32 + lane <= P.n_chunks) {
-		own_n = __ldcs(P.bases + g0 * 32 + lane);
-		m0_n = __ldcs(P.nmask + g0 * 32 + lane);
+	if (gw < n_groups && gw * kGroupChunks + lane <= P.n_chunks) {
+		own_n = __ldcs(P.bases + gw * kGroupChunks + lane);
+		m0_n = __ldcs(P.nmask + gw * kGroupChunks + lane);
 	}
-	for (uint64_t g = g0; g < g1; ++g) {
-		const uint64_t c = g * 32 + lane;
+	for (uint64_t g = gw; g < n_groups; g += n_warps) {
+		const uint64_t c = g * kGroupChunks + lane;
+		const uint64_t cn = c + n_warps * kGroupChunks;           // this lane's chunk in the warp's next group
 		const uint2 own = own_n;
 		uint32_t m0 = m0_n;
 		own_n = make_uint2(0, 0);
 		m0_n = 0xFFFFFFFFu;
-		if (c + 32 <= P.n_chunks) {                              // next group's words (the halo of this one among them)
-			own_n = __ldcs(P.bases + c + 32);
-			m0_n = __ldcs(P.nmask + c + 32);
+		if (g + n_warps < n_groups && cn <= P.n_chunks) {         // loaded now, used one iteration from now
+			own_n = __ldcs(P.bases + cn);
+			m0_n = __ldcs(P.nmask + cn);
 		}
 		uint2 nxt;
 		nxt.x = __shfl_down_sync(0xffffffffu, own.x, 1);
 		nxt.y = __shfl_down_sync(0xffffffffu, own.y, 1);
 		uint32_t m1 = __shfl_down_sync(0xffffffffu, m0, 1);
-		const uint32_t hx = __shfl_sync(0xffffffffu, own_n.x, 0), hy = __shfl_sync(0xffffffffu, own_n.y, 0);
-		const uint32_t hm = __shfl_sync(0xffffffffu, m0_n, 0);
-		if (lane == 31) { nxt.x = hx; nxt.y = hy; m1 = hm; }
-		if (c >= P.n_chunks) m0 = 0xFFFFFFFFu;                  // nothing starts in the padding chunks
+		if (lane == 31 || c >= P.n_chunks) m0 = 0xFFFFFFFFu;    // lane 31 is halo only; nothing starts in the padding
 		const uint32_t w[4] = { own.x, own.y, nxt.x, nxt.y };
 		const uint32_t valid = valid_windows(m0, m1, K);
 		uint32_t pass = 0;
 		if (valid) {
 			tk += __popc(valid);
-			// hash of the M-mer starting at each position: the multiplier's low SH zero bits push the
-			// bases beyond the M-mer out of the word, so no mask is needed
-			uint32_t h[NH];
+			// Two halves of 16 positions, as a real loop: the live set is 21 hashes + 16 minima instead
+			// of 37 + 32, which is what lets 1024 threads fit their 64 registers without spilling (with
+			// 224 KiB of shared memory there is next to no L1 left: every spill reload is an L2 round trip).
+			uint32_t bit = 0, prevw = 0;
+#pragma unroll 1
+			for (int half = 0; half < 2; ++half) {
+				const uint32_t x0 = half ? w[1] : w[0], x1 = half ? w[2] : w[1], x2 = half ? w[3] : w[2];
+				// hash of the M-mer starting at each position: the multiplier's low SH zero bits push the
+				// bases beyond the M-mer out of the word, so no mask is needed
+				constexpr int NHH = 16 + W - 1;
+				uint32_t h[NHH];
 #pragma unroll
-			for (int j = 0; j < NH; ++j) {
-				const int a = j >> 4, sh = (2 * j) & 31;
-				h[j] = __funnelshift_r(w[a], w[a + 1 < 4 ? a + 1 : 3], sh) * kHashMul;
-			}
-			// sliding minimum over W consecutive hashes (van Herk / Gil-Werman)
-			uint32_t win[32];
-#pragma unroll
-			for (int i = 0; i < 32; ++i) {
-				const int b = i / W * W;
-				uint32_t sfx = h[b + W - 1];
-#pragma unroll
-				for (int t = b + W - 2; t >= i; --t) sfx = min(sfx, h[t]);
-				uint32_t v = sfx;
-				if (i != b) {
-					uint32_t pfx = h[b + W];
-#pragma unroll
-					for (int t = b + W + 1; t <= i + W - 1; ++t) pfx = min(pfx, h[t]);
-					v = min(sfx, pfx);
+				for (int j = 0; j < NHH; ++j) {
+					const int sh = (2 * j) & 31;
+					h[j] = (j < 16 ? __funnelshift_r(x0, x1, sh) : __funnelshift_r(x1, x2, sh)) * kHashMul;
 				}
-				win[i] = v;
-			}
-			uint32_t bit = 0;
+				// sliding minimum over W consecutive hashes (van Herk / Gil-Werman)
+				uint32_t win[16];
 #pragma unroll
-			for (int i = 0; i < 32; ++i)
-				gate2_step<SH>(win[i], i ? win[i - 1] : ~win[0], s_l0_addr, base_lo, base_hi, P.four, bit, pass);
+				for (int i = 0; i < 16; ++i) {
+					const int b = i / W * W;
+					uint32_t sfx = h[b + W - 1];
+#pragma unroll
+					for (int t = b + W - 2; t >= i; --t) sfx = min(sfx, h[t]);
+					uint32_t v = sfx;
+					if (i != b) {
+						uint32_t pfx = h[b + W];
+#pragma unroll
+						for (int t = b + W + 1; t <= i + W - 1; ++t) pfx = min(pfx, h[t]);
+						v = min(sfx, pfx);
+					}
+					win[i] = v;
+				}
+				const uint32_t before = half ? prevw : ~win[0];       // position 0 always counts as a change
+#pragma unroll
+				for (int i = 0; i < 16; ++i)
+					gate2_step<SH>(win[i], i ? win[i - 1] : before, s_l0_addr, base_lo, base_hi, P.four, bit, pass);
+				prevw = win[15];
+			}
 			pass = __brev(pass) & valid;         // steps pushed position 0 first, so it ended up at bit 31
 		}
 
+		if (!POOL) {
+			// ---- tail, per lane: one candidate at a time ----
+			while (pass) {
+				uint32_t i;
+				asm("bfind.u32 %0, %1;" : "=r"(i) : "r"(pass));  // highest set bit (one FLO)
+				pass ^= 1u << i;
+				const bool up = i >= 16;
+				const uint32_t x0 = up ? w[1] : w[0], x1 = up ? w[2] : w[1], x2 = up ? w[3] : w[2];
+				const uint32_t lo = __funnelshift_r(x0, x1, 2 * i), hi = __funnelshift_r(x1, x2, 2 * i);
+				const uint32_t mix = lo * kG2MixA + hi * (kG2MixB << (64 - 2 * K));
+				const uint32_t v = __ldg(P.filter + (mix >> wshift));
+				const uint32_t t = mix * kG2MixC;
+				if (__funnelshift_r(v, v, t) & __funnelshift_r(v, v, t >> 5) & 1u) hits += resolve_one<K>(P, lo, hi);
+			}
+			continue;
+		}
 		// ---- tail: pool the warp's candidates, one lane per candidate ----
 		const uint32_t cnt = __popc(pass);
 		uint32_t incl = cnt;
