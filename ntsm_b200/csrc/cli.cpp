@@ -114,6 +114,13 @@ extern "C" int ntsm_main(int argc, char **argv)
 	if (die) { std::cerr << "Try '--help' for more information.\n"; return EXIT_FAILURE; }
 
 	const auto t0 = std::chrono::steady_clock::now();
+	// phase timing on stderr when NTSM_TIMING is set (measurement aid, not part of the reference's output)
+	const bool timing = getenv("NTSM_TIMING") != nullptr;
+	auto lap = [&, last = t0](const char *what) mutable {
+		const auto now = std::chrono::steady_clock::now();
+		if (timing) fprintf(stderr, "[ntsm timing] %-28s %.3f s\n", what, std::chrono::duration<double>(now - last).count());
+		last = now;
+	};
 
 	// FingerPrint fp;  (ntSeqMatchCount.cpp:177)
 	ntsm_sites *sites = nullptr;
@@ -121,6 +128,7 @@ extern "C" int ntsm_main(int argc, char **argv)
 	if (rc) { std::cerr << "file " << snp << " cannot be opened" << std::endl; return 1; }   // FingerPrint.hpp:493-499
 	if (verbose) std::cerr << "Opening " << snp << std::endl;
 	for (uint32_t i = 0; i < ntsm_sites_n_warnings(sites); ++i) std::cerr << ntsm_sites_warning(sites, i) << std::endl;
+	lap("sites.fa -> site table (host)");
 
 	const int n_dev = ntsm_device_count();
 	if (n_dev <= 0) {
@@ -153,6 +161,7 @@ extern "C" int ntsm_main(int argc, char **argv)
 			if (rcs[g]) { std::cerr << PROGRAM ": " << ntsm_last_error(ctxs[g]) << std::endl; return 1; }
 	}
 
+	lap("CUDA context + device tables");
 	// fp.computeCounts(inputFiles);  (:178)
 	std::vector<const char *> paths;
 	for (auto &f : inputFiles) paths.push_back(f.c_str());
@@ -160,6 +169,7 @@ extern "C" int ntsm_main(int argc, char **argv)
 	rc = ntsm_count_files(ctxs.data(), (uint32_t)gpus, paths.data(), (uint32_t)paths.size(), threads, verbose, &early);
 	if (rc) { std::cerr << ntsm_last_error(nullptr) << std::endl; return 1; }
 	if (early) std::cerr << "Reached desired (-m) threshold" << std::endl;   // FingerPrint.hpp:84-86
+	lap("parse + pack + count");
 
 	// combine the GPUs (k-mer level sums, then per-site max) and fetch the rows
 	const uint32_t S = ntsm_sites_n_sites(sites);
@@ -186,6 +196,7 @@ extern "C" int ntsm_main(int argc, char **argv)
 	ntsm_format_counts(sites, mr.data(), mv.data(), sr.data(), sv.data(), totals[0], &text[0], text.size());
 	fwrite(text.data(), 1, text.size(), stdout);
 	fflush(stdout);
+	lap("combine + rows + counts file");
 
 	// cerr << fp.printInfoSummary() << endl;  (:181, FingerPrint.hpp:313-349)
 	const uint32_t covered = ntsm_sites_covered(mr.data(), mv.data(), S);

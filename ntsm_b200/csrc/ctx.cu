@@ -177,7 +177,6 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 	if (!c || (!kmer_hash && n_kmers) || !allele_off) return fail(c, NTSM_ERR_ARG, "ntsm_load_sites: null argument");
 	CU(c, cudaSetDevice(c->device));
 	const uint32_t k = c->cfg.k;
-	const uint64_t m = kmer_mask(k);
 	uint64_t live = 0;
 	for (uint32_t i = 0; i < n_kmers; ++i) live += !(erased && erased[i]);
 
@@ -185,7 +184,6 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 	uint64_t cap = 1024;
 	while (cap < 2 * live) cap <<= 1;
 	if (cap > (1ull << 31)) return fail(c, NTSM_ERR_ARG, "too many site k-mers (%llu)", (unsigned long long)live);
-	std::vector<TableSlot> table(cap, TableSlot{ kEmptyKey, 0, 0 });
 
 	// which count kernel will run decides which pre-filter structures are built (NTSM_KERNEL / NTSM_GATE_M
 	// are measurement knobs: every variant gives the same counts)
@@ -201,92 +199,35 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 	uint32_t fbits = 16;
 	while (fbits < 30 && (1ull << fbits) < 40ull * 2ull * live) ++fbits;
 	if (const char *e = getenv("NTSM_FILTER_BITS")) fbits = (uint32_t)std::min(32, std::max(10, atoi(e)));
-	const uint32_t fshift = 32 - fbits;
-	std::vector<uint32_t> filter((1ull << fbits) / 32, 0u);      // layout depends on the variant
+	const size_t filter_words = (1ull << fbits) / 32;                 // layout depends on the variant
 	// minimizer bitmaps: level 1 = 4^M bits in global memory, level 0 = image of the shared-memory bitmap
 	const int mm_len = variant == 1 ? kMinimizerM : variant == 2 ? kGateM : gm;
-	std::vector<uint32_t> level1(variant ? (1ull << (2 * mm_len)) / 32 : 0, 0u);
-	std::vector<uint32_t> level0(variant >= 2 ? kL0Words : 0, 0u);
-
-	for (uint32_t i = 0; i < n_kmers; ++i) {
-		if (erased && erased[i]) continue;
-		const uint64_t h = kmer_hash[i];
-		if (h > m) return fail(c, NTSM_ERR_ARG, "k-mer hash %u out of range for k=%u", i, k);
-		uint32_t slot = (uint32_t)(h ^ (h >> 29)) & (uint32_t)(cap - 1);
-		while (table[slot].key != kEmptyKey) {
-			if (table[slot].key == h) return fail(c, NTSM_ERR_ARG, "duplicate k-mer hash at index %u", i);
-			slot = (slot + 1) & (uint32_t)(cap - 1);
-		}
-		table[slot].key = h;
-		table[slot].idx = i;
-		// the canonical k-mer (reference orientation) and the two stream-order spellings a read can show
-		const uint64_t canon = hash64_inv(h, m);
-		const uint64_t s1 = fw_to_stream(canon, k);   // read carries the canonical strand
-		const uint64_t s2 = ~canon & m;               // read carries the other strand (kmer_math.h)
-		const uint64_t ss[2] = { s1, s2 };
-		for (uint64_t s : ss) {
-			const uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
-			uint32_t l0w = 0, l1w = 0, gbit = 0, fw2, fm2;
-			switch (variant) {
-			case 0: {
-				const uint32_t ix = filter_mix(lo, hi) >> fshift;
-				filter[ix >> 5] |= 1u << (ix & 31);
-				break;
-			}
-			case 1: {
-				const uint32_t ix = filter_mix(lo, hi) >> fshift;
-				filter[ix >> 5] |= 1u << (ix & 31);
-				const uint32_t mm = minimizer_of(s, (int)k, kMinimizerM);
-				level1[mm >> 5] |= 1u << (mm & 31);
-				break;
-			}
-			case 2:
-				gate_slots(gate_minimizer_id(s, (int)k), l0w, l1w, gbit);
-				level1[l1w] |= 1u << gbit;
-				level0[l0w] |= 1u << gbit;
-				filter2_slots(filter_mix(lo, hi), fshift, fw2, fm2);
-				filter[fw2] |= fm2;
-				break;
-			default:
-				gate2_slots(gate2_minimizer_id(s, (int)k, gm), gm, l0w, l1w, gbit);
-				level1[l1w] |= 1u << gbit;
-				level0[l0w] |= 1u << gbit;
-				{
-					uint32_t ra, rb;
-					gate2_filter_slots(lo, hi, (int)k, fshift, fw2, ra, rb);
-					filter[fw2] |= (1u << ra) | (1u << rb);
-				}
-				break;
-			}
-		}
-	}
+	const size_t level1_words = variant ? (1ull << (2 * mm_len)) / 32 : 0;
+	const size_t level0_words = variant >= 2 ? kL0Words : 0;
 
 	cudaFree(c->d_filter); cudaFree(c->d_level1); cudaFree(c->d_level0); cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_allele_off); cudaFree(c->d_rows);
 	c->d_level1 = nullptr; c->d_level0 = nullptr; c->d_filter = nullptr; c->d_table = nullptr; c->d_counts = nullptr; c->d_allele_off = nullptr; c->d_rows = nullptr;
-	CU(c, cudaMalloc(&c->d_filter, filter.size() * 4));
+	CU(c, cudaMalloc(&c->d_filter, filter_words * 4));
 	CU(c, cudaMalloc(&c->d_table, cap * sizeof(TableSlot)));
 	CU(c, cudaMalloc(&c->d_counts, std::max<size_t>(1, n_kmers) * 4));
 	CU(c, cudaMalloc(&c->d_allele_off, (2 * (size_t)n_sites + 1) * 4));
 	CU(c, cudaMalloc(&c->d_rows, std::max<size_t>(1, n_sites) * 16));
-	CU(c, cudaMemcpy(c->d_filter, filter.data(), filter.size() * 4, cudaMemcpyHostToDevice));
-	if (!level1.empty()) {
+	if (level1_words) {
 		// gate2 forms probe addresses as {lo32(base) + offset, hi32(base)}: the bitmap must not cross a
 		// 4 GiB line.  cudaMalloc hands out 2 MiB-aligned blocks, so a second try always fits.
 		std::vector<void *> rejected;
 		for (int attempt = 0; attempt < 8; ++attempt) {
-			CU(c, cudaMalloc(&c->d_level1, level1.size() * 4));
-			const uintptr_t a = (uintptr_t)c->d_level1, z = a + level1.size() * 4 - 1;
+			CU(c, cudaMalloc(&c->d_level1, level1_words * 4));
+			const uintptr_t a = (uintptr_t)c->d_level1, z = a + level1_words * 4 - 1;
 			if ((a >> 32) == (z >> 32)) break;
 			rejected.push_back(c->d_level1);
 			c->d_level1 = nullptr;
 		}
 		for (void *r : rejected) cudaFree(r);
 		if (!c->d_level1) return fail(c, NTSM_ERR_CUDA, "could not place the minimizer bitmap inside one 4 GiB window");
-		CU(c, cudaMemcpy(c->d_level1, level1.data(), level1.size() * 4, cudaMemcpyHostToDevice));
 	}
-	if (!level0.empty()) {
-		CU(c, cudaMalloc(&c->d_level0, level0.size() * 4));
-		CU(c, cudaMemcpy(c->d_level0, level0.data(), level0.size() * 4, cudaMemcpyHostToDevice));
+	if (level0_words) {
+		CU(c, cudaMalloc(&c->d_level0, level0_words * 4));
 		CU(c, cudaFuncSetAttribute(count_kernel_gate<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
 		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 13, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
 		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 14, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
@@ -294,10 +235,49 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 14, true, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
 		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 14, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
 	}
+
+	// Build on the device (initCountsHash's insert loop, src/FingerPrint.hpp:506-552, with the host
+	// having applied the first-wins / dupes rules): the hashes go up once, one thread per k-mer
+	// claims a table slot with a 64-bit CAS and sets its bits in the bitmaps with atomicOr.
+	uint64_t *d_hash = nullptr;
+	uint8_t *d_erased = nullptr;
+	int *d_err = nullptr;
+	int h_err[2] = { 0, 0 };
+	cudaStream_t st = c->copy_stream;
+	auto cleanup = [&]() { cudaFree(d_hash); cudaFree(d_erased); cudaFree(d_err); };
+	auto build = [&]() -> int {
+		CU(c, cudaMalloc(&d_hash, std::max<size_t>(1, n_kmers) * 8));
+		CU(c, cudaMalloc(&d_erased, std::max<size_t>(1, n_kmers)));
+		CU(c, cudaMalloc(&d_err, sizeof h_err));
+		CU(c, cudaMemcpyAsync(d_hash, kmer_hash, (size_t)n_kmers * 8, cudaMemcpyHostToDevice, st));
+		if (erased) CU(c, cudaMemcpyAsync(d_erased, erased, n_kmers, cudaMemcpyHostToDevice, st));
+		else CU(c, cudaMemsetAsync(d_erased, 0, std::max<size_t>(1, n_kmers), st));
+		CU(c, cudaMemsetAsync(d_err, 0, sizeof h_err, st));
+		CU(c, cudaMemsetAsync(c->d_table, 0xFF, cap * sizeof(TableSlot), st));          // key = kEmptyKey everywhere
+		CU(c, cudaMemsetAsync(c->d_filter, 0, filter_words * 4, st));
+		if (level1_words) CU(c, cudaMemsetAsync(c->d_level1, 0, level1_words * 4, st));
+		if (level0_words) CU(c, cudaMemsetAsync(c->d_level0, 0, level0_words * 4, st));
+		BuildParams B;
+		B.hash = d_hash; B.erased = d_erased; B.n_kmers = n_kmers; B.k = k; B.variant = variant; B.gate_m = gm;
+		B.table = c->d_table; B.table_mask = (uint32_t)(cap - 1); B.filter = c->d_filter; B.filter_shift = 32 - fbits;
+		B.level1 = c->d_level1; B.level0 = c->d_level0; B.err = d_err;
+		if (n_kmers) {
+			build_tables_kernel<<<(n_kmers + 255) / 256, 256, 0, st>>>(B);
+			CU(c, cudaGetLastError());
+			c->launches++;
+		}
+		CU(c, cudaMemcpyAsync(c->d_allele_off, allele_off, (2 * (size_t)n_sites + 1) * 4, cudaMemcpyHostToDevice, st));
+		CU(c, cudaMemcpyAsync(h_err, d_err, sizeof h_err, cudaMemcpyDeviceToHost, st));
+		CU(c, cudaStreamSynchronize(st));
+		return NTSM_OK;
+	};
+	const int brc = build();
+	cleanup();
+	if (brc) return brc;
+	if (h_err[0] == 1) return fail(c, NTSM_ERR_ARG, "k-mer hash %d out of range for k=%u", h_err[1], k);
+	if (h_err[0] == 2) return fail(c, NTSM_ERR_ARG, "duplicate k-mer hash at index %d", h_err[1]);
 	c->kernel_variant = variant;
 	c->gate_m = gm;
-	CU(c, cudaMemcpy(c->d_table, table.data(), cap * sizeof(TableSlot), cudaMemcpyHostToDevice));
-	CU(c, cudaMemcpy(c->d_allele_off, allele_off, (2 * (size_t)n_sites + 1) * 4, cudaMemcpyHostToDevice));
 	c->n_kmers = n_kmers;
 	c->n_sites = n_sites;
 	c->filter_bits = fbits;

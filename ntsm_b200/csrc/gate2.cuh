@@ -113,6 +113,79 @@ __device__ __forceinline__ uint32_t resolve_one(const CountParams &P, uint32_t l
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// Device-side build of the lookup structures (the insert loop of FingerPrint::initCountsHash,
+// src/FingerPrint.hpp:506-552; the host has already applied first-wins / dupes / -d).  One thread
+// per listed k-mer: claim a slot of the open-addressing table with a 64-bit CAS on the key, then
+// set the k-mer's bits (both read orientations) in the bitmaps the chosen count kernel probes.
+struct BuildParams {
+	const uint64_t *hash;       // [n_kmers] reference hash64 values, dense (site-list) order
+	const uint8_t *erased;      // [n_kmers] 1 = listed but not in the table
+	uint32_t n_kmers, k;
+	int variant, gate_m;
+	TableSlot *table;           // pre-set to 0xFF bytes (key = kEmptyKey)
+	uint32_t table_mask;
+	uint32_t *filter;
+	uint32_t filter_shift;
+	uint32_t *level1, *level0;  // zeroed; nullptr when the variant has none
+	int *err;                   // [0] 0 ok, 1 hash out of range, 2 duplicate; [1] the offending index
+};
+
+__global__ void build_tables_kernel(const BuildParams B)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= B.n_kmers || B.erased[i]) return;
+	const uint64_t m = kmer_mask(B.k);
+	const uint64_t h = B.hash[i];
+	if (h > m) {
+		if (atomicCAS(B.err, 0, 1) == 0) B.err[1] = (int)i;
+		return;
+	}
+	uint32_t slot = (uint32_t)(h ^ (h >> 29)) & B.table_mask;
+	for (;;) {
+		const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&B.table[slot].key), kEmptyKey, h);
+		if (old == kEmptyKey) {
+			B.table[slot].idx = i;
+			break;
+		}
+		if (old == h) {                                            // the host hands over distinct hashes
+			if (atomicCAS(B.err, 0, 2) == 0) B.err[1] = (int)i;
+			return;
+		}
+		slot = (slot + 1) & B.table_mask;
+	}
+	// the canonical k-mer (reference orientation) and the two stream-order spellings a read can show
+	const uint64_t canon = hash64_inv(h, m);
+	const uint64_t ss[2] = { fw_to_stream(canon, B.k), ~canon & m };
+#pragma unroll
+	for (int o = 0; o < 2; ++o) {
+		const uint64_t s = ss[o];
+		const uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
+		uint32_t l0w = 0, l1w = 0, gbit = 0, fw2 = 0, fm2 = 0;
+		if (B.variant <= 1) {
+			const uint32_t ix = filter_mix(lo, hi) >> B.filter_shift;
+			atomicOr(B.filter + (ix >> 5), 1u << (ix & 31));
+			if (B.variant == 1) {
+				const uint32_t mm = minimizer_of(s, (int)B.k, kMinimizerM);
+				atomicOr(B.level1 + (mm >> 5), 1u << (mm & 31));
+			}
+		} else if (B.variant == 2) {
+			gate_slots(gate_minimizer_id(s, (int)B.k), l0w, l1w, gbit);
+			atomicOr(B.level1 + l1w, 1u << gbit);
+			atomicOr(B.level0 + l0w, 1u << gbit);
+			filter2_slots(filter_mix(lo, hi), B.filter_shift, fw2, fm2);
+			atomicOr(B.filter + fw2, fm2);
+		} else {
+			gate2_slots(gate2_minimizer_id(s, (int)B.k, B.gate_m), B.gate_m, l0w, l1w, gbit);
+			atomicOr(B.level1 + l1w, 1u << gbit);
+			atomicOr(B.level0 + l0w, 1u << gbit);
+			uint32_t ra, rb;
+			gate2_filter_slots(lo, hi, (int)B.k, B.filter_shift, fw2, ra, rb);
+			atomicOr(B.filter + fw2, (1u << ra) | (1u << rb));
+		}
+	}
+}
+
 constexpr int kCandSlots = 32;      // candidates one warp hands round per pass of its tail
 
 // Work layout.  A group is 31 chunks (992 positions) handled by lanes 0-30; lane 31 holds the chunk after them,
