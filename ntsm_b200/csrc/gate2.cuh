@@ -175,6 +175,16 @@ __global__ void build_tables_kernel(const BuildParams B)
 			atomicOr(B.level0 + l0w, 1u << gbit);
 			filter2_slots(filter_mix(lo, hi), B.filter_shift, fw2, fm2);
 			atomicOr(B.filter + fw2, fm2);
+		} else if (B.variant == 4) {
+			// seed kernel (seed.cuh): every M-mer of the k-mer, direct index; word = v >> 5, bit = 31 - (v & 31)
+			const uint32_t mm = (uint32_t)((1ull << (2 * B.gate_m)) - 1);
+			for (int j = 0; j + B.gate_m <= (int)B.k; ++j) {
+				const uint32_t v = (uint32_t)(s >> (2 * j)) & mm;
+				atomicOr(B.level1 + (v >> 5), 1u << (31 - (v & 31)));
+			}
+			uint32_t ra, rb;
+			gate2_filter_slots(lo, hi, (int)B.k, B.filter_shift, fw2, ra, rb);
+			atomicOr(B.filter + fw2, (1u << ra) | (1u << rb));
 		} else {
 			gate2_slots(gate2_minimizer_id(s, (int)B.k, B.gate_m), B.gate_m, l0w, l1w, gbit);
 			atomicOr(B.level1 + l1w, 1u << gbit);
@@ -187,6 +197,50 @@ __global__ void build_tables_kernel(const BuildParams B)
 }
 
 constexpr int kCandSlots = 32;      // candidates one warp hands round per pass of its tail
+
+// Tail shared by the gated and the seed kernels: the warp pools its candidate positions (bits of
+// `pass`, one word per lane over the lane's window w[0..3]), lane j takes candidate j, probes the
+// k-mer bitmap (level 2) and resolves survivors through the exact table.
+template <int K>
+__device__ __forceinline__ void pooled_tail(const CountParams &P, const uint32_t (&w)[4], uint32_t pass, uint32_t lane,
+                                            uint16_t *cand, uint32_t wshift, uint32_t &hits)
+{
+	const uint32_t cnt = __popc(pass);
+	uint32_t incl = cnt;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= (uint32_t)d) incl += t;
+	}
+	const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+	uint32_t idx = incl - cnt;                                // slot of this lane's next candidate
+	for (uint32_t r0 = 0; r0 < total; r0 += kCandSlots) {     // warp-uniform trip count, 1 almost always
+		while (pass && idx < r0 + kCandSlots) {
+			uint32_t i;
+			asm("bfind.u32 %0, %1;" : "=r"(i) : "r"(pass));  // highest set bit (one FLO)
+			pass ^= 1u << i;
+			cand[idx - r0] = (uint16_t)((lane << 5) | i);
+			++idx;
+		}
+		__syncwarp();
+		const bool mine = r0 + lane < total;
+		const uint32_t e = mine ? cand[lane] : (lane << 5);
+		const uint32_t src = e >> 5, i = e & 31;
+		const uint32_t y0 = __shfl_sync(0xffffffffu, w[0], src), y1 = __shfl_sync(0xffffffffu, w[1], src);
+		const uint32_t y2 = __shfl_sync(0xffffffffu, w[2], src), y3 = __shfl_sync(0xffffffffu, w[3], src);
+		if (mine) {
+			const bool up = i >= 16;
+			const uint32_t x0 = up ? y1 : y0, x1 = up ? y2 : y1, x2 = up ? y3 : y2;
+			const uint32_t lo = __funnelshift_r(x0, x1, 2 * i), hi = __funnelshift_r(x1, x2, 2 * i);
+			const uint32_t mix = lo * kG2MixA + hi * (kG2MixB << (64 - 2 * K));
+			const uint32_t v = __ldg(P.filter + (mix >> wshift));
+			const uint32_t t = mix * kG2MixC;
+			// level 2: bits (t & 31) and (t >> 5 & 31) of the word both set?
+			if (__funnelshift_r(v, v, t) & __funnelshift_r(v, v, t >> 5) & 1u) hits += resolve_one<K>(P, lo, hi);
+		}
+		__syncwarp();
+	}
+}
 
 // Work layout.  A group is 31 chunks (992 positions) handled by lanes 0-30; lane 31 holds the chunk after them,
 // which is only the halo of lane 30 (a window reaches K-1 <= 30 positions past its start).  That
@@ -320,42 +374,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel_gate2(const CountPara
 			}
 			continue;
 		}
-		// ---- tail: pool the warp's candidates, one lane per candidate ----
-		const uint32_t cnt = __popc(pass);
-		uint32_t incl = cnt;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-			if (lane >= (uint32_t)d) incl += t;
-		}
-		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-		uint32_t idx = incl - cnt;                                // slot of this lane's next candidate
-		for (uint32_t r0 = 0; r0 < total; r0 += kCandSlots) {     // warp-uniform trip count, 1 almost always
-			while (pass && idx < r0 + kCandSlots) {
-				uint32_t i;
-				asm("bfind.u32 %0, %1;" : "=r"(i) : "r"(pass));  // highest set bit (one FLO)
-				pass ^= 1u << i;
-				cand[idx - r0] = (uint16_t)((lane << 5) | i);
-				++idx;
-			}
-			__syncwarp();
-			const bool mine = r0 + lane < total;
-			const uint32_t e = mine ? cand[lane] : (lane << 5);
-			const uint32_t src = e >> 5, i = e & 31;
-			const uint32_t y0 = __shfl_sync(0xffffffffu, w[0], src), y1 = __shfl_sync(0xffffffffu, w[1], src);
-			const uint32_t y2 = __shfl_sync(0xffffffffu, w[2], src), y3 = __shfl_sync(0xffffffffu, w[3], src);
-			if (mine) {
-				const bool up = i >= 16;
-				const uint32_t x0 = up ? y1 : y0, x1 = up ? y2 : y1, x2 = up ? y3 : y2;
-				const uint32_t lo = __funnelshift_r(x0, x1, 2 * i), hi = __funnelshift_r(x1, x2, 2 * i);
-				const uint32_t mix = lo * kG2MixA + hi * (kG2MixB << (64 - 2 * K));
-				const uint32_t v = __ldg(P.filter + (mix >> wshift));
-				const uint32_t t = mix * kG2MixC;
-				// level 2: bits (t & 31) and (t >> 5 & 31) of the word both set?
-				if (__funnelshift_r(v, v, t) & __funnelshift_r(v, v, t >> 5) & 1u) hits += resolve_one<K>(P, lo, hi);
-			}
-			__syncwarp();
-		}
+		pooled_tail<K>(P, w, pass, lane, cand, wshift, hits);
 	}
 	flush_tallies(tk, hits, P.totals);
 }

@@ -57,6 +57,35 @@ __global__ void probe_shared(int iters, uint32_t *out, int words)
 	if (acc == 0x12345678u) out[0] = acc;
 }
 
+// 4. random 4-byte probes into the distributed shared memory of a thread-block cluster: every CTA
+//    holds `words` words, a probe picks (rank, word) at random -> is a cluster-wide bitmap in
+//    DSMEM cheaper per probe than one in L2?
+__global__ void probe_dsmem(int iters, uint32_t *out, uint32_t words, uint32_t cluster_size)
+{
+	extern __shared__ uint32_t s[];
+	for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) s[i] = i * 2654435761u;
+	asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+	const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s);
+	uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+	uint32_t acc = 0;
+	for (int i = 0; i < iters; i += 8) {
+		uint32_t v[8];
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			x = x * 1664525u + 1013904223u;
+			const uint32_t rank = (x >> 24) % cluster_size;
+			const uint32_t local = s_base + 4 * (uint32_t)(((uint64_t)((x >> 4) & 0x0FFFFFFFu) * words) >> 28);
+			uint32_t remote;
+			asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+			asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v[j]) : "r"(remote));
+		}
+#pragma unroll
+		for (int j = 0; j < 8; ++j) acc ^= v[j];
+	}
+	if (acc == 0x12345678u) out[0] = acc;
+	asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+
 static float time_ms(cudaEvent_t a, cudaEvent_t b) { float ms; cudaEventElapsedTime(&ms, a, b); return ms; }
 
 int main(int argc, char **argv)
@@ -107,6 +136,39 @@ int main(int argc, char **argv)
 			}
 			CK(cudaGetLastError());
 			printf("shared random probe %4d KB x%d CTA/SM : %7.1f Gprobe/s\n", words * 4 / 1024, per_sm, (double)blocks * threads * iters / time_ms(e0, e1) / 1e6);
+		}
+	}
+	if (which & 8) {
+		const int iters = 2048;
+		CK(cudaFuncSetAttribute(probe_dsmem, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+		for (int kb : {64, 200}) {
+			const uint32_t words = kb * 256;
+			CK(cudaFuncSetAttribute(probe_dsmem, cudaFuncAttributeMaxDynamicSharedMemorySize, words * 4));
+			for (int threads : {256, 1024}) for (int cs : {1, 2, 4, 8, 16}) {
+				cudaLaunchConfig_t lc = {};
+				cudaLaunchAttribute at[1];
+				at[0].id = cudaLaunchAttributeClusterDimension;
+				at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+				lc.attrs = at; lc.numAttrs = 1;
+				lc.blockDim = dim3(threads); lc.dynamicSmemBytes = words * 4; lc.stream = 0;
+				int nclusters = 0;
+				lc.gridDim = dim3(cs);
+				if (cudaOccupancyMaxActiveClusters(&nclusters, probe_dsmem, &lc) != cudaSuccess || nclusters == 0) {
+					printf("dsmem probe %3d KB/CTA cluster %2d x %4d threads: not launchable (%s)\n", kb, cs, threads, cudaGetErrorString(cudaGetLastError()));
+					continue;
+				}
+				const int blocks = nclusters * cs;
+				lc.gridDim = dim3(blocks);
+				cudaError_t le = cudaSuccess;
+				for (int rep = 0; rep < 2 && le == cudaSuccess; ++rep) {
+					CK(cudaEventRecord(e0));
+					le = cudaLaunchKernelEx(&lc, probe_dsmem, iters, d_out, words, (uint32_t)cs);
+					CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+				}
+				if (le != cudaSuccess) { printf("dsmem launch failed: %s\n", cudaGetErrorString(le)); cudaGetLastError(); continue; }
+				printf("dsmem random probe %3d KB/CTA cluster %2d x %4d threads (%3d CTAs): %7.1f Gprobe/s\n", kb, cs, threads, blocks,
+				       (double)blocks * threads * iters / time_ms(e0, e1) / 1e6);
+			}
 		}
 	}
 	if (which & 4) {
