@@ -306,7 +306,7 @@ def ours(args):
     del genome, codes
     torch.cuda.synchronize()
     a_bases = a_reads * READ_LEN
-    a_pos = a_reads * (READ_LEN + 1)
+    a_pos = a_reads * ((READ_LEN + 8) & ~7)                  # the host packer starts every read at a multiple of 8 positions
     fp_a = ntsm_b200.FingerPrint(sites, device=local, batch_bases=1 << 24, n_buffers=host_threads + 4)
     if world > 1:
         ndist.attach_comm(fp_a)

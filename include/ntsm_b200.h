@@ -20,9 +20,12 @@
  *   [2*(p%16), 2*(p%16)+2) of the little-endian uint32 word bases2[p/16]
  *   (A=0 C=1 G=2 T/U=3, decoded with the reference table vendor/KseqHashIterator.hpp:114-127)
  *   and an invalid flag in bit (p%32) of nmask[p/32] (1 = the byte decoded to 4, i.e. "N").
- *   Reads are laid end to end with exactly one invalid separator position after each read,
- *   so no k-mer window can span two reads.  read_off[r] is the position of read r's first
- *   base (read_off[n_reads] = end).  The tail is padded with invalid positions up to
+ *   Reads are laid end to end with at least one invalid position after each read, so no k-mer
+ *   window can span two reads.  The library's own packers start every read at a multiple of 8
+ *   positions (a read of n bases occupies (n + 8) & ~7 positions: bases, separator, padding) so
+ *   that both planes are byte-granular per read; streams handed to ntsm_count_packed_* only
+ *   need the one separator.  read_off[r] is the position of read r's first base
+ *   (read_off[n_reads] = end).  The tail is padded with invalid positions up to
  *   ntsm_padded_positions(n_pos).
  */
 #ifndef NTSM_B200_H
@@ -120,7 +123,7 @@ int ntsm_submit_batch(ntsm_ctx *ctx, ntsm_batch *b);
 int ntsm_release_batch(ntsm_ctx *ctx, ntsm_batch *b);
 
 /* standalone packer with the same layout (no ctx): packs n_reads reads buf[off[r]..off[r+1])
- * into caller memory sized for ntsm_padded_positions(sum(len)+n_reads). Returns n_pos. */
+ * into caller memory sized for ntsm_padded_positions(sum((len + 8) & ~7)). Returns n_pos. */
 /* which decode+pack implementation the host uses: "avx512vbmi", "avx2" or "scalar" (picked from the
  * CPU at load time).  force: NULL = just ask; "" = back to automatic; a name = use it if the CPU can. */
 const char *ntsm_pack_isa(const char *force);

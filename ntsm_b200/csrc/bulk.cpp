@@ -58,9 +58,9 @@ void producer(Bulk &bk)
 int run(Bulk &bk, uint32_t threads, uint64_t total_bases)
 {
 	if (bk.n_reads == 0) return NTSM_OK;
-	// size blocks so that a block fills about one batch (bases + one separator per read)
+	// size blocks so that a block fills about one batch
 	const uint64_t cap = ntsm_ctx_batch_bases(bk.ctxs[0]);
-	const uint64_t avg = std::max<uint64_t>(1, total_bases / bk.n_reads) + 1;
+	const uint64_t avg = total_bases / bk.n_reads + 8;               // a read spans its bases + separator, rounded up to 8 positions
 	bk.reads_per_block = std::max<uint64_t>(1, (cap - cap / 64) / avg);
 	const uint64_t n_blocks = (bk.n_reads + bk.reads_per_block - 1) / bk.reads_per_block;
 	uint32_t nt = threads ? threads : 1;

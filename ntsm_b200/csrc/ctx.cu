@@ -406,7 +406,7 @@ static int make_batch(ntsm_ctx *c, ntsm_batch **out)
 {
 	ntsm_batch *b = new ntsm_batch();
 	b->ctx = c;
-	b->cap_pos = c->cfg.batch_bases;
+	b->cap_pos = c->cfg.batch_bases & ~(kReadAlign - 1);
 	const uint64_t padded = padded_positions(b->cap_pos);
 	CU(c, cudaMallocHost(&b->h_bases, padded / 32 * 8));
 	CU(c, cudaMallocHost(&b->h_mask, padded / 32 * 4));
@@ -473,8 +473,8 @@ extern "C" int ntsm_batch_append(ntsm_batch *b, const char *seq, uint64_t len, u
 	const uint64_t from = *pos >= (uint64_t)(k - 1) ? *pos - (k - 1) : 0;
 	const uint64_t start = *pos == 0 ? 0 : from;
 	const uint64_t need = len - start;
-	const uint64_t room = b->cap_pos - b->pk.pos;       // positions left, including the separator
-	if (need + 1 <= room) {
+	const uint64_t room = b->cap_pos - b->pk.pos;       // positions left (a multiple of 8, like every read's span)
+	if (read_span(need) <= room) {
 		b->pk.put_read(seq + start, need);
 		b->n_bases += len - *pos;
 		b->n_reads += (*pos == 0);
@@ -483,7 +483,7 @@ extern "C" int ntsm_batch_append(ntsm_batch *b, const char *seq, uint64_t len, u
 	}
 	const uint64_t split_min = std::max<uint64_t>(2 * k, std::min<uint64_t>(4096, b->cap_pos / 4));
 	if (b->pk.pos != 0 && room < split_min + 1) return 0;   // full: submit and come back
-	const uint64_t take = room - 1;                          // >= 2k > k-1, so the read always advances
+	const uint64_t take = room - 1;                          // spans exactly `room`; >= 2k > k-1, so the read always advances
 	b->pk.put_read(seq + start, take);
 	b->n_bases += start + take - *pos;
 	b->n_reads += (*pos == 0);

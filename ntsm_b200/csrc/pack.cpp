@@ -20,38 +20,32 @@ struct CodeTableInit {
 static const CodeTableInit g_code_init;
 const uint8_t *code_table() { return g_code_init.t; }
 
-static inline void pack32_scalar(const char *s, unsigned n, uint64_t *b, uint32_t *m)
+// One read of n bytes appended at dst.pos (a multiple of 8): its bases, then invalid positions up to
+// read_span(n).  Three implementations of the same function, picked once at start-up: AVX-512 VBMI
+// (64 bases per step: one byte permute through the 128-entry decode table, two multiply-adds to
+// squeeze four codes into a byte), AVX2+BMI2 (32 per step: compares, pdep to interleave the
+// bit-planes), scalar table walk.  All write whole groups; whatever a group covers beyond the
+// read's span is invalid and is overwritten by the next read or by finish().
+static void run_scalar(Packer &dst, const char *s, uint64_t n)
 {
 	const uint8_t *t = g_code_init.t;
-	uint64_t bb = 0;
-	uint32_t mm = 0;
-	for (unsigned j = 0; j < n; ++j) {
-		const unsigned c = t[(unsigned char)s[j]];
-		bb |= (uint64_t)(c & 3) << (2 * j);
-		mm |= (uint32_t)(c >> 2) << j;
+	uint8_t *ob = reinterpret_cast<uint8_t *>(dst.bases) + dst.pos / 4;
+	uint8_t *om = reinterpret_cast<uint8_t *>(dst.mask) + dst.pos / 8;
+	const uint64_t span = read_span(n);
+	for (uint64_t i = 0; i < span; i += 8) {
+		unsigned bb = 0, mm = 0;
+		for (unsigned j = 0; j < 8; ++j) {
+			const unsigned c = i + j < n ? t[(unsigned char)s[i + j]] : 4u;
+			bb |= (c & 3) << (2 * j);
+			mm |= (c >> 2) << j;
+		}
+		ob[0] = (uint8_t)bb;
+		ob[1] = (uint8_t)(bb >> 8);
+		om[0] = (uint8_t)mm;
+		ob += 2;
+		om += 1;
 	}
-	*b = bb;
-	*m = mm;
-}
-
-// One run of n bytes (+ the separator position when sep) appended to the stream.  Three
-// implementations of the same function, picked once at start-up: AVX-512 VBMI (64 bases per
-// step: one byte permute through the 128-entry decode table), AVX2+BMI2 (32 per step: compares),
-// scalar table walk.  The interleave of the two code bit-planes into 2-bit fields is pdep.
-static void run_scalar(Packer &dst, const char *s, uint64_t n, bool sep)
-{
-	Packer p = dst;          // local copy: stores into the stream cannot alias the accumulators
-	uint64_t i = 0, b;
-	uint32_t m;
-	for (; i + 32 <= n; i += 32) {
-		pack32_scalar(s + i, 32, &b, &m);
-		p.put_group(b, m, 32);
-	}
-	const unsigned r = (unsigned)(n - i);
-	pack32_scalar(s + i, r, &b, &m);
-	if (sep) m |= 1u << r;
-	if (r + sep) p.put_group(b, m, r + sep);
-	dst = p;
+	dst.pos += span;
 }
 
 #if defined(__x86_64__)
@@ -77,20 +71,23 @@ NTSM_TGT_AVX2 static inline void planes32_avx2(__m256i v, uint32_t *bit0, uint32
 	    _mm256_or_si256(_mm256_or_si256(_mm256_or_si256(isA, isC), _mm256_or_si256(isG, isT)), isRaw));
 }
 
-NTSM_TGT_AVX2 static void run_avx2(Packer &dst, const char *s, uint64_t n, bool sep)
+NTSM_TGT_AVX2 static void run_avx2(Packer &dst, const char *s, uint64_t n)
 {
-	Packer p = dst;          // local copy: stores into the stream cannot alias the accumulators
 	const uint64_t kEven = 0x5555555555555555ULL, kOdd = 0xAAAAAAAAAAAAAAAAULL;
+	uint8_t *ob = reinterpret_cast<uint8_t *>(dst.bases) + dst.pos / 4;
+	uint8_t *om = reinterpret_cast<uint8_t *>(dst.mask) + dst.pos / 8;
 	uint64_t i = 0;
 	uint32_t b0, b1, va;
-	for (; i + 32 <= n; i += 32) {
+	for (; i + 32 <= n; i += 32, ob += 8, om += 4) {
 		planes32_avx2(_mm256_loadu_si256((const __m256i *)(s + i)), &b0, &b1, &va);
-		p.put_group(_pdep_u64(b0, kEven) | _pdep_u64(b1, kOdd), ~va, 32);
+		const uint64_t bb = _pdep_u64(b0, kEven) | _pdep_u64(b1, kOdd);
+		const uint32_t mm = ~va;
+		memcpy(ob, &bb, 8);
+		memcpy(om, &mm, 4);
 	}
-	const unsigned r = (unsigned)(n - i);           // 0..31 bytes left; the separator rides in the same group
-	if (r + sep == 0) { dst = p; return; }
+	const unsigned r = (unsigned)(n - i);           // 0..31 bases left; the separator and the padding ride in the same group
 	// A 32-byte load that stays inside the 4 KiB page of its first byte cannot fault, so the bytes
-	// after the run are read and masked off; only a load that would cross a page is bounced.
+	// after the read are loaded and masked off; only a load that would cross a page is bounced.
 	__m256i v = _mm256_setzero_si256();
 	if (r) {
 		if (((uintptr_t)(s + i) & 4095u) <= 4096u - 32u) {
@@ -102,9 +99,12 @@ NTSM_TGT_AVX2 static void run_avx2(Packer &dst, const char *s, uint64_t n, bool 
 		}
 	}
 	planes32_avx2(v, &b0, &b1, &va);
-	const uint32_t keep = (1u << r) - 1;
-	p.put_group(_pdep_u64(b0 & keep, kEven) | _pdep_u64(b1 & keep, kOdd), (~va & keep) | ((uint32_t)sep << r), r + sep);
-	dst = p;
+	const uint32_t keep = (uint32_t)((1ull << r) - 1);
+	const uint64_t bb = _pdep_u64(b0 & keep, kEven) | _pdep_u64(b1 & keep, kOdd);
+	const uint32_t mm = ~(va & keep);               // everything from the separator on is invalid
+	memcpy(ob, &bb, 8);
+	memcpy(om, &mm, 4);
+	dst.pos += read_span(n);
 }
 
 struct alignas(64) Vbmi128 {
@@ -113,48 +113,42 @@ struct alignas(64) Vbmi128 {
 };
 static const Vbmi128 g_vbmi_tab;
 
-NTSM_TGT_AVX512 static inline void planes64_avx512(__m512i v, __m512i tab_lo, __m512i tab_hi, uint64_t *bit0, uint64_t *bit1,
-                                                  uint64_t *inv)
+// 64 ASCII bytes -> 16 bytes of 2-bit codes (four positions per byte) + 64 invalid flags
+NTSM_TGT_AVX512 static inline __m128i pack64_avx512(__m512i v, __m512i tab_lo, __m512i tab_hi, uint64_t *inv)
 {
 	// index bits 0-6 pick one of 128 table bytes (bit 7 is ignored by the permute); bytes >= 0x80
 	// are never bases, their own sign bit marks them invalid
 	const __m512i code = _mm512_permutex2var_epi8(tab_lo, v, tab_hi);
-	const uint64_t bad = (uint64_t)_mm512_movepi8_mask(_mm512_or_si512(code, v));
-	*bit0 = _mm512_test_epi8_mask(code, _mm512_set1_epi8(1)) & ~bad;     // 0x81 would otherwise decode like 0x01
-	*bit1 = _mm512_test_epi8_mask(code, _mm512_set1_epi8(2)) & ~bad;
-	*inv = bad;
+	const __mmask64 bad = _mm512_movepi8_mask(_mm512_or_si512(code, v));
+	const __m512i c = _mm512_maskz_mov_epi8(~bad, code);                                  // invalid positions carry code 0
+	const __m512i t16 = _mm512_maddubs_epi16(c, _mm512_set1_epi16(0x0401));               // c0 + 4 c1 per 16-bit lane
+	const __m512i t32 = _mm512_madd_epi16(t16, _mm512_set1_epi32(0x00100001));            // + 16 (c2 + 4 c3) per 32-bit lane
+	*inv = (uint64_t)bad;
+	return _mm512_cvtepi32_epi8(t32);
 }
 
-NTSM_TGT_AVX512 static void run_avx512(Packer &dst, const char *s, uint64_t n, bool sep)
+NTSM_TGT_AVX512 static void run_avx512(Packer &dst, const char *s, uint64_t n)
 {
-	Packer p = dst;          // local copy: stores into the stream cannot alias the accumulators
-	const uint64_t kEven = 0x5555555555555555ULL, kOdd = 0xAAAAAAAAAAAAAAAAULL;
 	const __m512i tab_lo = _mm512_load_si512(g_vbmi_tab.t), tab_hi = _mm512_load_si512(g_vbmi_tab.t + 64);
-	uint64_t i = 0, b0, b1, iv;
-	for (; i + 64 <= n; i += 64) {
-		planes64_avx512(_mm512_loadu_si512(s + i), tab_lo, tab_hi, &b0, &b1, &iv);
-		p.put_group(_pdep_u64(b0, kEven) | _pdep_u64(b1, kOdd), (uint32_t)iv, 32);
-		p.put_group(_pdep_u64(b0 >> 32, kEven) | _pdep_u64(b1 >> 32, kOdd), (uint32_t)(iv >> 32), 32);
+	uint8_t *ob = reinterpret_cast<uint8_t *>(dst.bases) + dst.pos / 4;
+	uint8_t *om = reinterpret_cast<uint8_t *>(dst.mask) + dst.pos / 8;
+	uint64_t i = 0, iv;
+	for (; i + 64 <= n; i += 64, ob += 16, om += 8) {
+		const __m128i bb = pack64_avx512(_mm512_loadu_si512(s + i), tab_lo, tab_hi, &iv);
+		_mm_storeu_si128((__m128i *)ob, bb);
+		memcpy(om, &iv, 8);
 	}
-	const unsigned r = (unsigned)(n - i);           // 0..63 bytes left
-	const unsigned total = r + sep;
-	if (total == 0) { dst = p; return; }
+	const unsigned r = (unsigned)(n - i);           // 0..63 bases left
 	const uint64_t keep = (1ull << r) - 1;          // a masked load never touches (or faults on) the bytes it skips
-	planes64_avx512(_mm512_maskz_loadu_epi8((__mmask64)keep, s + i), tab_lo, tab_hi, &b0, &b1, &iv);
-	b0 &= keep;
-	b1 &= keep;
-	iv = (iv & keep) | ((uint64_t)sep << r);
-	if (total <= 32) {
-		p.put_group(_pdep_u64(b0, kEven) | _pdep_u64(b1, kOdd), (uint32_t)iv, total);
-	} else {
-		p.put_group(_pdep_u64(b0, kEven) | _pdep_u64(b1, kOdd), (uint32_t)iv, 32);
-		p.put_group(_pdep_u64(b0 >> 32, kEven) | _pdep_u64(b1 >> 32, kOdd), (uint32_t)(iv >> 32), total - 32);
-	}
-	dst = p;
+	const __m128i bb = pack64_avx512(_mm512_maskz_loadu_epi8((__mmask64)keep, s + i), tab_lo, tab_hi, &iv);
+	iv |= ~keep;                                    // byte 0 decodes as 'A': everything from the separator on is invalid
+	_mm_storeu_si128((__m128i *)ob, bb);          // skipped bytes loaded as 0 = code 0
+	memcpy(om, &iv, 8);
+	dst.pos += read_span(n);
 }
 #endif
 
-typedef void (*RunFn)(Packer &, const char *, uint64_t, bool);
+typedef void (*RunFn)(Packer &, const char *, uint64_t);
 static RunFn pick_run()
 {
 	const char *force = getenv("NTSM_PACK_ISA");        // "scalar" | "avx2" | "avx512": tests walk all three
@@ -186,18 +180,14 @@ const char *pack_isa()
 }
 void pack_reselect() { g_run = pick_run(); }
 
-void Packer::put_bases(const char *s, uint64_t n) { g_run(*this, s, n, false); }
-void Packer::put_read(const char *s, uint64_t n) { g_run(*this, s, n, true); }
+void Packer::put_read(const char *s, uint64_t n) { g_run(*this, s, n); }
 
 uint64_t Packer::finish()
 {
-	const uint64_t n = pos;
+	const uint64_t n = pos;                       // a multiple of 8: both planes end on a byte
 	const uint64_t end = padded_positions(n);
-	while (pos & 31) put_code(4);
-	for (uint64_t w = pos >> 5; w < end >> 5; ++w) {
-		bases[w] = 0;
-		mask[w] = 0xFFFFFFFFu;
-	}
+	memset(reinterpret_cast<uint8_t *>(bases) + n / 4, 0, (end - n) / 4);
+	memset(reinterpret_cast<uint8_t *>(mask) + n / 8, 0xFF, (end - n) / 8);
 	pos = end;
 	return n;
 }

@@ -75,7 +75,7 @@ def pack_reads(reads):
     buf = b"".join(reads)
     off = np.zeros(len(reads) + 1, np.uint64)
     np.cumsum([len(r) for r in reads], out=off[1:])
-    n_pos_max = len(buf) + len(reads)
+    n_pos_max = sum((len(r) + 8) & ~7 for r in reads)        # bases + separator, rounded up to 8 positions per read
     padded = L.ntsm_padded_positions(n_pos_max)
     bases = np.zeros(padded // 16, np.uint32)
     mask = np.zeros(padded // 32, np.uint32)

@@ -350,3 +350,39 @@ def test_cfg3_ont_like_long_reads_vs_oracle(oracle):
         reads.append(revcomp(r.encode()) if rng.random() < 0.5 else r.encode())
     assert max(map(len, reads)) > 50000
     _check_against_oracle(oracle, PANEL, reads, batch_bases=1 << 16)
+
+
+# ---------------------------------------------------------------- kernel variants
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4"])
+def test_every_k19_kernel_variant_vs_oracle(oracle, monkeypatch, variant):
+    """NTSM_KERNEL picks the k = 19 count kernel (0 plain, 1 minimizer, 2 gated, 3 gate2, 4 strided
+    seeds = default): each must give the oracle's per-k-mer counters on the same reads."""
+    monkeypatch.setenv("NTSM_KERNEL", variant)
+    rng = random.Random(1900 + int(variant))
+    wins = _windows(PANEL, limit=8000)
+    reads = _reads(rng, wins, 6000, "ACGTN") + [bytes(rng.choice(b"ACGT") for _ in range(rng.randrange(0, 400))) for _ in range(2000)]
+    _check_against_oracle(oracle, PANEL, reads, batch_bases=1 << 18)
+
+
+def test_seed_kernel_dense_hits_and_every_phase(oracle):
+    """Stress for count_kernel_seed (seed.cuh): reads that are nothing but site windows back to back
+    (nearly every seed marked, so the pooled tail runs several rounds per warp), read lengths that
+    walk the read starts through every chunk phase and lane, N runs right before and after the
+    seed positions, and batches of odd sizes so the last group is ragged."""
+    rng = random.Random(77)
+    wins = _windows(PANEL, limit=6000)
+    reads = []
+    for n in range(2500):
+        parts = [rng.choice(wins) for _ in range(rng.randrange(1, 8))]
+        r = "".join(parts)
+        if n % 3 == 0:                      # an N every few bases around a window boundary
+            p = rng.randrange(len(r))
+            r = r[:p] + "N" * rng.randrange(1, 7) + r[p:]
+        if n % 5 == 0:
+            r = r[rng.randrange(0, 6):]
+        r = r.encode()
+        reads.append(revcomp(r) if rng.random() < 0.5 else r)
+    reads += [wins[i % len(wins)][: 19 + i % 13].encode() for i in range(600)]        # 19..31-base reads: 1..13 windows each
+    for bb in (1 << 12, 40001, 1 << 20):
+        ofp = _check_against_oracle(oracle, PANEL, reads, batch_bases=bb, n_buffers=3)
+    assert ofp.total_counts > 3 * len(reads)

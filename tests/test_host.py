@@ -183,7 +183,7 @@ def _py_pack(reads, nt4):
     codes = []
     for r in reads:
         codes.extend(nt4(b) for b in r)
-        codes.append(4)
+        codes.extend([4] * (((len(r) + 8) & ~7) - len(r)))        # separator + padding to a multiple of 8
     n = len(codes)
     padded = (n + 8191) // 8192 * 8192 + 64
     codes += [4] * (padded - n)
@@ -201,9 +201,9 @@ def test_packer_layout(L, oracle):
                  for _ in range(rng.randrange(1, 30))]
         b2, mk, n_pos, roff = ntsm_b200.pack_reads(reads)
         wb, wm, wn = _py_pack(reads, oracle.nt4)
-        assert n_pos == wn == sum(len(r) + 1 for r in reads)
+        assert n_pos == wn == sum((len(r) + 8) & ~7 for r in reads)
         assert np.array_equal(b2[:len(wb)], wb) and np.array_equal(mk[:len(wm)], wm)
-        assert list(roff[:-1]) == list(np.cumsum([0] + [len(r) + 1 for r in reads])[:-1])
+        assert list(roff[:-1]) == list(np.cumsum([0] + [(len(r) + 8) & ~7 for r in reads])[:-1])
 
 
 def test_packer_isa_variants_agree(L):
@@ -242,10 +242,10 @@ def test_packer_reads_nothing_past_a_page_edge(L):
                 read = bytes(b"ACGTN"[i % 5] for i in range(n))
                 C.memmove(base + 4096 - n, read, n)
                 off = np.array([0, n], np.uint64)
-                padded = L.ntsm_padded_positions(n + 1)
+                padded = L.ntsm_padded_positions((n + 8) & ~7)
                 b2 = np.zeros(padded // 16, np.uint32)
                 mk = np.zeros(padded // 32, np.uint32)
-                assert L.ntsm_pack_reads(base + 4096 - n, off.ctypes.data, 1, b2.ctypes.data, mk.ctypes.data, None) == n + 1
+                assert L.ntsm_pack_reads(base + 4096 - n, off.ctypes.data, 1, b2.ctypes.data, mk.ctypes.data, None) == (n + 8) & ~7
                 wb, wm, _, _ = ntsm_b200.pack_reads([read])
                 assert np.array_equal(b2, wb) and np.array_equal(mk, wm), (isa, n)
     finally:
