@@ -20,6 +20,7 @@
 #include "kernels.cuh"
 #include "gate2.cuh"
 #include "seed.cuh"
+#include "pair.cuh"
 #include "pack.h"
 
 using namespace ntsm;
@@ -50,7 +51,7 @@ struct ntsm_ctx {
 	uint32_t *d_filter = nullptr;
 	uint32_t *d_level1 = nullptr;           // 4^M-bit minimizer bitmap of the k = 19 kernels (layout per variant)
 	uint32_t *d_level0 = nullptr;           // image of the gated kernels' shared-memory level-0 bitmap
-	int kernel_variant = 4;                 // k = 19: 0 plain, 1 minimizer, 2 smem-gated minimizer, 3 gate2, 4 strided seeds (default)
+	int kernel_variant = 5;                 // k = 19: 0 plain, 1 minimizer, 2 smem-gated minimizer, 3 gate2, 4 strided seeds, 5 paired seeds (default)
 	int seed_cfg = 1;                       // seed kernel launch shape (NTSM_SEED_CFG): 0 = 1024x1, 1 = 1024x2 (default), 2 = 512x4, 3 = 256x8
 	int gate_m = 14;                        // M-mer length of gate2 (13 or 14)
 	int gate_threads = 1024;                // gate2 CTA size (NTSM_GATE_THREADS: 512 / 768 / 1024)
@@ -189,11 +190,11 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 
 	// which count kernel will run decides which pre-filter structures are built (NTSM_KERNEL / NTSM_GATE_M
 	// are measurement knobs: every variant gives the same counts)
-	int variant = k == 19 ? 4 : 0, gm = 14;
+	int variant = k == 19 ? 5 : 0, gm = 14;
 	if (const char *e = getenv("NTSM_KERNEL")) variant = atoi(e);
 	if (const char *e = getenv("NTSM_GATE_M")) gm = atoi(e);
-	if (k != 19 || variant < 0 || variant > 4) variant = 0;
-	if (gm < 13 || gm > 14 || variant == 4) gm = 14;
+	if (k != 19 || variant < 0 || variant > 5) variant = 0;
+	if (gm < 13 || gm > 14 || variant >= 4) gm = 14;
 	if (const char *e = getenv("NTSM_SEED_CFG")) c->seed_cfg = std::min(3, std::max(0, atoi(e)));
 	if (const char *e = getenv("NTSM_TAIL_POOL")) c->pool_tail = atoi(e) != 0;
 	if (const char *e = getenv("NTSM_GATE_THREADS")) c->gate_threads = atoi(e);
@@ -205,7 +206,7 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 	const size_t filter_words = (1ull << fbits) / 32;                 // layout depends on the variant
 	// minimizer bitmaps: level 1 = 4^M bits in global memory, level 0 = image of the shared-memory bitmap
 	const int mm_len = variant == 1 ? kMinimizerM : variant == 2 ? kGateM : gm;
-	const size_t level1_words = variant ? (1ull << (2 * mm_len)) / 32 : 0;
+	const size_t level1_words = variant == 5 ? kPairWords : variant ? (1ull << (2 * mm_len)) / 32 : 0;
 	const size_t level0_words = variant == 2 || variant == 3 ? kL0Words : 0;
 
 	cudaFree(c->d_filter); cudaFree(c->d_level1); cudaFree(c->d_level0); cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_allele_off); cudaFree(c->d_rows);
@@ -358,14 +359,19 @@ static int launch_count(ntsm_ctx *c, const uint2 *d_bases, const uint32_t *d_mas
 	const uint64_t tiles = (P.n_chunks + kCountThreads - 1) / kCountThreads;
 	const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)c->sm_count * 16);
 	const unsigned g2 = (unsigned)std::min<uint64_t>((P.n_chunks + kGateThreads - 1) / kGateThreads, (uint64_t)c->sm_count);
-	if (c->cfg.k == 19 && c->kernel_variant == 4) {
+	if (c->cfg.k == 19 && c->kernel_variant >= 4) {
 		// persistent: MINB CTAs per SM (fewer when the batch has fewer 31-chunk groups than that many CTAs have warps)
 		const uint64_t groups = (P.n_chunks + kGroupChunks - 1) / kGroupChunks;
 		static const int shape[4][2] = { { 1024, 1 }, { 1024, 2 }, { 512, 4 }, { 256, 8 } };
 		const int th = shape[c->seed_cfg][0], mb = shape[c->seed_cfg][1];
 		const uint64_t wpc = th / 32;
 		const unsigned gs = (unsigned)std::min<uint64_t>((groups + wpc - 1) / wpc, (uint64_t)c->sm_count * mb);
-		if (c->seed_cfg == 1) count_kernel_seed<19, kSeedM, 1024, 2><<<gs, 1024, 0, st>>>(P);
+		if (c->kernel_variant == 5) {
+			if (c->seed_cfg == 1) count_kernel_pair<19, 1024, 2><<<gs, 1024, 0, st>>>(P);
+			else if (c->seed_cfg == 2) count_kernel_pair<19, 512, 4><<<gs, 512, 0, st>>>(P);
+			else if (c->seed_cfg == 3) count_kernel_pair<19, 256, 8><<<gs, 256, 0, st>>>(P);
+			else count_kernel_pair<19, 1024, 1><<<gs, 1024, 0, st>>>(P);
+		} else if (c->seed_cfg == 1) count_kernel_seed<19, kSeedM, 1024, 2><<<gs, 1024, 0, st>>>(P);
 		else if (c->seed_cfg == 2) count_kernel_seed<19, kSeedM, 512, 4><<<gs, 512, 0, st>>>(P);
 		else if (c->seed_cfg == 3) count_kernel_seed<19, kSeedM, 256, 8><<<gs, 256, 0, st>>>(P);
 		else count_kernel_seed<19, kSeedM, 1024, 1><<<gs, 1024, 0, st>>>(P);
@@ -734,6 +740,10 @@ extern "C" const char *ntsm_ctx_kernel_name(const ntsm_ctx *c)
 	if (c->cfg.k != 19 || c->kernel_variant == 0) return c->cfg.k == 19 ? "count_kernel<19>" : "count_kernel<0>";
 	if (c->kernel_variant == 1) return "count_kernel_min<19,13>";
 	if (c->kernel_variant == 2) return "count_kernel_gate<19>";
+	if (c->kernel_variant == 5) {
+		static const char *names[4] = { "count_kernel_pair<19,1024,1>", "count_kernel_pair<19,1024,2>", "count_kernel_pair<19,512,4>", "count_kernel_pair<19,256,8>" };
+		return names[c->seed_cfg];
+	}
 	if (c->kernel_variant == 4) {
 		static const char *names[4] = { "count_kernel_seed<19,14,1024,1>", "count_kernel_seed<19,14,1024,2>", "count_kernel_seed<19,14,512,4>", "count_kernel_seed<19,14,256,8>" };
 		return names[c->seed_cfg];

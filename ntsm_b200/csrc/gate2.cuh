@@ -185,6 +185,16 @@ __global__ void build_tables_kernel(const BuildParams B)
 			uint32_t ra, rb;
 			gate2_filter_slots(lo, hi, (int)B.k, B.filter_shift, fw2, ra, rb);
 			atomicOr(B.filter + fw2, (1u << ra) | (1u << rb));
+		} else if (B.variant == 5) {
+			// paired-seed kernel (pair.cuh): every 14-mer of the k-mer entered once per role (pair_slots)
+			for (int j = 0; j + 14 <= (int)B.k; ++j) {
+				const uint32_t v = (uint32_t)(s >> (2 * j)) & 0x0FFFFFFFu;
+				atomicOr(B.level1 + (v >> 4), 1u << (v & 15));
+				atomicOr(B.level1 + (v & 0xFFFFFFu), 1u << (16 + (v >> 24)));
+			}
+			uint32_t ra, rb;
+			gate2_filter_slots(lo, hi, (int)B.k, B.filter_shift, fw2, ra, rb);
+			atomicOr(B.filter + fw2, (1u << ra) | (1u << rb));
 		} else {
 			gate2_slots(gate2_minimizer_id(s, (int)B.k, B.gate_m), B.gate_m, l0w, l1w, gbit);
 			atomicOr(B.level1 + l1w, 1u << gbit);

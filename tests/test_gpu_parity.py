@@ -353,10 +353,10 @@ def test_cfg3_ont_like_long_reads_vs_oracle(oracle):
 
 
 # ---------------------------------------------------------------- kernel variants
-@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4"])
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4", "5"])
 def test_every_k19_kernel_variant_vs_oracle(oracle, monkeypatch, variant):
     """NTSM_KERNEL picks the k = 19 count kernel (0 plain, 1 minimizer, 2 gated, 3 gate2, 4 strided
-    seeds = default): each must give the oracle's per-k-mer counters on the same reads."""
+    seeds, 5 paired seeds = default): each must give the oracle's per-k-mer counters on the same reads."""
     monkeypatch.setenv("NTSM_KERNEL", variant)
     rng = random.Random(1900 + int(variant))
     wins = _windows(PANEL, limit=8000)
@@ -364,11 +364,13 @@ def test_every_k19_kernel_variant_vs_oracle(oracle, monkeypatch, variant):
     _check_against_oracle(oracle, PANEL, reads, batch_bases=1 << 18)
 
 
-def test_seed_kernel_dense_hits_and_every_phase(oracle):
-    """Stress for count_kernel_seed (seed.cuh): reads that are nothing but site windows back to back
+@pytest.mark.parametrize("variant", ["4", "5"])
+def test_seed_kernel_dense_hits_and_every_phase(oracle, monkeypatch, variant):
+    """Stress for count_kernel_seed (seed.cuh) and count_kernel_pair (pair.cuh): reads that are nothing but site windows back to back
     (nearly every seed marked, so the pooled tail runs several rounds per warp), read lengths that
     walk the read starts through every chunk phase and lane, N runs right before and after the
     seed positions, and batches of odd sizes so the last group is ragged."""
+    monkeypatch.setenv("NTSM_KERNEL", variant)
     rng = random.Random(77)
     wins = _windows(PANEL, limit=6000)
     reads = []

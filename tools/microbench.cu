@@ -42,6 +42,26 @@ __global__ void probe_global_grouped(const uint32_t *__restrict__ t, uint32_t ma
 	if (acc == 0x12345678u) out[0] = acc;
 }
 
+// line-local: groups of g lanes probe g DIFFERENT 32-byte sectors of the same 128-byte line (32 sectors but only
+// 32/g lines per warp instruction) -> is the L1->L2 wall counted in sectors or in line requests?
+__global__ void probe_global_line(const uint32_t *__restrict__ t, uint32_t mask, int iters, int group, uint32_t *out)
+{
+	const int lane = threadIdx.x & 31;
+	uint32_t x = ((blockIdx.x * blockDim.x + threadIdx.x) / group) * 2654435761u + 12345u;
+	uint32_t acc = 0;
+	for (int i = 0; i < iters; i += 8) {
+		uint32_t v[8];
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			x = x * 1664525u + 1013904223u;
+			v[j] = __ldg(t + ((((x >> 4) & mask) & ~31u) | ((uint32_t)(lane % group) << 3) | ((x >> 1) & 7u)));
+		}
+#pragma unroll
+		for (int j = 0; j < 8; ++j) acc ^= v[j];
+	}
+	if (acc == 0x12345678u) out[0] = acc;
+}
+
 __global__ void probe_shared(int iters, uint32_t *out, int words)
 {
 	extern __shared__ uint32_t s[];
@@ -136,6 +156,25 @@ int main(int argc, char **argv)
 			}
 			CK(cudaGetLastError());
 			printf("shared random probe %4d KB x%d CTA/SM : %7.1f Gprobe/s\n", words * 4 / 1024, per_sm, (double)blocks * threads * iters / time_ms(e0, e1) / 1e6);
+		}
+	}
+	if (which & 16) {
+		const int iters = 512, threads = 256, blocks = prop.multiProcessorCount * 8;
+		for (size_t mb : {32, 64}) {
+			size_t bytes = mb << 20;
+			uint32_t *t; CK(cudaMalloc(&t, bytes)); CK(cudaMemset(t, 1, bytes));
+			const uint32_t mask = (uint32_t)(bytes / 4 - 1);
+			const double n = (double)blocks * threads * iters;
+			for (int group : {1, 2, 4}) {
+				for (int rep = 0; rep < 2; ++rep) {
+					CK(cudaEventRecord(e0));
+					probe_global_line<<<blocks, threads>>>(t, mask, iters, group, d_out);
+					CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+				}
+				printf("global line-grouped probe T=%3zu MB, %d sectors of one line per %d lanes (%2d lines, 32 sectors per warp-load): %7.1f Gsector/s\n",
+				       mb, group, group, 32 / group, n / time_ms(e0, e1) / 1e6);
+			}
+			CK(cudaFree(t));
 		}
 	}
 	if (which & 8) {
