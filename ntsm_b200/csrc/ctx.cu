@@ -52,6 +52,7 @@ struct ntsm_ctx {
 	uint32_t *d_level1 = nullptr;           // 4^M-bit minimizer bitmap of the k = 19 kernels (layout per variant)
 	uint32_t *d_level0 = nullptr;           // image of the gated kernels' shared-memory level-0 bitmap
 	int kernel_variant = 5;                 // k = 19: 0 plain, 1 minimizer, 2 smem-gated minimizer, 3 gate2, 4 strided seeds, 5 paired seeds (default)
+	int pair_fold = kPairFoldDefault;       // paired-seed table folded 2^pair_fold : 1 (NTSM_PAIR_FOLD)
 	int seed_cfg = 1;                       // seed kernel launch shape (NTSM_SEED_CFG): 0 = 1024x1, 1 = 1024x2 (default), 2 = 512x4, 3 = 256x8
 	int gate_m = 14;                        // M-mer length of gate2 (13 or 14)
 	int gate_threads = 1024;                // gate2 CTA size (NTSM_GATE_THREADS: 512 / 768 / 1024)
@@ -196,6 +197,7 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 	if (k != 19 || variant < 0 || variant > 5) variant = 0;
 	if (gm < 13 || gm > 14 || variant >= 4) gm = 14;
 	if (const char *e = getenv("NTSM_SEED_CFG")) c->seed_cfg = std::min(3, std::max(0, atoi(e)));
+	if (const char *e = getenv("NTSM_PAIR_FOLD")) c->pair_fold = std::min(kPairFoldMax, std::max(0, atoi(e)));
 	if (const char *e = getenv("NTSM_TAIL_POOL")) c->pool_tail = atoi(e) != 0;
 	if (const char *e = getenv("NTSM_GATE_THREADS")) c->gate_threads = atoi(e);
 
@@ -206,7 +208,7 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 	const size_t filter_words = (1ull << fbits) / 32;                 // layout depends on the variant
 	// minimizer bitmaps: level 1 = 4^M bits in global memory, level 0 = image of the shared-memory bitmap
 	const int mm_len = variant == 1 ? kMinimizerM : variant == 2 ? kGateM : gm;
-	const size_t level1_words = variant == 5 ? kPairWords : variant ? (1ull << (2 * mm_len)) / 32 : 0;
+	const size_t level1_words = variant == 5 ? kPairWords >> c->pair_fold : variant ? (1ull << (2 * mm_len)) / 32 : 0;
 	const size_t level0_words = variant == 2 || variant == 3 ? kL0Words : 0;
 
 	cudaFree(c->d_filter); cudaFree(c->d_level1); cudaFree(c->d_level0); cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_allele_off); cudaFree(c->d_rows);
@@ -264,7 +266,7 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 		BuildParams B;
 		B.hash = d_hash; B.erased = d_erased; B.n_kmers = n_kmers; B.k = k; B.variant = variant; B.gate_m = gm;
 		B.table = c->d_table; B.table_mask = (uint32_t)(cap - 1); B.filter = c->d_filter; B.filter_shift = 32 - fbits;
-		B.level1 = c->d_level1; B.level0 = c->d_level0; B.err = d_err;
+		B.level1 = c->d_level1; B.level0 = c->d_level0; B.err = d_err; B.pair_word_mask = pair_word_mask(c->pair_fold);
 		if (n_kmers) {
 			build_tables_kernel<<<(n_kmers + 255) / 256, 256, 0, st>>>(B);
 			CU(c, cudaGetLastError());
@@ -354,6 +356,7 @@ static int launch_count(ntsm_ctx *c, const uint2 *d_bases, const uint32_t *d_mas
 	P.table_mask = c->table_cap - 1;
 	P.k = c->cfg.k;
 	P.four = 4;
+	P.pair_word_mask = pair_word_mask(c->pair_fold);
 	P.counts = c->d_counts;
 	P.totals = c->d_totals;
 	const uint64_t tiles = (P.n_chunks + kCountThreads - 1) / kCountThreads;

@@ -128,6 +128,7 @@ struct BuildParams {
 	uint32_t *filter;
 	uint32_t filter_shift;
 	uint32_t *level1, *level0;  // zeroed; nullptr when the variant has none
+	uint32_t pair_word_mask;    // variant 5: words of the (folded) pair table - 1
 	int *err;                   // [0] 0 ok, 1 hash out of range, 2 duplicate; [1] the offending index
 };
 
@@ -189,8 +190,8 @@ __global__ void build_tables_kernel(const BuildParams B)
 			// paired-seed kernel (pair.cuh): every 14-mer of the k-mer entered once per role (pair_slots)
 			for (int j = 0; j + 14 <= (int)B.k; ++j) {
 				const uint32_t v = (uint32_t)(s >> (2 * j)) & 0x0FFFFFFFu;
-				atomicOr(B.level1 + (v >> 4), 1u << (v & 15));
-				atomicOr(B.level1 + (v & 0xFFFFFFu), 1u << (16 + (v >> 24)));
+				atomicOr(B.level1 + ((v >> 4) & B.pair_word_mask), 1u << (v & 15));
+				atomicOr(B.level1 + (v & 0xFFFFFFu & B.pair_word_mask), 1u << (16 + (v >> 24)));
 			}
 			uint32_t ra, rb;
 			gate2_filter_slots(lo, hi, (int)B.k, B.filter_shift, fw2, ra, rb);

@@ -44,6 +44,7 @@ struct CountParams {
 	uint32_t table_mask;       // capacity - 1
 	uint32_t k;
 	uint32_t four;             // = 4, kept in a register so address scaling stays an IMAD (FMA pipe), not an LEA
+	uint32_t pair_word_mask;   // paired-seed kernel: (words of the pair table) - 1
 	uint32_t *counts;
 	unsigned long long *totals;   // [0] valid windows (TK), [1] hits
 };

@@ -30,12 +30,23 @@ constexpr int kPairM = 14;                                  // seed length
 constexpr int kPairD = 2;                                   // distance between the two seeds of a pair
 constexpr size_t kPairWords = (size_t)1 << (2 * (kPairM - kPairD));   // 4^12 words
 
+constexpr int kPairFoldDefault = 1;                         // table folded 2:1 by default (32 MiB), see below
+constexpr int kPairFoldMax = 4;
+
+// The full table is 64 MiB, and with the 16 MiB k-mer bitmap next to it that is more than ONE of the
+// two L2 partitions of a B200 holds: ncu on the unfolded table (profiles/r01v8_*) shows the L2
+// sector hit rate at 49 % and 2.5 B/base of DRAM reads instead of 0.38.  Folding drops the top
+// `fold` bits of the word index (the high bit(s) of the last shared base: two cores that differ only
+// there share a word, their role bits ORed) -- half the footprint per fold bit for twice the
+// level-1 false-positive rate, at no instruction cost (the mask is a register either way).
+NTSM_HD uint32_t pair_word_mask(int fold) { return (uint32_t)(kPairWords >> fold) - 1u; }
+
 // the two table entries of stream-order 14-mer v (28 bits, first base in the low bits)
-NTSM_HD void pair_slots(uint32_t v, uint32_t &word_a, uint32_t &bit_a, uint32_t &word_b, uint32_t &bit_b)
+NTSM_HD void pair_slots(uint32_t v, uint32_t word_mask, uint32_t &word_a, uint32_t &bit_a, uint32_t &word_b, uint32_t &bit_b)
 {
-	word_a = v >> 4;                    // role A: v's last 12 bases are the shared ones
+	word_a = (v >> 4) & word_mask;      // role A: v's last 12 bases are the shared ones
 	bit_a = v & 15;
-	word_b = v & 0xFFFFFFu;             // role B: v's first 12 bases are the shared ones
+	word_b = v & 0xFFFFFFu & word_mask; // role B: v's first 12 bases are the shared ones
 	bit_b = 16 + (v >> 24);
 }
 
@@ -43,7 +54,7 @@ NTSM_HD void pair_slots(uint32_t v, uint32_t &word_a, uint32_t &bit_a, uint32_t 
 // for the 8 windows the pair closes (bit t <-> window p - 5 + t), which of them may still be a site
 // k-mer; 0 without issuing the load when need == 0.  The address is {base_lo + 4 * key, base_hi}: the
 // table never crosses a 4 GiB line (checked at load).
-__device__ __forceinline__ uint32_t pair_probe(uint32_t x, uint32_t need, uint32_t base_lo, uint32_t base_hi)
+__device__ __forceinline__ uint32_t pair_probe(uint32_t x, uint32_t need, uint32_t base_lo, uint32_t base_hi, uint32_t off_mask)
 {
 	uint32_t w;
 	asm("{\n\t"
@@ -52,14 +63,14 @@ __device__ __forceinline__ uint32_t pair_probe(uint32_t x, uint32_t need, uint32
 	    ".reg .u64 a1;\n\t"
 	    "setp.ne.u32 p, %2, 0;\n\t"
 	    "shr.u32 off, %1, 2;\n\t"
-	    "and.b32 off, off, 0x3FFFFFC;\n\t"            // 4 * ((x >> 4) & 0xFFFFFF)
+	    "and.b32 off, off, %5;\n\t"                   // 4 * ((x >> 4) & word mask)
 	    "add.u32 alo, off, %3;\n\t"
 	    "mov.b64 a1, {alo, %4};\n\t"
 	    "mov.u32 %0, 0;\n\t"
 	    "@p ld.global.nc.u32 %0, [a1];\n\t"
 	    "}"
 	    : "=r"(w)
-	    : "r"(x), "r"(need), "r"(base_lo), "r"(base_hi));
+	    : "r"(x), "r"(need), "r"(base_lo), "r"(base_hi), "r"(off_mask));
 	const uint32_t a = 0u - ((w >> (x & 15u)) & 1u);               // all-ones if seed A is marked
 	const uint32_t b = 0u - ((w >> ((x >> 28) + 16u)) & 1u);       // all-ones if seed B is marked
 	return (a | 0xC0u) & (b | 0x03u) & 0xFFu;                      // A closes t in [0,6), B closes t in [2,8)
@@ -83,6 +94,7 @@ __global__ void __launch_bounds__(THREADS, MINB) count_kernel_pair(const CountPa
 	__shared__ uint16_t s_cand[THREADS / 32][kCandSlots];
 	const uint32_t base_lo = (uint32_t)(uintptr_t)P.minimizer2, base_hi = (uint32_t)((uintptr_t)P.minimizer2 >> 32);
 	const uint32_t wshift = P.filter_shift + 5;
+	const uint32_t off_mask = P.pair_word_mask << 2;
 	const uint32_t lane = threadIdx.x & 31;
 	uint16_t *cand = s_cand[threadIdx.x >> 5];
 	uint32_t tk = 0, hits = 0;
@@ -124,10 +136,10 @@ __global__ void __launch_bounds__(THREADS, MINB) count_kernel_pair(const CountPa
 		if (lane == 0) pv = 0;                                    // closed by lane 31 of the warp that owns that chunk
 		const uint32_t n5 = __funnelshift_l(pv, valid, 5);        // bit i + 5 <-> window i, i = -5 .. 26
 
-		const uint32_t r0 = pair_probe(own.x, n5 & 0xFFu, base_lo, base_hi);
-		const uint32_t r1 = pair_probe(__funnelshift_r(own.x, own.y, 16), n5 & 0xFF00u, base_lo, base_hi);
-		const uint32_t r2 = pair_probe(own.y, n5 & 0xFF0000u, base_lo, base_hi);
-		const uint32_t r3 = pair_probe(__funnelshift_r(own.y, nxt.x, 16), n5 & 0xFF000000u, base_lo, base_hi);
+		const uint32_t r0 = pair_probe(own.x, n5 & 0xFFu, base_lo, base_hi, off_mask);
+		const uint32_t r1 = pair_probe(__funnelshift_r(own.x, own.y, 16), n5 & 0xFF00u, base_lo, base_hi, off_mask);
+		const uint32_t r2 = pair_probe(own.y, n5 & 0xFF0000u, base_lo, base_hi, off_mask);
+		const uint32_t r3 = pair_probe(__funnelshift_r(own.y, nxt.x, 16), n5 & 0xFF000000u, base_lo, base_hi, off_mask);
 		const uint32_t nb = __shfl_down_sync(0xffffffffu, r0, 1);   // the next chunk's pair 0 closes windows 27-31
 		const uint32_t plo = r0 | (r1 << 8) | (r2 << 16) | (r3 << 24);
 		const uint32_t pass = __funnelshift_r(plo, nb, 5) & valid;

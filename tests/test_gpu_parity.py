@@ -388,3 +388,15 @@ def test_seed_kernel_dense_hits_and_every_phase(oracle, monkeypatch, variant):
     for bb in (1 << 12, 40001, 1 << 20):
         ofp = _check_against_oracle(oracle, PANEL, reads, batch_bases=bb, n_buffers=3)
     assert ofp.total_counts > 3 * len(reads)
+
+
+@pytest.mark.parametrize("fold", ["0", "1", "2", "4"])
+def test_pair_table_fold_vs_oracle(oracle, monkeypatch, fold):
+    """NTSM_PAIR_FOLD folds the paired-seed table 2^fold : 1 (pair.cuh): a smaller level-1 table only
+    lets more windows through to the exact path, so the counters must not change."""
+    monkeypatch.setenv("NTSM_KERNEL", "5")
+    monkeypatch.setenv("NTSM_PAIR_FOLD", fold)
+    rng = random.Random(2100 + int(fold))
+    wins = _windows(PANEL, limit=8000)
+    reads = _reads(rng, wins, 5000, "ACGTN") + [bytes(rng.choice(b"ACGT") for _ in range(rng.randrange(0, 400))) for _ in range(1500)]
+    _check_against_oracle(oracle, PANEL, reads, batch_bases=1 << 18)
