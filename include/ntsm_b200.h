@@ -208,6 +208,23 @@ int64_t ntsm_reader_next(ntsm_reader *r, const char **seq);
 const char *ntsm_reader_name(const ntsm_reader *r);
 void ntsm_reader_close(ntsm_reader *r);
 
+/* ---------------- byte source: gzopen/gzread as kseq uses them (src/FingerPrint.hpp:50,
+ * vendor/kseq.h:68-79 over KSEQ_INIT(gzFile, gzread)) ----------------
+ * Delivers exactly the bytes zlib's gzread would for the file (plain files pass through, gzip members
+ * are inflated one after the other, trailing garbage is ignored, an error ends the stream after the
+ * bytes that preceded it), but inflates with the library's own decoder over a memory-mapped file
+ * and, for BGZF files, block-parallel on up to `helpers` extra threads.  ntsm_gz_mode: "zlib" |
+ * "fast" | "bgzf" (what is producing bytes now); ntsm_gz_fell_back: 1 once an irregular member made
+ * the source hand the rest of the file to zlib.  ntsm_reader_open2 is ntsm_reader_open with helpers. */
+typedef struct ntsm_gz ntsm_gz;
+int ntsm_gz_open(ntsm_gz **out, const char *path, int helpers);
+int ntsm_gz_read(ntsm_gz *g, void *dst, unsigned n);   /* gzread's contract: short only at the end, 0 = end, -1 = error */
+const char *ntsm_gz_mode(const ntsm_gz *g);
+int ntsm_gz_fell_back(const ntsm_gz *g);
+void ntsm_gz_close(ntsm_gz *g);
+uint32_t ntsm_crc32(uint32_t crc, const void *buf, uint64_t len);   /* the CRC-32 of gzip trailers (carry-less multiply when available) */
+int ntsm_reader_open2(ntsm_reader **out, const char *path, int helpers);
+
 /* ---------------- whole path: FingerPrint::computeCounts (src/FingerPrint.hpp:46-87) -------- */
 /* Reads every file with `threads` parser threads (one file per thread at a time, like the
  * reference's omp parallel for over files), packs reads into pinned batches and streams batch i

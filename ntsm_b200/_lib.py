@@ -82,6 +82,13 @@ _SIGS = {
     "ntsm_reader_next": (C.c_int64, [_P, C.POINTER(C.c_char_p)]),
     "ntsm_reader_name": (C.c_char_p, [_P]),
     "ntsm_reader_close": (None, [_P]),
+    "ntsm_reader_open2": (C.c_int, [C.POINTER(_P), C.c_char_p, C.c_int]),
+    "ntsm_gz_open": (C.c_int, [C.POINTER(_P), C.c_char_p, C.c_int]),
+    "ntsm_gz_read": (C.c_int, [_P, C.c_void_p, C.c_uint]),
+    "ntsm_gz_mode": (C.c_char_p, [_P]),
+    "ntsm_gz_fell_back": (C.c_int, [_P]),
+    "ntsm_gz_close": (None, [_P]),
+    "ntsm_crc32": (C.c_uint32, [C.c_uint32, C.c_void_p, C.c_uint64]),
     "ntsm_count_files": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_int)]),
     "ntsm_main": (C.c_int, [C.c_int, _P]),
 }
@@ -93,6 +100,24 @@ def lib_path():
     return _LIB_PATH
 
 
+def _preload_bundled_nccl():
+    """libntsm_b200.so needs libnccl.so.2.  torch ships a newer one than the system's and refuses to
+    start on the older: whichever of the two is mapped first serves both, so map torch's first (it
+    is what the library runs on whenever torch was imported before it, i.e. in bench.py and the
+    multi-rank tests)."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []):
+            so = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(so):
+                C.CDLL(so, mode=C.RTLD_GLOBAL)
+                return so
+    except Exception:
+        pass
+    return None
+
+
 def lib():
     """The loaded library.  No fallback: a missing build is an error, not a slow path."""
     global _lib
@@ -100,6 +125,7 @@ def lib():
         if not os.path.exists(_LIB_PATH):
             raise ImportError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                               "or `make -C ntsm_b200/csrc` (there is no CPU fallback)" % _LIB_PATH)
+        _preload_bundled_nccl()
         L = C.CDLL(_LIB_PATH, mode=C.RTLD_GLOBAL)
         for name, (res, args) in _SIGS.items():
             f = getattr(L, name)          # AttributeError here = header/library mismatch

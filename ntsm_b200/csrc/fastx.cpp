@@ -9,12 +9,11 @@ namespace ntsm {
 
 static constexpr size_t kWindow = 1u << 20;
 
-bool FastxReader::open(const char *path)
+bool FastxReader::open(const char *path, int helpers)
 {
 	close();
-	f_ = gzopen(path, "r");          // plain files pass through, like the reference (FingerPrint.hpp:50)
-	if (!f_) return false;
-	gzbuffer(f_, 1u << 18);
+	if (!src_.open(path, helpers)) return false;   // plain files pass through, like the reference's gzopen (FingerPrint.hpp:50)
+	open_ = true;
 	buf_.resize(kWindow);
 	beg_ = end_ = 0;
 	eof_ = err_ = src_err_ = false;
@@ -27,8 +26,8 @@ bool FastxReader::open(const char *path)
 
 void FastxReader::close()
 {
-	if (f_) gzclose(f_);
-	f_ = nullptr;
+	if (open_) src_.close();
+	open_ = false;
 }
 
 bool FastxReader::fill()
@@ -39,7 +38,7 @@ bool FastxReader::fill()
 		return false;
 	}
 	beg_ = 0;
-	const int n = gzread(f_, buf_.data(), (unsigned)buf_.size());
+	const int n = src_.read(buf_.data(), (unsigned)buf_.size());
 	if (n <= 0) {
 		eof_ = true;
 		err_ = n < 0;
@@ -140,9 +139,12 @@ bool FastxReader::next_fast(int64_t *len)
 		memmove(buf_.data(), buf_.data() + beg_, tail);
 		beg_ = 0;
 		end_ = tail;
-		const int n = gzread(f_, buf_.data() + tail, (unsigned)(buf_.size() - tail));
+		const int n = src_.read(buf_.data() + tail, (unsigned)(buf_.size() - tail));
 		if (n < 0) { src_err_ = true; eof_ = true; return false; }
-		if ((size_t)n < buf_.size() - tail) eof_ = true;   // gzread only comes back short at the end of the input
+		if ((size_t)n < buf_.size() - tail) {              // the source only comes back short at the end of the input,
+			eof_ = true;                                   // or ahead of a data error it will report next
+			if (src_.bad()) src_err_ = true;
+		}
 		end_ = tail + (size_t)n;
 		if (n == 0) return false;
 	}
@@ -224,6 +226,18 @@ extern "C" int ntsm_reader_open(ntsm_reader **out, const char *path)
 	if (!out || !path) return NTSM_ERR_ARG;
 	ntsm_reader *h = new ntsm_reader();
 	if (!h->r.open(path)) {
+		delete h;
+		return NTSM_ERR_IO;
+	}
+	*out = h;
+	return NTSM_OK;
+}
+
+extern "C" int ntsm_reader_open2(ntsm_reader **out, const char *path, int helpers)
+{
+	if (!out || !path) return NTSM_ERR_ARG;
+	ntsm_reader *h = new ntsm_reader();
+	if (!h->r.open(path, helpers)) {
 		delete h;
 		return NTSM_ERR_IO;
 	}

@@ -1,8 +1,8 @@
 // fastx.h -- FASTA/FASTQ(.gz) record reader with the exact record grammar of kseq_read
 // (vendor/kseq.h:178-219) as FingerPrint::computeCounts drives it (src/FingerPrint.hpp:64-67).
 //
-// Same grammar, different machinery: a 1 MiB inflate window scanned with memchr instead of a
-// 16 KiB buffer walked byte by byte.  Behaviour that must match (all covered by tests/golden):
+// Same grammar, different machinery: a 1 MiB window scanned with memchr instead of a 16 KiB buffer
+// walked byte by byte, filled by GzSource (gzsource.h: the byte stream gzread would deliver).  Behaviour that must match (all covered by tests/golden):
 //   * a record starts at the next '>' or '@' (anywhere, when hunting; at a line start otherwise);
 //   * name = header up to the first isspace(); rest of the header line is ignored;
 //   * sequence = concatenation of the following lines until a line STARTING with '>', '+' or '@';
@@ -15,10 +15,11 @@
 //   * return codes: >=0 sequence length, -1 end of file, -2 bad quality, -3 read error.
 #pragma once
 #include <stdint.h>
-#include <zlib.h>
 
 #include <string>
 #include <vector>
+
+#include "gzsource.h"
 
 namespace ntsm {
 
@@ -29,7 +30,9 @@ public:
 	FastxReader(const FastxReader &) = delete;
 	FastxReader &operator=(const FastxReader &) = delete;
 
-	bool open(const char *path);
+	// helpers: idle threads the byte source may use for block-parallel inflate (gzsource.h)
+	bool open(const char *path, int helpers = 0);
+	const char *source_mode() const { return src_.mode(); }
 	void close();
 	// next record; sequence available through seq()/name() until the following call
 	int64_t next();
@@ -51,7 +54,8 @@ private:
 	bool take_line(std::vector<char> &dst);
 	bool skip_line();
 
-	gzFile f_ = nullptr;
+	GzSource src_;
+	bool open_ = false;
 	std::vector<unsigned char> buf_;
 	size_t beg_ = 0, end_ = 0;
 	bool eof_ = false, err_ = false, src_err_ = false;

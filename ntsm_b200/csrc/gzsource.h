@@ -1,0 +1,58 @@
+// gzsource.h -- the byte stream gzread() would deliver for a file, produced faster.
+//
+// The reference opens every input with gzopen and pulls it through gzread (src/FingerPrint.hpp:50,
+// vendor/kseq.h:68-79): plain files pass through, gzip files are inflated member after member,
+// trailing garbage after a member is ignored, an error ends the file.  For gzip'd FASTQ that call
+// is the whole cost of ingest (cfg 4 of BASELINE.json), so GzSource
+// produces the same bytes three ways:
+//   zlib      gzread itself: anything that is not a regular gzip file, and the continuation of any
+//             file the other two modes gave up on;
+//   fast      the file memory-mapped and decoded by ntsm::Inflater (inflate.h), CRC-32 and ISIZE
+//             of every member checked before its last bytes are handed out;
+//   bgzf      a BGZF file (gzip members that carry their own size in a 'BC' extra field, as
+//             bgzip / htslib and the Illumina converters write) inflated block-parallel by helper
+//             threads -- the threads `-t` leaves idle when there are fewer files than threads,
+//             because the reference only parallelises over files (src/FingerPrint.hpp:47-48).
+// Whenever a member is not perfectly regular (header flags we do not parse, a decode error, a
+// checksum mismatch, a block that is not BGZF after all) the source re-opens the file with zlib at
+// that member's offset, skips the bytes of it that were already decoded, and carries on with zlib's
+// inflate -- so which bytes of a damaged file count as decodable is zlib's verdict.  How many of
+// them the reference then gets to see is reproduced as well: kseq pulls 16 KiB per gzread
+// (vendor/kseq.h:229) and gzread drops the whole call in which a data error turns up, so only whole
+// 16 KiB reads ahead of the error are released (a truncated file, by contrast, just ends).
+#pragma once
+#include <stdint.h>
+#include <zlib.h>
+
+#include <memory>
+#include <string>
+
+namespace ntsm {
+
+class GzSource {
+public:
+	GzSource();
+	~GzSource();
+	GzSource(const GzSource &) = delete;
+	GzSource &operator=(const GzSource &) = delete;
+
+	// helpers: extra threads this source may start for block-parallel inflate (0 = none).
+	// NTSM_INFLATE=zlib forces plain gzread (tests, comparisons).
+	bool open(const char *path, int helpers = 0);
+	void close();
+	// gzread's contract: the number of bytes delivered, short only at the end of the input;
+	// 0 at the end; -1 on a read/format error (after the bytes that preceded it were delivered)
+	int read(void *dst, unsigned n);
+	const char *mode() const;          // "zlib" | "fast" | "bgzf" -- what is producing bytes right now
+	bool fell_back() const;            // a fast mode handed the file over to zlib
+	bool bad() const;                  // a data error was met (read() returns -1 once the bytes before it are out)
+
+private:
+	struct Impl;
+	std::unique_ptr<Impl> p_;
+};
+
+// CRC-32 (IEEE, as in gzip trailers) with carry-less multiplies when the CPU has them
+uint32_t crc32_fast(uint32_t crc, const uint8_t *buf, size_t len);
+
+}  // namespace ntsm

@@ -24,6 +24,7 @@ struct Shared {
 	uint32_t n_paths;
 	int verbose;
 	uint64_t max_counts;
+	uint32_t helpers = 0, helpers_extra = 0;    // idle -t threads lent to each parser for block-parallel inflate
 	std::atomic<uint32_t> next_file{0};
 	std::atomic<uint64_t> next_batch{0};
 	std::atomic<bool> early{false};
@@ -46,8 +47,9 @@ void check_cap(Shared &sh)
 	if (hits > sh.max_counts) sh.early.store(true);
 }
 
-void worker(Shared &sh)
+void worker(Shared &sh, uint32_t wi)
 {
+	const int helpers = (int)(sh.helpers + (wi < sh.helpers_extra ? 1 : 0));
 	ntsm::FastxReader rd;
 	ntsm::BatchWriter bw(sh.ctxs, sh.n_ctx, &sh.next_batch);
 	auto set_error = [&](int code, const std::string &text) {
@@ -64,7 +66,7 @@ void worker(Shared &sh)
 	for (;;) {
 		const uint32_t fi = sh.next_file.fetch_add(1);
 		if (fi >= sh.n_paths || sh.error.load()) break;
-		if (!rd.open(sh.paths[fi])) {                               // FingerPrint.hpp:51-57
+		if (!rd.open(sh.paths[fi], helpers)) {                               // FingerPrint.hpp:51-57
 			set_error(NTSM_ERR_IO, std::string("file ") + sh.paths[fi] + " cannot be opened");
 			break;
 		}
@@ -95,10 +97,13 @@ extern "C" int ntsm_count_files(ntsm_ctx *const *ctxs, uint32_t n_ctx, const cha
 	sh.max_counts = 0;
 	sh.max_counts = ntsm_ctx_max_counts(ctxs[0]);   // every ctx carries the same cap
 	uint32_t nt = threads ? threads : 1;
-	if (nt > n_paths) nt = n_paths ? n_paths : 1;                   // -t never uses more than #files (:47-48)
+	if (nt > n_paths) nt = n_paths ? n_paths : 1;                   // the reference never uses more than #files (:47-48) ...
+	const uint32_t spare = (threads ? threads : 1) - nt;            // ... the rest of -t inflates BGZF blocks for the parsers (gzsource.h)
+	sh.helpers = spare / nt;
+	sh.helpers_extra = spare % nt;
 	std::vector<std::thread> pool;
-	for (uint32_t t = 1; t < nt; ++t) pool.emplace_back(worker, std::ref(sh));
-	worker(sh);
+	for (uint32_t t = 1; t < nt; ++t) pool.emplace_back(worker, std::ref(sh), t);
+	worker(sh, 0);
 	for (auto &t : pool) t.join();
 	for (uint32_t i = 0; i < n_ctx; ++i) {
 		const int rc = ntsm_sync(ctxs[i]);

@@ -231,6 +231,53 @@ def build_cases():
         s_multi += h + "\r\n" + s[:30].lower() + "\r\n" + s[30:] + "\r\n"
     case("sites_multiline_crlf", {"sites.fa": s_multi, "reads.fq": fastq(reads[:400])}, ["-s", "sites.fa", "reads.fq"])
 
+    # --- gzip inputs the way gzread treats them: damage, truncation, garbage, BGZF ---------------
+    # (own generator so the cases above keep their bytes).  What the reference sees of a damaged
+    # stream is decided by zlib's gzread under kseq's 16 KiB reads; these pin it.
+    import struct
+    import zlib
+    grng = random.Random(20261018)
+    greads = panel_reads(grng, recs300, 1500)
+    gtext = fastq(greads, qual="F").encode()                     # ~470 KB: ~29 reads of 16 KiB
+    whole = gzip.compress(gtext, 6, mtime=0)
+
+    def flipped(blob, frac, bit=3):
+        b = bytearray(blob)
+        b[int(len(b) * frac)] ^= 1 << bit
+        return bytes(b)
+
+    def bgzf(data, block=0xFF00, eof_marker=True):
+        out = bytearray()
+        for i in list(range(0, len(data), block)) + ([len(data)] if eof_marker else []):
+            chunk = data[i:i + block]
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            body = co.compress(chunk) + co.flush()
+            out += b"\x1f\x8b\x08\x04\0\0\0\0\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, 12 + 6 + len(body) + 8 - 1)
+            out += body + struct.pack("<II", zlib.crc32(chunk), len(chunk))
+        return bytes(out)
+
+    blocks = bgzf(gtext)
+    two = gzip.compress(gtext[:200000], 9, mtime=0) + gzip.compress(gtext[200000:], 1, mtime=0)
+    gz_cases = {
+        "gz_single": whole,
+        "gz_bitflip_mid": flipped(whole, 0.55),
+        "gz_bitflip_early": flipped(whole, 0.02, 6),
+        "gz_bad_crc": whole[:-8] + bytes([whole[-8] ^ 0xFF]) + whole[-7:],
+        "gz_bad_isize": whole[:-1] + bytes([whole[-1] ^ 1]),
+        "gz_truncated": whole[:int(len(whole) * 0.7)],
+        "gz_truncated_in_trailer": whole[:-3],
+        "gz_garbage_tail": whole + b"not a gzip member\n" * 3,
+        "gz_two_members_second_damaged": flipped(two, 0.8),
+        "gz_second_member_bad_method": two[:len(gzip.compress(gtext[:200000], 9, mtime=0)) + 2] + b"\x07" + two[len(gzip.compress(gtext[:200000], 9, mtime=0)) + 3:],
+        "bgzf": blocks,
+        "bgzf_no_eof_marker": bgzf(gtext, eof_marker=False),
+        "bgzf_bitflip_block": flipped(blocks, 0.6, 1),
+        "bgzf_truncated": blocks[:int(len(blocks) * 0.45)],
+        "bgzf_then_plain_member": bgzf(gtext[:250000], eof_marker=False) + gzip.compress(gtext[250000:], 6, mtime=0),
+    }
+    for nm, blob in gz_cases.items():
+        case(nm, {}, ["-t", "4", "-s", S300, "reads.fq.gz"], binary_files={"reads.fq.gz": blob})
+
 
 def run_case(name, files, argv, binary_files):
     d = os.path.join(OUT, "cases", name)
