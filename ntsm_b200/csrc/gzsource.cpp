@@ -182,6 +182,7 @@ struct GzSource::Impl {
 	bool gz_direct = false;
 	const uint8_t *map = nullptr;
 	size_t size = 0;
+	bool map_is_heap = false;             // NTSM_GZ_INPUT=read: the file was read into memory instead of mapped (measurement knob)
 
 	// ---- staging -------------------------------------------------------------------------------
 	// How much of a DAMAGED gzip file the reference gets to see follows from zlib's gzread.c and from
@@ -249,7 +250,8 @@ struct GzSource::Impl {
 		gz = nullptr;
 		if (zs_init) inflateEnd(&zs);
 		zs_init = false;
-		if (map) munmap((void *)map, size);
+		if (map && map_is_heap) free((void *)map);
+		else if (map) munmap((void *)map, size);
 		map = nullptr;
 	}
 
@@ -611,9 +613,25 @@ bool GzSource::open(const char *path, int helpers)
 	unsigned char magic[2] = { 0, 0 };
 	if (want_fast && fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size >= 18 && pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f &&
 	    magic[1] == 0x8b) {
-		void *m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+		void *m = MAP_FAILED;
+		const char *gin = getenv("NTSM_GZ_INPUT");
+		if (gin && !strcmp(gin, "read")) {
+			m = malloc((size_t)sb.st_size);
+			size_t got = 0;
+			while (m && got < (size_t)sb.st_size) {
+				const ssize_t r = pread(fd, (char *)m + got, (size_t)sb.st_size - got, (off_t)got);
+				if (r <= 0) break;
+				got += (size_t)r;
+			}
+			if (!m || got != (size_t)sb.st_size) {
+				free(m);
+				m = MAP_FAILED;
+			} else s.map_is_heap = true;
+		} else {
+			m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+			if (m != MAP_FAILED && !(gin && !strcmp(gin, "mmap_plain"))) madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
+		}
 		if (m != MAP_FAILED) {
-			madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
 			s.map = (const uint8_t *)m;
 			s.size = (size_t)sb.st_size;
 			::close(fd);
