@@ -64,6 +64,7 @@ typedef struct ntsm_cfg {
 
 const char *ntsm_version(void);
 int ntsm_device_count(void); /* visible CUDA devices; 0 when there is none (nothing can be counted then) */
+int ntsm_device_warmup(int device); /* create the device's primary context now (thread-safe; lets a caller overlap it with reading sites.fa) */
 /* text of the last error on this ctx, or (ctx == NULL) of the calling thread */
 const char *ntsm_last_error(const ntsm_ctx *ctx);
 

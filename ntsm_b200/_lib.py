@@ -22,6 +22,7 @@ _SIGS = {
     # name: (restype, argtypes)
     "ntsm_version": (C.c_char_p, []),
     "ntsm_device_count": (C.c_int, []),
+    "ntsm_device_warmup": (C.c_int, [C.c_int]),
     "ntsm_last_error": (C.c_char_p, [_P]),
     "ntsm_nt4": (C.c_uint32, [C.c_uint8]),
     "ntsm_hash64": (C.c_uint64, [C.c_uint64, C.c_uint32]),

@@ -122,6 +122,18 @@ extern "C" int ntsm_main(int argc, char **argv)
 		last = now;
 	};
 
+	// the CUDA primary contexts come up on their own threads while this one reads the site file
+	std::vector<std::thread> warm;
+	{
+		const int nd = ntsm_device_count();
+		const int ng = gpus <= 0 || gpus > nd ? nd : gpus;
+		for (int g = 0; g < ng; ++g) warm.emplace_back([g] { ntsm_device_warmup(g); });
+	}
+	struct Joiner {
+		std::vector<std::thread> &t;
+		~Joiner() { for (auto &x : t) if (x.joinable()) x.join(); }
+	} joiner{warm};
+
 	// FingerPrint fp;  (ntSeqMatchCount.cpp:177)
 	ntsm_sites *sites = nullptr;
 	int rc = ntsm_sites_load(&sites, snp.c_str(), k, dupes);
@@ -142,13 +154,26 @@ extern "C" int ntsm_main(int argc, char **argv)
 	cfg.max_counts = ntsm_sites_max_counts(sites, covThresh);
 	cfg.batch_bases = batch_bases ? batch_bases : (cfg.max_counts ? (1ull << 22) : 0);
 	cfg.n_buffers = 2 + (threads < 1 ? 1 : threads);
+	for (auto &x : warm) x.join();
 	std::vector<ntsm_ctx *> ctxs((size_t)gpus, nullptr);
-	for (int g = 0; g < gpus; ++g) {
-		cfg.device = g;
-		if ((rc = ntsm_ctx_create(&ctxs[g], &cfg)) || (rc = ntsm_load_siteset(ctxs[g], sites))) {
-			std::cerr << PROGRAM ": " << ntsm_last_error(ctxs[g]) << std::endl;
-			return 1;
-		}
+	{
+		// one thread per GPU: pinned ring, streams, table upload + build_tables_kernel
+		std::vector<std::thread> th;
+		std::vector<int> rcs((size_t)gpus, 0);
+		std::vector<std::string> errs((size_t)gpus);
+		for (int g = 0; g < gpus; ++g)
+			th.emplace_back([&, g] {
+				ntsm_cfg c = cfg;
+				c.device = g;
+				if ((rcs[g] = ntsm_ctx_create(&ctxs[g], &c)) == 0) rcs[g] = ntsm_load_siteset(ctxs[g], sites);
+				if (rcs[g]) errs[g] = ntsm_last_error(ctxs[g]);      // the text of a failed create lives in this thread
+			});
+		for (auto &t : th) t.join();
+		for (int g = 0; g < gpus; ++g)
+			if (rcs[g]) {
+				std::cerr << PROGRAM ": " << errs[g] << std::endl;
+				return 1;
+			}
 	}
 	if (gpus > 1) {   // one NCCL communicator over the GPUs of this process; init must run concurrently
 		char id[NTSM_NCCL_ID_BYTES];

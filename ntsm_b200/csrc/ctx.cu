@@ -113,6 +113,14 @@ extern "C" int ntsm_device_count(void)
 	return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
 }
 
+extern "C" int ntsm_device_warmup(int device)
+{
+	// creating the primary context is most of a short run's wall time; a caller can start it on a
+	// thread of its own while it still reads the site file (the CLI does)
+	if (cudaSetDevice(device) != cudaSuccess) return NTSM_ERR_CUDA;
+	return cudaFree(nullptr) == cudaSuccess ? NTSM_OK : NTSM_ERR_CUDA;
+}
+
 // ------------------------------------------------------------------ context
 extern "C" int ntsm_ctx_create(ntsm_ctx **out, const ntsm_cfg *cfg)
 {

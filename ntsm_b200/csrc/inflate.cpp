@@ -301,24 +301,16 @@ template <bool SAFE> Inflater::Status Inflater::huffman_loop(const uint8_t *hist
 		uint32_t e;
 		NTSM_LOOKUP(e, lit, kLitBits);
 		if (e & kLit) {
-			bb >>= e & 0xFF;
-			bl -= (int)(e & 0xFF);
-			*out++ = (uint8_t)(e >> 12);
-			NTSM_LOOKUP(e, lit, kLitBits);
-			if (e & kLit) {
+			// a run of literals: a lookup needs at most 15 bits, so keep going while that many are left
+			do {
 				bb >>= e & 0xFF;
 				bl -= (int)(e & 0xFF);
 				*out++ = (uint8_t)(e >> 12);
+				if (bl < 15) break;
 				NTSM_LOOKUP(e, lit, kLitBits);
-				if (e & kLit) {
-					bb >>= e & 0xFF;
-					bl -= (int)(e & 0xFF);
-					*out++ = (uint8_t)(e >> 12);
-					if (SAFE && bl < 0) { why = "truncated stream"; st = kError; break; }
-					continue;
-				}
-			}
+			} while (e & kLit);
 			if (SAFE && bl < 0) { why = "truncated stream"; st = kError; break; }
+			if (e & kLit) continue;                            // out of bits after a literal: refill at the top
 			NTSM_REFILL();                                     // e is looked up but not dropped yet; a match needs up to 48 bits
 		}
 		if (e & kEob) {

@@ -13,7 +13,7 @@
 //
 // Shape: 64-bit bit buffer refilled with one unaligned 8-byte load; 11-bit primary literal/length
 // table and 9-bit primary distance table with second-level tables for longer codes; entries carry
-// "bits to drop" and the base value so a symbol costs one lookup; up to three literals per refill;
+// "bits to drop" and the base value so a symbol costs one lookup; literals decoded in runs per refill;
 // matches copied 8 bytes at a time (distance 1 as a fill).  The decoder runs from a memory-mapped
 // input straight into a caller-owned window and can stop at any symbol boundary when the window is
 // full, so a multi-gigabyte member streams through a 1 MiB window.
@@ -40,7 +40,7 @@ public:
 	const uint8_t *in_pos() const { return in_; }
 	const char *error() const { return err_; }
 
-	static constexpr size_t kSlack = 512;      // one iteration writes at most 3 literals + 258 + 7 bytes past the limit
+	static constexpr size_t kSlack = 512;      // one iteration writes at most 56 literals + 258 + 7 bytes past the limit
 
 private:
 	static constexpr int kLitBits = 11, kDistBits = 9, kPreBits = 7;
