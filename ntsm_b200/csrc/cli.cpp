@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <chrono>
 #include <fstream>
@@ -176,6 +177,21 @@ extern "C" int ntsm_main(int argc, char **argv)
 			}
 	}
 	if (gpus > 1) {   // one NCCL communicator over the GPUs of this process; init must run concurrently
+		// whatever a library prints while the communicator comes up must not reach the counts file:
+		// file descriptor 1 points at stderr until it is done
+		fflush(stdout);
+		const int saved_out = dup(1);
+		if (saved_out >= 0) dup2(2, 1);
+		struct RestoreStdout {
+			int fd;
+			~RestoreStdout()
+			{
+				if (fd < 0) return;
+				fflush(stdout);
+				dup2(fd, 1);
+				close(fd);
+			}
+		} restore_stdout{saved_out};
 		char id[NTSM_NCCL_ID_BYTES];
 		if ((rc = ntsm_nccl_unique_id(id))) { std::cerr << PROGRAM ": " << ntsm_last_error(nullptr) << std::endl; return 1; }
 		std::vector<std::thread> th;

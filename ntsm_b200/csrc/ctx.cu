@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <strings.h>
 
 #include <algorithm>
 #include <condition_variable>
@@ -630,12 +631,22 @@ extern "C" int ntsm_sync(ntsm_ctx *c)
 }
 
 // ------------------------------------------------------------------ multi-GPU
+// stdout is the counts file, so NCCL's version banner must not land there.  NCCL honours
+// NCCL_DEBUG_FILE only for levels above VERSION (2.27: debug.cc), and GPU hosts commonly export
+// NCCL_DEBUG=VERSION: raise that to WARN (which prints the same banner) so the file setting applies.
+static void nccl_banner_to_stderr()
+{
+	const char *lvl = getenv("NCCL_DEBUG");
+	if (lvl && !strcasecmp(lvl, "VERSION")) setenv("NCCL_DEBUG", "WARN", 1);
+	setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
+}
+
 extern "C" int ntsm_nccl_unique_id(void *id_out)
 {
 	static_assert(sizeof(ncclUniqueId) == NTSM_NCCL_ID_BYTES, "ncclUniqueId size");
 	if (!id_out) return NTSM_ERR_ARG;
 	ncclUniqueId id;
-	setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
+	nccl_banner_to_stderr();
 	NC(nullptr, ncclGetUniqueId(&id));
 	memcpy(id_out, &id, sizeof id);
 	return NTSM_OK;
@@ -647,8 +658,7 @@ extern "C" int ntsm_comm_init(ntsm_ctx *c, const void *id, int rank, int n_ranks
 	CU(c, cudaSetDevice(c->device));
 	ncclUniqueId uid;
 	memcpy(&uid, id, sizeof uid);
-	// stdout is the counts file: NCCL's version/debug banner (NCCL_DEBUG=VERSION on some hosts) goes to stderr
-	setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
+	nccl_banner_to_stderr();
 	NC(c, ncclCommInitRank(&c->comm, n_ranks, uid, rank));
 	c->rank = rank;
 	c->n_ranks = n_ranks;

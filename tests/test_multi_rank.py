@@ -139,3 +139,34 @@ def test_two_gpus_nccl_allreduce_matches_oracle(oracle):
         assert text == whole.counts_text()
         assert summ == whole.summary()
         assert np.array_equal(cnt, whole.lists()[2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nccl_debug", ["VERSION", "WARN", None])
+def test_cli_all_gpus_of_one_process_equals_one_gpu(nccl_debug):
+    """ntsmCount --gpus N (one process, one NCCL communicator over its GPUs) must print the very same
+    counts file as --gpus 1 -- including when the host exports NCCL_DEBUG=VERSION, which makes NCCL
+    print its banner to stdout unless it is kept away from the counts file."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "ntsm_b200", "bin", "ntsmCount")
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = []
+        for i in range(3):
+            p = os.path.join(tmp, "r%d.fa" % i)
+            with open(p, "w") as fh:
+                for j, r in enumerate(_reads(500 + i, 3000)):
+                    fh.write(">r%d\n%s\n" % (j, r.decode()))
+            paths.append(p)
+        env = {k: v for k, v in os.environ.items() if k != "NCCL_DEBUG"}
+        if nccl_debug:
+            env["NCCL_DEBUG"] = nccl_debug
+        outs = []
+        for g in ("1", str(torch.cuda.device_count())):
+            p = subprocess.run([exe, "--gpus", g, "--batch-bases", "100000", "-t", "3", "-s", SITES] + paths, capture_output=True, env=env)
+            assert p.returncode == 0, p.stderr.decode()
+            outs.append(p.stdout)
+        assert outs[0].startswith(b"#@TK\t")
+        assert outs[0] == outs[1]
