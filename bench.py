@@ -207,7 +207,14 @@ def ours(args):
 
     # ---- FingerPrint object on this rank's GPU ------------------------------------------
     t0 = time.time()
-    sites = ntsm_b200.SiteSet(PANEL, 19)
+    panel, wc, wl = PANEL, None, None
+    if args.synthetic_sites:          # cfg5 (kernel-only sweeps): 10^6-site synthetic panel instead of the human one
+        from ntsm_b200 import synth_np
+        panel = "/tmp/ntsm_bench_sites_%d.fa" % args.synthetic_sites
+        win, n_kept = synth_np.synthetic_panel(panel, args.synthetic_sites, 5)
+        wc, wl = synth_np.panel_alleles_from_windows(win)
+        log("rank %d: synthetic panel of %d sites written in %.1f s" % (rank, n_kept, time.time() - t0))
+    sites = ntsm_b200.SiteSet(panel, 19)
     fp = ntsm_b200.FingerPrint(sites, device=local, batch_bases=1 << 26, n_buffers=3)
     # a real (non-default) torch stream: the ABI reads a NULL handle as "use the ctx's own stream",
     # and torch.cuda.Event only sees the stream it is recorded on
@@ -222,7 +229,8 @@ def ours(args):
     # ---- this rank's shard, generated on the device ----------------------------------------
     t0 = time.time()
     n_reads = int(args.gbases * 1e9 / READ_LEN) // 32 * 32
-    wc, wl = synth.panel_windows(PANEL)
+    if wc is None:
+        wc, wl = synth.panel_windows(PANEL)
     genome = synth.Genome(args.genome_mb * 1_000_000, wc, wl, 2, dev)
     bases, mask, n_pos, n_bases = synth.make_packed_shard(genome, n_reads, READ_LEN, 0.01, seed=1000 + rank)
     del genome
@@ -265,7 +273,8 @@ def ours(args):
     if args.kernel_only:       # variant sweeps: device-resident number only, not a bench line for the driver
         if rank == 0:
             print(json.dumps({"kernel_only": True, "value": value, "unit": "Gbases/s", "kernel_ms": ms_kernel, "ms_per_step": ms_step,
-                              "n_gpus": world, "gbases_per_gpu": n_bases / 1e9, "check": check,
+                              "n_gpus": world, "gbases_per_gpu": n_bases / 1e9, "check": check, "kernel": fp.kernel_name,
+                              "n_sites": int(sites.n_sites), "n_kmers": int(sites.n_kmers), "filter_bits": int(fp.filter_bits),
                               "env": {k: v for k, v in os.environ.items() if k.startswith("NTSM_")}}))
         if world > 1:
             dist.barrier()
@@ -451,8 +460,11 @@ def main():
     ap.add_argument("--genome-mb", type=int, default=int(os.environ.get("NTSM_BENCH_GENOME_MB", 3100)))
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--kernel-only", action="store_true", help="device-resident leg only (kernel variant sweeps)")
+    ap.add_argument("--synthetic-sites", type=int, default=0, help="with --kernel-only: cfg5's synthetic panel of this many sites")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.synthetic_sites and not args.kernel_only:
+        ap.error("--synthetic-sites is a --kernel-only measurement; the bench line is BASELINE configs[1]")
     if args.impl == "reference":
         reference_arm(args)
     else:

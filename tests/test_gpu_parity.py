@@ -400,3 +400,34 @@ def test_pair_table_fold_vs_oracle(oracle, monkeypatch, fold):
     wins = _windows(PANEL, limit=8000)
     reads = _reads(rng, wins, 5000, "ACGTN") + [bytes(rng.choice(b"ACGT") for _ in range(rng.randrange(0, 400))) for _ in range(1500)]
     _check_against_oracle(oracle, PANEL, reads, batch_bases=1 << 18)
+
+
+# ---------------------------------------------------------------- the counts file's consumer
+def test_counts_file_is_accepted_by_the_reference_ntsmEval(tmp_path):
+    """the file our binary prints goes through the reference's own consumer
+    (ntsmEval, src/CompareCounts.hpp:30-114 parses #@TK/#@KS and the six columns): single-sample QC
+    (cov, errorRate, miss, hom, het) equals what it reports for the reference's file, and the two
+    files compare as the same sample."""
+    evalbin = os.path.join(ROOT, "oracle", "_ref", "ntsmEval")
+    if not os.path.exists(evalbin):
+        pytest.skip("oracle/_ref/ntsmEval not built (make -C oracle ref, where /root/reference exists)")
+    d, opts, files = _case_files("gz_single")
+    argv = json.load(open(os.path.join(d, "cmd.json")))["argv"]
+    p = subprocess.run([NTSMCOUNT] + argv, cwd=d, capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()
+    ours, ref = tmp_path / "ours.txt", tmp_path / "ref.txt"
+    ours.write_bytes(p.stdout)
+    ref.write_bytes(open(os.path.join(d, "stdout.txt"), "rb").read())
+
+    def qc(path):
+        o = subprocess.run([evalbin, str(path)], capture_output=True, text=True)
+        assert o.returncode == 0, o.stderr
+        rows = [l.split("\t") for l in (o.stdout + o.stderr).splitlines() if l.startswith(str(path))]
+        return [f.split("Time:")[0] for f in rows[0][1:]]
+
+    assert qc(ours) == qc(ref) and len(qc(ours)) == 5
+    o = subprocess.run([evalbin, "-a", str(ours), str(ref)], capture_output=True, text=True)
+    assert o.returncode == 0, o.stderr
+    hdr, row = [l.split("\t") for l in o.stdout.splitlines() if l.startswith(("sample1", str(ours)))][:2]
+    rec = dict(zip(hdr, row))
+    assert rec["same"] == "1" and float(rec["relate"]) == 1.0 and rec["ibs0"] == "0"
