@@ -44,7 +44,9 @@ struct BatchWriter {
 	}
 
 	// FingerPrint::insertCount(seq, len) (src/FingerPrint.hpp:89) for this producer.  on_submit is
-	// called after every batch this read caused to be submitted (the -m check hooks in there).
+	// called after every batch this read caused to be submitted (the -m check hooks in there); if it
+	// returns true the cap was reached by what is already submitted and the rest of this read is
+	// dropped (the reference stops before it, src/FingerPrint.hpp:67).
 	template <class F> bool append(const char *seq, uint64_t len, F &&on_submit)
 	{
 		uint64_t pos = 0;
@@ -59,12 +61,12 @@ struct BatchWriter {
 			if (r == 1) return true;
 			ntsm_ctx *went = nullptr;
 			if (!submit(&went)) return false;
-			on_submit(went);
+			if (on_submit(went)) return true;
 		}
 	}
 	bool append(const char *seq, uint64_t len)
 	{
-		return append(seq, len, [](ntsm_ctx *) {});
+		return append(seq, len, [](ntsm_ctx *) { return false; });
 	}
 };
 

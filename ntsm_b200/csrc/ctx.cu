@@ -40,6 +40,11 @@ struct ntsm_batch {
 	uint64_t cap_pos = 0;             // usable positions
 	uint64_t n_bases = 0, n_reads = 0;
 	int state = 0;                    // 0 free, 1 acquired, 2 in flight
+	// -m only: where every read of this batch ends (stream position of its separator) and the bases
+	// of the batch up to and including it -- what an exact stop after read i needs (ntsm_trim_to_cap)
+	std::vector<uint32_t> read_end;
+	std::vector<uint64_t> read_bases;
+	uint64_t n_pos = 0;               // data positions as submitted
 };
 
 struct ntsm_ctx {
@@ -75,6 +80,11 @@ struct ntsm_ctx {
 	uint64_t done_kmers = 0, done_hits = 0, done_bases = 0;   // over completed batches
 	uint64_t submitted_bases = 0;
 	uint64_t launches = 0;
+	// exact -m stop: the last batch submitted, a scratch tally, and what launch_count adds per hit
+	ntsm_batch *last_batch = nullptr;
+	unsigned long long *d_scratch_totals = nullptr;
+	uint32_t launch_delta = 1;
+	unsigned long long *launch_totals = nullptr;   // nullptr = d_totals
 	bool reduced = false;
 	ncclComm_t comm = nullptr;
 	int rank = 0, n_ranks = 1;
@@ -206,6 +216,9 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 	if (k != 19 || variant < 0 || variant > 5) variant = 0;
 	if (gm < 13 || gm > 14 || variant >= 4) gm = 14;
 	if (const char *e = getenv("NTSM_SEED_CFG")) c->seed_cfg = std::min(3, std::max(0, atoi(e)));
+	// panels far larger than the human one (cfg 5: 26 M k-mers) saturate a folded pair table and nothing
+	// stays in L2 anyway: measured 318 (unfolded) vs 241 Gbases/s (profiles/r01v12_sweep_cfg5.jsonl)
+	c->pair_fold = live > 5000000 ? 0 : kPairFoldDefault;
 	if (const char *e = getenv("NTSM_PAIR_FOLD")) c->pair_fold = std::min(kPairFoldMax, std::max(0, atoi(e)));
 	if (const char *e = getenv("NTSM_TAIL_POOL")) c->pool_tail = atoi(e) != 0;
 	if (const char *e = getenv("NTSM_GATE_THREADS")) c->gate_threads = atoi(e);
@@ -366,8 +379,9 @@ static int launch_count(ntsm_ctx *c, const uint2 *d_bases, const uint32_t *d_mas
 	P.k = c->cfg.k;
 	P.four = 4;
 	P.pair_word_mask = pair_word_mask(c->pair_fold);
+	P.delta = c->launch_delta;
 	P.counts = c->d_counts;
-	P.totals = c->d_totals;
+	P.totals = c->launch_totals ? c->launch_totals : c->d_totals;
 	const uint64_t tiles = (P.n_chunks + kCountThreads - 1) / kCountThreads;
 	const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)c->sm_count * 16);
 	const unsigned g2 = (unsigned)std::min<uint64_t>((P.n_chunks + kGateThreads - 1) / kGateThreads, (uint64_t)c->sm_count);
@@ -468,6 +482,8 @@ extern "C" int ntsm_acquire_batch(ntsm_ctx *c, ntsm_batch **out)
 				b->state = 1;
 				b->pk.reset(b->h_bases, b->h_mask);
 				b->n_bases = b->n_reads = 0;
+				b->read_end.clear();
+				b->read_bases.clear();
 				*out = b;
 				return NTSM_OK;
 			}
@@ -492,13 +508,20 @@ extern "C" int ntsm_batch_append(ntsm_batch *b, const char *seq, uint64_t len, u
 	const uint64_t start = *pos == 0 ? 0 : from;
 	const uint64_t need = len - start;
 	const uint64_t room = b->cap_pos - b->pk.pos;       // positions left (a multiple of 8, like every read's span)
+	const bool capped = b->ctx->cfg.max_counts != 0;
 	if (read_span(need) <= room) {
 		b->pk.put_read(seq + start, need);
 		b->n_bases += len - *pos;
 		b->n_reads += (*pos == 0);
 		*pos = len;
+		if (capped) {                                        // the read's separator sits right after its last base
+			b->read_end.push_back((uint32_t)(b->pk.pos - read_span(need) + need));
+			b->read_bases.push_back(b->n_bases);
+		}
 		return 1;
 	}
+	// with a -m cap a read is kept whole (the stop is decided read by read) unless it is longer than a batch
+	if (capped && b->pk.pos != 0) return 0;
 	const uint64_t split_min = std::max<uint64_t>(2 * k, std::min<uint64_t>(4096, b->cap_pos / 4));
 	if (b->pk.pos != 0 && room < split_min + 1) return 0;   // full: submit and come back
 	const uint64_t take = room - 1;                          // spans exactly `room`; >= 2k > k-1, so the read always advances
@@ -534,6 +557,8 @@ static int enqueue_batch(ntsm_ctx *c, ntsm_batch *b, const void *src_bases, cons
 	CU(c, cudaEventRecord(b->done, c->compute_stream));
 	b->state = 2;
 	b->n_bases = n_bases;
+	b->n_pos = n_pos;
+	c->last_batch = b;
 	c->submitted_bases += n_bases;
 	c->inflight.push_back(b);
 	c->cv.notify_all();
@@ -630,6 +655,83 @@ extern "C" int ntsm_sync(ntsm_ctx *c)
 	return NTSM_OK;
 }
 
+namespace ntsm {
+__global__ void set_u64_kernel(unsigned long long *p, unsigned long long v) { *p = v; }
+}  // namespace ntsm
+
+// ------------------------------------------------------------------ exact -m stop
+// The reference checks the cap after EVERY read (processSingleRead, src/FingerPrint.hpp:473-488): the
+// counted reads are the shortest prefix whose hits exceed it.  Batches are what the GPU sees, so when
+// the batch just completed pushed the summed tally over the cap, find the read inside it where that
+// happened and make the counters what they would be had the batch ended there: re-run prefixes of the
+// batch (still resident on the device) with delta 0 into a scratch tally to bisect over the recorded
+// read ends, then take the whole batch back out (delta -1) and put the prefix back in (delta +1).
+// A prefix ends at a read's separator; the positions after it that share its 32-position chunk are
+// masked off by patching that one mask word for the duration of a launch.
+// hits_elsewhere = hits on the other GPUs.  Returns 1 if the counters now stop exactly after the
+// deciding read, 0 if nothing could be done (no read ends recorded: the stop stays batch-granular).
+int ntsm_trim_to_cap(ntsm_ctx *c, uint64_t hits_elsewhere, uint64_t cap)
+{
+	if (!c) return NTSM_ERR_ARG;
+	CU(c, cudaSetDevice(c->device));
+	std::lock_guard<std::mutex> g(c->mu);
+	ntsm_batch *b = c->last_batch;
+	if (!b || b->state != 0 || b->read_end.empty() || !c->inflight.empty()) return 0;
+	if (!c->d_scratch_totals) CU(c, cudaMalloc(&c->d_scratch_totals, 3 * sizeof(unsigned long long)));
+	cudaStream_t st = c->compute_stream;
+	unsigned long long out[2] = { 0, 0 };
+	// tallies {TK, hits} of positions [0, e) of the batch, adding `delta` per hit to the counters
+	auto run_prefix = [&](uint64_t e, uint32_t delta) -> int {
+		const uint64_t ce = e / 32;
+		const uint32_t r = (uint32_t)(e & 31);
+		const uint32_t patched = r ? (b->h_mask[ce] | (~0u << r)) : 0;
+		if (r) CU(c, cudaMemcpyAsync(b->d_mask + ce, &patched, 4, cudaMemcpyHostToDevice, st));
+		CU(c, cudaMemsetAsync(c->d_scratch_totals, 0, 3 * sizeof(unsigned long long), st));
+		c->launch_delta = delta;
+		c->launch_totals = c->d_scratch_totals;
+		const int rc = launch_count(c, b->d_bases, b->d_mask, e, st);
+		c->launch_delta = 1;
+		c->launch_totals = nullptr;
+		if (rc) return rc;
+		CU(c, cudaMemcpyAsync(out, c->d_scratch_totals, sizeof out, cudaMemcpyDeviceToHost, st));
+		if (r) CU(c, cudaMemcpyAsync(b->d_mask + ce, b->h_mask + ce, 4, cudaMemcpyHostToDevice, st));
+		CU(c, cudaStreamSynchronize(st));
+		return NTSM_OK;
+	};
+	int rc = run_prefix(b->n_pos, 0);
+	if (rc) return rc;
+	const uint64_t tk_b = out[0], hits_b = out[1];
+	const uint64_t total = hits_elsewhere + c->done_hits;
+	if (total <= cap || hits_b > total) return 0;
+	const uint64_t base = total - hits_b;                      // summed tally before this batch
+	if (base > cap) return 0;                                   // an earlier batch already decided; nothing to trim here
+	const size_t n = b->read_end.size();
+	if ((rc = run_prefix(b->read_end[n - 1], 0))) return rc;
+	if (base + out[1] <= cap) return 0;                         // the cap falls inside a read longer than a batch
+	size_t lo = 0, hi = n - 1;                                  // smallest i with base + hits(prefix i) > cap
+	while (lo < hi) {
+		const size_t mid = lo + (hi - lo) / 2;
+		if ((rc = run_prefix(b->read_end[mid], 0))) return rc;
+		if (base + out[1] > cap) hi = mid;
+		else lo = mid + 1;
+	}
+	if ((rc = run_prefix(b->n_pos, 0xFFFFFFFFu))) return rc;   // the whole batch out ...
+	if ((rc = run_prefix(b->read_end[lo], 1))) return rc;      // ... its deciding prefix back in
+	const uint64_t tk_p = out[0], hits_p = out[1];
+	c->done_kmers = c->done_kmers - tk_b + tk_p;
+	c->done_hits = c->done_hits - hits_b + hits_p;
+	set_u64_kernel<<<1, 1, 0, st>>>(c->d_totals + 0, (unsigned long long)c->done_kmers);
+	set_u64_kernel<<<1, 1, 0, st>>>(c->d_totals + 1, (unsigned long long)c->done_hits);
+	CU(c, cudaGetLastError());
+	CU(c, cudaStreamSynchronize(st));
+	c->launches += 2;
+	const uint64_t dropped = b->n_bases - b->read_bases[lo];
+	c->done_bases -= dropped;
+	c->submitted_bases -= dropped;
+	b->read_end.clear();
+	return 1;
+}
+
 // ------------------------------------------------------------------ multi-GPU
 // stdout is the counts file, so NCCL's version banner must not land there.  NCCL honours
 // NCCL_DEBUG_FILE only for levels above VERSION (2.27: debug.cc), and GPU hosts commonly export
@@ -664,10 +766,6 @@ extern "C" int ntsm_comm_init(ntsm_ctx *c, const void *id, int rank, int n_ranks
 	c->n_ranks = n_ranks;
 	return NTSM_OK;
 }
-
-namespace ntsm {
-__global__ void set_u64_kernel(unsigned long long *p, unsigned long long v) { *p = v; }
-}  // namespace ntsm
 
 // enqueue on the compute stream: base tally -> device, the two all-reduces (if a communicator is
 // attached), the per-site reduce.  No host synchronisation.

@@ -105,7 +105,7 @@ __device__ __forceinline__ uint32_t resolve_one(const CountParams &P, uint32_t l
 	for (;;) {
 		const TableSlot e = P.table[slot];
 		if (e.key == h) {
-			atomicAdd(P.counts + e.idx, 1u);                     // FingerPrint.hpp:93-94
+			atomicAdd(P.counts + e.idx, P.delta);                // FingerPrint.hpp:93-94 (delta = 1)
 			return 1;
 		}
 		if (e.key == kEmptyKey) return 0;

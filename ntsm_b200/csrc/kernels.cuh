@@ -45,6 +45,7 @@ struct CountParams {
 	uint32_t k;
 	uint32_t four;             // = 4, kept in a register so address scaling stays an IMAD (FMA pipe), not an LEA
 	uint32_t pair_word_mask;   // paired-seed kernel: (words of the pair table) - 1
+	uint32_t delta;            // added to counts[idx] per hit: 1 to count, 0xFFFFFFFF to take a batch back out, 0 to only tally
 	uint32_t *counts;
 	unsigned long long *totals;   // [0] valid windows (TK), [1] hits
 };
@@ -84,7 +85,7 @@ __device__ __forceinline__ uint32_t resolve_survivors(const CountParams &P, cons
 		for (;;) {
 			const TableSlot e = P.table[slot];
 			if (e.key == h) {
-				atomicAdd(P.counts + e.idx, 1u);                 // FingerPrint.hpp:93-94
+				atomicAdd(P.counts + e.idx, P.delta);            // FingerPrint.hpp:93-94 (delta = 1)
 				++hits;
 				break;
 			}

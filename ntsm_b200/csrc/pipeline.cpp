@@ -24,6 +24,7 @@ struct Shared {
 	uint32_t n_paths;
 	int verbose;
 	uint64_t max_counts;
+	bool exact_cap = false;                     // one parser thread: the -m stop is trimmed to the deciding read
 	uint32_t helpers = 0, helpers_extra = 0;    // idle -t threads lent to each parser for block-parallel inflate
 	std::atomic<uint32_t> next_file{0};
 	std::atomic<uint64_t> next_batch{0};
@@ -58,10 +59,26 @@ void worker(Shared &sh, uint32_t wi)
 	};
 	// -m: wait for the batch just submitted so the stop decision does not depend on timing
 	// (deterministic for one parser thread, like the reference's -t 1)
-	auto after_submit = [&](ntsm_ctx *went) {
-		if (!sh.max_counts || !went) return;
+	auto after_submit = [&](ntsm_ctx *went) -> bool {
+		if (!sh.max_counts) return false;
+		if (!went || sh.early.load()) return sh.early.load();
 		ntsm_sync(went);
-		check_cap(sh);
+		uint64_t hits = 0, own = 0;
+		for (uint32_t i = 0; i < sh.n_ctx; ++i) {
+			uint64_t h = 0;
+			ntsm_poll_totals(sh.ctxs[i], nullptr, &h, nullptr, nullptr);
+			hits += h;
+			if (sh.ctxs[i] == went) own = h;
+		}
+		if (hits <= sh.max_counts) return false;
+		// FingerPrint.hpp:476-487 checks after every read: with one parser thread (the reference's
+		// deterministic -t 1) the batch is cut back to the read that crossed the cap
+		if (sh.exact_cap) {
+			const int rc = ntsm_trim_to_cap(went, hits - own, sh.max_counts);
+			if (rc < 0) set_error(rc, ntsm_last_error(went));
+		}
+		sh.early.store(true);
+		return true;
 	};
 	for (;;) {
 		const uint32_t fi = sh.next_file.fetch_add(1);
@@ -99,6 +116,7 @@ extern "C" int ntsm_count_files(ntsm_ctx *const *ctxs, uint32_t n_ctx, const cha
 	uint32_t nt = threads ? threads : 1;
 	if (nt > n_paths) nt = n_paths ? n_paths : 1;                   // the reference never uses more than #files (:47-48) ...
 	const uint32_t spare = (threads ? threads : 1) - nt;            // ... the rest of -t inflates BGZF blocks for the parsers (gzsource.h)
+	sh.exact_cap = nt == 1;
 	sh.helpers = spare / nt;
 	sh.helpers_extra = spare % nt;
 	std::vector<std::thread> pool;

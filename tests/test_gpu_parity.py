@@ -32,8 +32,6 @@ def test_cli_matches_reference_fixture(name):
     """Our ntsmCount binary vs what the reference binary printed for the same argv."""
     d, opts, files = _case_files(name)
     argv = json.load(open(os.path.join(d, "cmd.json")))["argv"]
-    if opts["m"] > 0:
-        argv = ["--batch-bases", "4096"] + argv      # -m is checked per batch: make batches read-sized
     p = subprocess.run([NTSMCOUNT] + argv, cwd=d, capture_output=True)
     ref_rc = int(open(os.path.join(d, "rc.txt")).read())
     ref_out = open(os.path.join(d, "stdout.txt"), "rb").read()
@@ -43,10 +41,8 @@ def test_cli_matches_reference_fixture(name):
         assert [l for l in _filter_err(p.stderr.decode()) if "collision" in l] == [l for l in _filter_err(ref_err) if "collision" in l]
         return
     assert p.returncode == 0, p.stderr.decode()
-    if opts["m"] > 0 and "Reached desired" in ref_err:
-        # early stop is batch-granular here: the prefix property is tested below
-        assert "Reached desired (-m) threshold" in p.stderr.decode()
-        return
+    # -m with one parser thread stops after the very read the reference stops after (ntsm_trim_to_cap),
+    # so these fixtures are compared byte for byte like all the others
     assert p.stdout == ref_out
     keep = lambda t: [l for l in t.splitlines() if l.startswith(("Warning", "Reached", "Total ", "Distinct ", "Sites Covered"))]
     assert keep(p.stderr.decode()) == keep(ref_err)
@@ -250,10 +246,52 @@ def test_properties_linearity_strand_and_reset(oracle):
     fp.close()
 
 
+@pytest.mark.parametrize("name", ["panel300_m1", "panel300_m0.5_two_files"])
+@pytest.mark.parametrize("batch", ["4096", "30000", "1000003", None])
+def test_m_cap_stops_after_the_same_read_as_the_reference(name, batch):
+    """-m, one parser thread (the reference's deterministic -t 1): whatever the batch size -- the cap
+    crossed in the first batch, the last one, one holding a single read or thousands -- the counts
+    file and the totals are the reference's."""
+    d, opts, files = _case_files(name)
+    argv = json.load(open(os.path.join(d, "cmd.json")))["argv"]
+    if batch:
+        argv = ["--batch-bases", batch] + argv
+    p = subprocess.run([NTSMCOUNT] + argv, cwd=d, capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()
+    assert p.stdout == open(os.path.join(d, "stdout.txt"), "rb").read()
+    keep = lambda t: [l for l in t.splitlines() if l.startswith(("Reached", "Total ", "Distinct ", "Sites Covered"))]
+    assert keep(p.stderr.decode()) == keep(open(os.path.join(d, "stderr.txt")).read())
+
+
+def test_m_cap_exact_vs_oracle_many_caps(oracle, tmp_path):
+    """computeCounts with a cap, one thread: for a spread of caps and batch sizes the counts equal the
+    oracle's read-by-read stop (src/FingerPrint.hpp:473-488), per k-mer."""
+    sites = os.path.join(GOLDEN, "shared", "sites300.fa")
+    rng = random.Random(19)
+    reads = _reads(rng, _windows(sites), 3000) + [rng.choice(_windows(sites)).encode() * 40 for _ in range(30)]   # some long reads
+    rng.shuffle(reads)
+    f = tmp_path / "reads.fa"
+    f.write_bytes(b"".join(b">r%d\n%s\n" % (i, r) for i, r in enumerate(reads)))
+    n_early = 0
+    for cov, bb in ((0.05, 8192), (0.3, 8192), (1.0, 50000), (2.0, 1 << 20), (3.5, 12345), (1000.0, 8192)):
+        fp = ntsm_b200.FingerPrint(sites, cov_thresh=cov, batch_bases=bb)
+        fp.computeCounts([str(f)], threads=1)
+        o = oracle.fingerprint(sites, 19, False, cov)
+        o.count_file(str(f))
+        assert fp.counts_text() == o.counts_text(), (cov, bb)
+        assert fp.printInfoSummary() == o.summary(), (cov, bb)
+        assert np.array_equal(fp.kmer_counts(), o.lists()[2]), (cov, bb)
+        assert bool(fp.early_term) == o.early_term, (cov, bb)
+        n_early += o.early_term
+        fp.close()
+    assert n_early >= 3
+
+
 def test_m_cap_prefix_property(oracle, tmp_path):
-    """-m: we stop at a batch boundary.  Whatever prefix of the file was consumed, the counts must
-    equal the oracle's counts on exactly that prefix, the cap must have been exceeded by it, and
-    not exceeded one batch earlier."""
+    """-m, the weaker property that also holds where the stop stays batch-granular (several parser
+    threads, where the reference itself is racy): whatever prefix of the file was consumed, the
+    counts must equal the oracle's counts on exactly that prefix, the cap must have been exceeded by
+    it, and the prefix is at most a batch longer than the reference's."""
     sites = os.path.join(GOLDEN, "shared", "sites300.fa")
     rng = random.Random(9)
     reads = _reads(rng, _windows(sites), 4000)

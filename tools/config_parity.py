@@ -172,9 +172,13 @@ def main():
                 if want is None:
                     info["verdict"] = "no expected entry"
                     ok = False
+                elif cfg == "cfg4m" and info["rc"] == 0 and info.get("sha256") == want.get("sha256") and info["stdout_bytes"] == want.get("stdout_bytes"):
+                    # -m -t 1: the stop is trimmed to the read that crosses the cap, like the reference's
+                    info["verdict"] = "bit-exact"
+                    info["reference"] = {k: want.get(k) for k in ("bases", "hits", "seconds", "tool_seconds")}
                 elif cfg == "cfg4m":
-                    # -m: we stop at a batch boundary (2^22 positions per batch in the CLI), the reference after
-                    # the read that crosses the cap.  Same file order, so our reads are a superset prefix.
+                    # fallback judgement (several parser threads / GPUs racing): a batch-granular stop, the
+                    # reference after the read that crosses the cap.  Same file order, so our reads are a superset prefix.
                     nocap = expected[key].get("cfg4")
                     slack = 2 * (1 << 22) * max(1, args.gpus)
                     good = info["rc"] == 0 and info["early_stop"] and want["bases"] <= info["bases"] <= want["bases"] + slack
