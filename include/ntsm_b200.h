@@ -230,9 +230,11 @@ int ntsm_reader_open2(ntsm_reader **out, const char *path, int helpers);
 /* Reads every file with `threads` parser threads (one file per thread at a time, like the
  * reference's omp parallel for over files), packs reads into pinned batches and streams batch i
  * to ctxs[i % n_ctx].  With a -m cap (cfg.max_counts of ctxs[0]) the summed hit tally is checked
- * after every submitted batch against the batches completed so far (batch granularity, one batch
- * of lag); parsing stops once it is exceeded and *early (nullable) is set = m_earlyTerm.
- * Every read parsed before the stop is counted.  Returns NTSM_ERR_IO (text in ntsm_last_error)
+ * after every submitted batch; parsing stops once it is exceeded and *early (nullable) is set =
+ * m_earlyTerm.  With one parser thread (threads == 1 or one file: the reference's deterministic
+ * -t 1) the last batch is then cut back to the read that crossed the cap, so the counters are
+ * exactly the reference's (src/FingerPrint.hpp:473-488); with more threads the stop is
+ * batch-granular and every read parsed before it is counted.  Returns NTSM_ERR_IO (text in ntsm_last_error)
  * if a file cannot be opened. */
 int ntsm_count_files(ntsm_ctx *const *ctxs, uint32_t n_ctx, const char *const *paths, uint32_t n_paths,
                      uint32_t threads, int verbose, int *early);
