@@ -228,11 +228,13 @@ def ours(args):
 
     # ---- this rank's shard, generated on the device ----------------------------------------
     t0 = time.time()
-    n_reads = int(args.gbases * 1e9 / READ_LEN) // 32 * 32
+    read_len = args.read_len
+    n_reads = int(args.gbases * 1e9 / read_len) // 32 * 32
     if wc is None:
         wc, wl = synth.panel_windows(PANEL)
     genome = synth.Genome(args.genome_mb * 1_000_000, wc, wl, 2, dev)
-    bases, mask, n_pos, n_bases = synth.make_packed_shard(genome, n_reads, READ_LEN, 0.01, seed=1000 + rank)
+    bases, mask, n_pos, n_bases = synth.make_packed_shard(genome, n_reads, read_len, args.err, seed=1000 + rank,
+                                                          chunk_reads=max(32, ((1 << 27) // read_len) // 32 * 32))
     del genome
     torch.cuda.synchronize()
     alg_bytes = (3 * n_bases + 7) // 8 + 8 * n_reads          # 2-bit + N-mask per base, one u64 offset per read
@@ -274,6 +276,7 @@ def ours(args):
         if rank == 0:
             print(json.dumps({"kernel_only": True, "value": value, "unit": "Gbases/s", "kernel_ms": ms_kernel, "ms_per_step": ms_step,
                               "n_gpus": world, "gbases_per_gpu": n_bases / 1e9, "check": check, "kernel": fp.kernel_name,
+                              "read_len": read_len, "err": args.err,
                               "n_sites": int(sites.n_sites), "n_kmers": int(sites.n_kmers), "filter_bits": int(fp.filter_bits),
                               "env": {k: v for k, v in os.environ.items() if k.startswith("NTSM_")}}))
         if world > 1:
@@ -461,10 +464,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--kernel-only", action="store_true", help="device-resident leg only (kernel variant sweeps)")
     ap.add_argument("--synthetic-sites", type=int, default=0, help="with --kernel-only: cfg5's synthetic panel of this many sites")
+    ap.add_argument("--read-len", type=int, default=READ_LEN, help="with --kernel-only: fixed read length (cfg3-like long reads)")
+    ap.add_argument("--err", type=float, default=0.01, help="with --kernel-only: substitution rate")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.synthetic_sites and not args.kernel_only:
-        ap.error("--synthetic-sites is a --kernel-only measurement; the bench line is BASELINE configs[1]")
+    if (args.synthetic_sites or args.read_len != READ_LEN or args.err != 0.01) and not args.kernel_only:
+        ap.error("--synthetic-sites / --read-len / --err are --kernel-only measurements; the bench line is BASELINE configs[1]")
     if args.impl == "reference":
         reference_arm(args)
     else:
