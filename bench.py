@@ -234,7 +234,8 @@ def ours(args):
         wc, wl = synth.panel_windows(PANEL)
     genome = synth.Genome(args.genome_mb * 1_000_000, wc, wl, 2, dev)
     bases, mask, n_pos, n_bases = synth.make_packed_shard(genome, n_reads, read_len, args.err, seed=1000 + rank,
-                                                          chunk_reads=max(32, ((1 << 27) // read_len) // 32 * 32))
+                                                          chunk_reads=(1 << 20) if read_len == READ_LEN else max(32, ((1 << 27) // read_len) // 32 * 32))
+    # (the ASCII e2e leg regenerates the first reads of this shard chunk by chunk with the same seeds: 2^20 reads per chunk)
     del genome
     torch.cuda.synchronize()
     alg_bytes = (3 * n_bases + 7) // 8 + 8 * n_reads          # 2-bit + N-mask per base, one u64 offset per read

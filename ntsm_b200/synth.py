@@ -53,7 +53,9 @@ def panel_windows(path, limit_sites=None):
     for i, w in enumerate(wins):
         codes[i, :len(w)] = lut[np.frombuffer(w.encode(), np.uint8)]
         lens[i] = len(w)
-    np.savez(cache, codes=codes, lens=lens)
+    tmp = "%s.%d.tmp.npz" % (cache, os.getpid())         # several ranks may build the cache at once: publish it atomically
+    np.savez(tmp, codes=codes, lens=lens)
+    os.replace(tmp, cache)
     return codes, lens
 
 
