@@ -41,6 +41,30 @@ def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries do not know that: NCCL prints its version banner
+# to stdout when the host exports NCCL_DEBUG=VERSION (and honours NCCL_DEBUG_FILE only above that
+# level).  So the real stdout is put aside, file descriptor 1 is pointed at stderr for the life of the
+# process, and the JSON line is the only thing ever written to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
+def emit(obj):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def env_int(name, default):
     return int(os.environ.get(name, default))
 
@@ -167,7 +191,7 @@ def reference_arm(args):
     ms = 1000 * sum(times) / len(times)
     v = bases / (ms / 1000) / 1e9
     sample = "%d x %dbp reads of the bench workload in %d FASTQ files (-t only parallelises over files)" % (n_reads, READ_LEN, cores)
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Gbases/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic", "config": config_dict(args, args.gbases),
@@ -275,7 +299,7 @@ def ours(args):
 
     if args.kernel_only:       # variant sweeps: device-resident number only, not a bench line for the driver
         if rank == 0:
-            print(json.dumps({"kernel_only": True, "value": value, "unit": "Gbases/s", "kernel_ms": ms_kernel, "ms_per_step": ms_step,
+            emit(({"kernel_only": True, "value": value, "unit": "Gbases/s", "kernel_ms": ms_kernel, "ms_per_step": ms_step,
                               "n_gpus": world, "gbases_per_gpu": n_bases / 1e9, "check": check, "kernel": fp.kernel_name,
                               "read_len": read_len, "err": args.err,
                               "n_sites": int(sites.n_sites), "n_kmers": int(sites.n_kmers), "filter_bits": int(fp.filter_bits),
@@ -448,7 +472,7 @@ def ours(args):
             "check": dict(check, e2e_TK=int(a_rows[4][0]), e2e_packed_TK=e2e_check, ascii_equals_packed=ascii_check),
             "parity_vs_reference_on_cpu_sample": parity,
         }
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -468,6 +492,7 @@ def main():
     ap.add_argument("--read-len", type=int, default=READ_LEN, help="with --kernel-only: fixed read length (cfg3-like long reads)")
     ap.add_argument("--err", type=float, default=0.01, help="with --kernel-only: substitution rate")
     args = ap.parse_args()
+    protect_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if (args.synthetic_sites or args.read_len != READ_LEN or args.err != 0.01) and not args.kernel_only:
         ap.error("--synthetic-sites / --read-len / --err are --kernel-only measurements; the bench line is BASELINE configs[1]")
