@@ -4,7 +4,13 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ntsm_b200.h"
@@ -13,50 +19,77 @@
 
 namespace {
 
-// exact set of 64-bit keys -> dense index (open addressing, grows by doubling)
-class KeyIndex {
+// Exact "first occurrence wins" over all k-mer occurrences of the site file, in parallel.
+//
+// The reference inserts k-mers one by one, in file order, into a hash map (src/FingerPrint.hpp:
+// 516-548): the first occurrence of a hash value owns it, every later one is a collision.  The same
+// partition falls out of an order-free formulation: every occurrence g (numbered in file order)
+// writes min(g) into the slot of its key; afterwards occurrence g is a first occurrence iff the
+// slot holds g.  That is two embarrassingly parallel passes over a lock-free open-addressing table
+// (64-bit CAS to claim a key, CAS-min on the value), which matters for panels like BASELINE's
+// config 5 (26 M k-mers: the serial map took most of the CLI's wall time).
+class MinIndexTable {
 public:
-	KeyIndex() { resize(1u << 16); }
-	// returns the existing index, or inserts `idx` and returns UINT32_MAX
-	uint32_t find_or_insert(uint64_t key, uint32_t idx)
+	explicit MinIndexTable(uint64_t n_keys)
 	{
-		if ((size_ + 1) * 2 > keys_.size()) resize(keys_.size() * 2);
-		size_t i = slot(key);
-		while (vals_[i] != kEmpty) {
-			if (keys_[i] == key) return vals_[i];
-			i = (i + 1) & (keys_.size() - 1);
-		}
-		keys_[i] = key;
-		vals_[i] = idx;
-		++size_;
-		return kEmpty;
+		cap_ = 1024;
+		while (cap_ < 2 * n_keys) cap_ <<= 1;
+		keys_.reset(new std::atomic<uint64_t>[cap_]);
+		vals_.reset(new std::atomic<uint32_t>[cap_]);
 	}
-	size_t size() const { return size_; }
+	void clear_range(uint64_t lo, uint64_t hi)
+	{
+		for (uint64_t i = lo; i < hi; ++i) {
+			keys_[i].store(kEmptyKey, std::memory_order_relaxed);
+			vals_[i].store(0xFFFFFFFFu, std::memory_order_relaxed);
+		}
+	}
+	uint64_t capacity() const { return cap_; }
+	void put_min(uint64_t key, uint32_t g)
+	{
+		uint64_t i = slot(key);
+		for (;;) {
+			uint64_t k = keys_[i].load(std::memory_order_acquire);
+			if (k == kEmptyKey && keys_[i].compare_exchange_strong(k, key, std::memory_order_acq_rel)) k = key;
+			if (k == key) {
+				uint32_t cur = vals_[i].load(std::memory_order_relaxed);
+				while (g < cur && !vals_[i].compare_exchange_weak(cur, g, std::memory_order_relaxed)) {}
+				return;
+			}
+			i = (i + 1) & (cap_ - 1);
+		}
+	}
+	uint32_t get(uint64_t key) const
+	{
+		uint64_t i = slot(key);
+		while (keys_[i].load(std::memory_order_relaxed) != key) i = (i + 1) & (cap_ - 1);
+		return vals_[i].load(std::memory_order_relaxed);
+	}
 
 private:
-	static constexpr uint32_t kEmpty = 0xFFFFFFFFu;
-	size_t slot(uint64_t k) const
+	static constexpr uint64_t kEmptyKey = ~0ull;          // hash64 values have at most 62 bits
+	uint64_t slot(uint64_t k) const
 	{
 		k ^= k >> 31;
 		k *= 0x9E3779B97F4A7C15ULL;
-		return (size_t)(k >> 20) & (keys_.size() - 1);
+		return (k >> 20) & (cap_ - 1);
 	}
-	void resize(size_t cap)
-	{
-		std::vector<uint64_t> ok;
-		std::vector<uint32_t> ov;
-		ok.swap(keys_);
-		ov.swap(vals_);
-		keys_.assign(cap, 0);
-		vals_.assign(cap, kEmpty);
-		size_ = 0;
-		for (size_t i = 0; i < ok.size(); ++i)
-			if (ov[i] != kEmpty) find_or_insert(ok[i], ov[i]);
-	}
-	std::vector<uint64_t> keys_;
-	std::vector<uint32_t> vals_;
-	size_t size_ = 0;
+	uint64_t cap_ = 0;
+	std::unique_ptr<std::atomic<uint64_t>[]> keys_;
+	std::unique_ptr<std::atomic<uint32_t>[]> vals_;
 };
+
+template <class F> void parallel_for(unsigned n_threads, uint64_t n, F &&body)   // body(thread, lo, hi)
+{
+	if (n_threads <= 1 || n < 2) {
+		body(0u, (uint64_t)0, n);
+		return;
+	}
+	std::vector<std::thread> th;
+	for (unsigned t = 0; t < n_threads; ++t)
+		th.emplace_back([&, t] { body(t, n * t / n_threads, n * (t + 1) / n_threads); });
+	for (auto &x : th) x.join();
+}
 
 }  // namespace
 
@@ -80,42 +113,118 @@ extern "C" int ntsm_sites_load(ntsm_sites **out, const char *path, uint32_t k, i
 	ntsm_sites *s = new ntsm_sites();
 	s->k = k;
 	s->allow_dupes = allow_dupes != 0;
-	KeyIndex index;
-	std::vector<uint32_t> dupes;
 	const uint64_t m = ntsm::kmer_mask(k);
 	const unsigned shift = 2 * (k - 1);
+
+	// 1. the records (kseq grammar), sequences and names kept back to back                       :508
+	std::string seqs, names;
+	std::vector<uint64_t> seq_off(1, 0), name_off(1, 0);
 	int64_t l;
-	while ((l = rd.next()) >= 0) {                                   // :508
-		const bool is_ref = (s->n_records % 2) == 0;                 // :510
-		s->allele_off.push_back((uint32_t)s->hashes.size());
-		const char *seq = rd.seq();
-		uint64_t fw = 0, rv = 0;
-		unsigned run = 0;
-		for (int64_t p = 0; p < l; ++p) {                            // KseqHashIterator :95-112
-			const unsigned c = ntsm::nt4((unsigned char)seq[p]);
-			if (c < 4) {
-				fw = ((fw << 2) | c) & m;
-				rv = (rv >> 2) | ((uint64_t)(3 - c) << shift);
-				if (++run >= k) {
-					const uint64_t hv = ntsm::hash64(fw < rv ? fw : rv, m);
-					const uint32_t prev = index.find_or_insert(hv, (uint32_t)s->hashes.size());
-					if (prev != 0xFFFFFFFFu) {                       // :520-524 / :541-545
-						char w[512];
-						snprintf(w, sizeof w, "Warning: %s of %s file has a k-mer collision at pos: %llu", rd.name(),
-						         is_ref ? "REF" : "VAR", (unsigned long long)(p + 1));
-						s->warnings.emplace_back(w);
-						dupes.push_back(prev);
-					} else {                                         // :526-527 / :547-548
-						s->hashes.push_back(hv);
+	while ((l = rd.next()) >= 0) {
+		seqs.append(rd.seq(), (size_t)l);
+		seq_off.push_back(seqs.size());
+		names.append(rd.name());
+		name_off.push_back(names.size());
+	}
+	rd.close();
+	const uint64_t n_rec = seq_off.size() - 1;
+	s->n_records = (uint32_t)n_rec;
+
+	unsigned n_threads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+	if (seqs.size() < (1u << 20)) n_threads = 1;           // small panels: not worth starting threads
+	if (const char *e = getenv("NTSM_SITES_THREADS")) n_threads = (unsigned)std::min(256, std::max(1, atoi(e)));
+
+	// 2. every k-mer occurrence of every record (KseqHashIterator :95-112 + hash64), records split
+	//    over the threads in contiguous ranges: (hash, 1-based end position) in file order
+	std::vector<std::vector<uint64_t>> t_hash(n_threads);
+	std::vector<std::vector<uint32_t>> t_pos(n_threads);
+	std::vector<uint32_t> rec_occ(n_rec + 1, 0);            // occurrences per record, then their prefix sum
+	parallel_for(n_threads, n_rec, [&](unsigned t, uint64_t lo, uint64_t hi) {
+		std::vector<uint64_t> &H = t_hash[t];
+		std::vector<uint32_t> &P = t_pos[t];
+		for (uint64_t r = lo; r < hi; ++r) {
+			const char *seq = seqs.data() + seq_off[r];
+			const uint64_t len = seq_off[r + 1] - seq_off[r];
+			uint64_t fw = 0, rv = 0;
+			unsigned run = 0;
+			uint32_t cnt = 0;
+			for (uint64_t p = 0; p < len; ++p) {
+				const unsigned c = ntsm::nt4((unsigned char)seq[p]);
+				if (c < 4) {
+					fw = ((fw << 2) | c) & m;
+					rv = (rv >> 2) | ((uint64_t)(3 - c) << shift);
+					if (++run >= k) {
+						H.push_back(ntsm::hash64(fw < rv ? fw : rv, m));
+						P.push_back((uint32_t)(p + 1));
+						++cnt;
 					}
+				} else {
+					fw = rv = 0;
+					run = 0;
 				}
-			} else {
-				fw = rv = 0;
-				run = 0;
+			}
+			rec_occ[r + 1] = cnt;
+		}
+	});
+	for (uint64_t r = 0; r < n_rec; ++r) rec_occ[r + 1] += rec_occ[r];
+	const uint64_t n_occ = rec_occ[n_rec];
+	if (n_occ >= 0xFFFFFFFFull) {
+		delete s;
+		return NTSM_ERR_ARG;
+	}
+	std::vector<uint64_t> occ_hash(n_occ);
+	std::vector<uint32_t> occ_pos(n_occ);
+	{
+		uint64_t at = 0;
+		for (unsigned t = 0; t < n_threads; ++t) {         // thread t's records precede thread t+1's
+			if (!t_hash[t].empty()) {
+				memcpy(occ_hash.data() + at, t_hash[t].data(), t_hash[t].size() * 8);
+				memcpy(occ_pos.data() + at, t_pos[t].data(), t_pos[t].size() * 4);
+			}
+			at += t_hash[t].size();
+			std::vector<uint64_t>().swap(t_hash[t]);
+			std::vector<uint32_t>().swap(t_pos[t]);
+		}
+	}
+
+	// 3. first occurrence of every hash value: min over occurrence numbers, then read back
+	std::vector<uint32_t> first_of(n_occ);
+	{
+		MinIndexTable tab(n_occ);
+		parallel_for(n_threads, tab.capacity(), [&](unsigned, uint64_t lo, uint64_t hi) { tab.clear_range(lo, hi); });
+		parallel_for(n_threads, n_occ, [&](unsigned, uint64_t lo, uint64_t hi) {
+			for (uint64_t g = lo; g < hi; ++g) tab.put_min(occ_hash[g], (uint32_t)g);
+		});
+		parallel_for(n_threads, n_occ, [&](unsigned, uint64_t lo, uint64_t hi) {
+			for (uint64_t g = lo; g < hi; ++g) first_of[g] = tab.get(occ_hash[g]);
+		});
+	}
+
+	// 4. file order again: dense indices for first occurrences, a warning and a dupe entry for the rest
+	std::vector<uint32_t> dupes;
+	std::vector<uint32_t> dense_of(n_occ);
+	uint64_t n_first = 0;
+	for (uint64_t g = 0; g < n_occ; ++g) n_first += first_of[g] == g;
+	s->hashes.reserve(n_first);
+	s->allele_off.reserve(n_rec + 2);
+	s->names.reserve(n_rec / 2 + 1);
+	for (uint64_t r = 0; r < n_rec; ++r) {
+		const bool is_ref = (r % 2) == 0;                            // :510
+		s->allele_off.push_back((uint32_t)s->hashes.size());
+		const std::string name(names.data() + name_off[r], names.data() + name_off[r + 1]);
+		for (uint64_t g = rec_occ[r]; g < rec_occ[r + 1]; ++g) {
+			if (first_of[g] == g) {                                  // :526-527 / :547-548
+				dense_of[g] = (uint32_t)s->hashes.size();
+				s->hashes.push_back(occ_hash[g]);
+			} else {                                                 // :520-524 / :541-545
+				char w[512];
+				snprintf(w, sizeof w, "Warning: %s of %s file has a k-mer collision at pos: %llu", name.c_str(),
+				         is_ref ? "REF" : "VAR", (unsigned long long)occ_pos[g]);
+				s->warnings.emplace_back(w);
+				dupes.push_back(dense_of[first_of[g]]);
 			}
 		}
-		if (is_ref) s->names.emplace_back(rd.name());                // :530
-		s->n_records++;
+		if (is_ref) s->names.push_back(name);                        // :530
 	}
 	s->allele_off.push_back((uint32_t)s->hashes.size());
 	if (s->n_records % 2) s->allele_off.push_back((uint32_t)s->hashes.size());   // absent var list = empty

@@ -7,6 +7,7 @@ import json
 import os
 import random
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -278,3 +279,46 @@ def test_format_counts_aborts_like_reference(L):
     s = ntsm_b200.SiteSet(opts["sites"], 19, False)
     z = np.zeros(s.n_sites, np.uint32)
     assert L.ntsm_format_counts(s._h, z.ctypes.data, z.ctypes.data, z.ctypes.data, z.ctypes.data, 0, None, 0) == -134
+
+
+@pytest.mark.parametrize("threads", ["1", "3", "8", "32"])
+def test_site_table_parallel_first_wins_with_many_duplicates(L, oracle, tmp_path, monkeypatch, threads):
+    """ntsm_sites_load finds first occurrences with a parallel min-over-occurrence-number table
+    (sites.cpp); the result must not depend on the thread count and must equal the oracle's serial
+    insert loop (src/FingerPrint.hpp:506-563) -- dense order, per-site offsets, erased flags and the
+    collision warnings in file order -- on a panel full of duplicates: k-mers repeated inside a
+    record, between the two alleles of a site, and between sites far apart."""
+    import random
+    rng = random.Random(31)
+    pool = ["".join(rng.choice("ACGT") for _ in range(19)) for _ in range(300)]
+    recs = []
+    for i in range(1500):
+        for tag in ("ref", "var"):
+            kms = [rng.choice(pool) if rng.random() < 0.3 else "".join(rng.choice("ACGT") for _ in range(19)) for _ in range(rng.randrange(1, 9))]
+            if rng.random() < 0.1:
+                kms.append(kms[0])                                   # the same k-mer twice in one record
+            body = "N".join(kms)
+            if rng.random() < 0.2:
+                body = body.lower()
+            recs.append(">site%d %s\n%s\n" % (i, tag, body))
+    recs.append(">odd ref\n%s\n" % pool[0])                           # odd record count
+    p = tmp_path / "dups.fa"
+    p.write_text("".join(recs))
+    monkeypatch.setenv("NTSM_SITES_THREADS", threads)
+    for dupes in (False, True):
+        s = ntsm_b200.SiteSet(str(p), 19, dupes)
+        fp = oracle.fingerprint(str(p), 19, dupes, 0)
+        hs, off, cnt = fp.lists()
+        assert s.n_sites == fp.n_sites and s.table_size == fp.table_size
+        assert np.array_equal(s.hashes, hs) and np.array_equal(s.allele_off, off)
+        assert np.array_equal(s.erased.astype(bool), cnt == 0xFFFFFFFF)
+        assert s.names == fp.names()
+        assert len(s.warnings) > 1000
+    # the warnings are the reference's own, in its order: compare with the real binary when it is here
+    ref = os.path.join(ROOT, "oracle", "_ref", "ntsmCount")
+    if os.path.exists(ref):
+        reads = tmp_path / "r.fa"
+        reads.write_text(">r\nACGT\n")
+        out = subprocess.run([ref, "-d", "-s", str(p), str(reads)], capture_output=True, text=True)
+        want = [l for l in out.stderr.splitlines() if "k-mer collision" in l]
+        assert s.warnings == want
