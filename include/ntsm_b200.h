@@ -225,6 +225,9 @@ int ntsm_gz_fell_back(const ntsm_gz *g);
 void ntsm_gz_close(ntsm_gz *g);
 uint32_t ntsm_crc32(uint32_t crc, const void *buf, uint64_t len);   /* the CRC-32 of gzip trailers (carry-less multiply when available) */
 int ntsm_reader_open2(ntsm_reader **out, const char *path, int helpers);
+/* which newline scanner the reader's FASTQ fast path uses: "avx512", "avx2" or "memchr" (picked from the
+ * CPU at load time).  force: NULL = just ask; "" = back to automatic; a name = use it if the CPU can. */
+const char *ntsm_scan_isa(const char *force);
 
 /* ---------------- whole path: FingerPrint::computeCounts (src/FingerPrint.hpp:46-87) -------- */
 /* Reads every file with `threads` parser threads (one file per thread at a time, like the

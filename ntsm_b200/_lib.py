@@ -84,6 +84,7 @@ _SIGS = {
     "ntsm_reader_name": (C.c_char_p, [_P]),
     "ntsm_reader_close": (None, [_P]),
     "ntsm_reader_open2": (C.c_int, [C.POINTER(_P), C.c_char_p, C.c_int]),
+    "ntsm_scan_isa": (C.c_char_p, [C.c_char_p]),
     "ntsm_gz_open": (C.c_int, [C.POINTER(_P), C.c_char_p, C.c_int]),
     "ntsm_gz_read": (C.c_int, [_P, C.c_void_p, C.c_uint]),
     "ntsm_gz_mode": (C.c_char_p, [_P]),

@@ -1,6 +1,8 @@
 // fastx.cpp -- see fastx.h.  Grammar per vendor/kseq.h:178-219; return codes per :171-176.
 #include "fastx.h"
 
+#include <immintrin.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/ntsm_b200.h"
@@ -97,6 +99,89 @@ const char *FastxReader::name()
 	return name_.c_str();
 }
 
+// The next (up to) four '\n' positions at or after p, before e.  A FASTQ record is four lines, and four
+// memchr calls per ~300-byte record were most of the fast path's time (call overhead, not bytes);
+// one pass of 64-byte compares finds all four.
+namespace {
+
+__attribute__((target("avx512f,avx512bw,bmi"))) int newlines4_avx512(const unsigned char *p, const unsigned char *e, const unsigned char **out)
+{
+	int found = 0;
+	const __m512i nl = _mm512_set1_epi8('\n');
+	while (p + 64 <= e) {
+		uint64_t m = _mm512_cmpeq_epi8_mask(_mm512_loadu_si512((const void *)p), nl);
+		while (m) {
+			out[found++] = p + __builtin_ctzll(m);
+			if (found == 4) return 4;
+			m &= m - 1;
+		}
+		p += 64;
+	}
+	if (p < e) {
+		const __mmask64 keep = ~0ull >> (64 - (e - p));
+		uint64_t m = _mm512_cmpeq_epi8_mask(_mm512_maskz_loadu_epi8(keep, (const void *)p), nl) & keep;
+		while (m) {
+			out[found++] = p + __builtin_ctzll(m);
+			if (found == 4) return 4;
+			m &= m - 1;
+		}
+	}
+	return found;
+}
+
+__attribute__((target("avx2,bmi"))) int newlines4_avx2(const unsigned char *p, const unsigned char *e, const unsigned char **out)
+{
+	int found = 0;
+	const __m256i nl = _mm256_set1_epi8('\n');
+	while (p + 32 <= e) {
+		uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256((const __m256i *)p), nl));
+		while (m) {
+			out[found++] = p + __builtin_ctz(m);
+			if (found == 4) return 4;
+			m &= m - 1;
+		}
+		p += 32;
+	}
+	while (p < e && found < 4) {
+		const unsigned char *q = (const unsigned char *)memchr(p, '\n', (size_t)(e - p));
+		if (!q) break;
+		out[found++] = q;
+		p = q + 1;
+	}
+	return found;
+}
+
+int newlines4_memchr(const unsigned char *p, const unsigned char *e, const unsigned char **out)
+{
+	int found = 0;
+	while (p < e && found < 4) {
+		const unsigned char *q = (const unsigned char *)memchr(p, '\n', (size_t)(e - p));
+		if (!q) break;
+		out[found++] = q;
+		p = q + 1;
+	}
+	return found;
+}
+
+typedef int (*Newlines4)(const unsigned char *, const unsigned char *, const unsigned char **);
+Newlines4 pick_newlines4()
+{
+	const char *force = getenv("NTSM_SCAN_ISA");           // "memchr" | "avx2" | "avx512": tests walk all three
+	const bool a2 = __builtin_cpu_supports("avx2"), a5 = a2 && __builtin_cpu_supports("avx512bw");
+	if (force) {
+		if (!strcmp(force, "memchr")) return newlines4_memchr;
+		if (!strcmp(force, "avx2") && a2) return newlines4_avx2;
+		if (!strcmp(force, "avx512") && a5) return newlines4_avx512;
+	}
+	return a5 ? newlines4_avx512 : a2 ? newlines4_avx2 : newlines4_memchr;
+}
+Newlines4 g_newlines4 = pick_newlines4();
+
+}  // namespace
+
+void fastx_rescan_isa() { g_newlines4 = pick_newlines4(); }
+const char *fastx_scan_isa() { return g_newlines4 == newlines4_avx512 ? "avx512" : g_newlines4 == newlines4_avx2 ? "avx2" : "memchr"; }
+
 bool FastxReader::next_fast(int64_t *len)
 {
 	if (last_ != 0 || err_) return false;                  // only when the next record starts at the next byte
@@ -106,19 +191,27 @@ bool FastxReader::next_fast(int64_t *len)
 		}
 		const unsigned char *p = buf_.data() + beg_, *e = buf_.data() + end_;
 		if (*p != '@') return false;
+		const unsigned char *nl[4];
 		const unsigned char *nl1, *nl2, *nl3, *nl4;
 		bool complete = false;
 		do {
-			if (!(nl1 = (const unsigned char *)memchr(p + 1, '\n', (size_t)(e - p - 1)))) break;
+			// the same walk the four memchr calls did: each newline is looked for from just behind the
+			// previous one (the one skipped byte, nl2[1], is checked to be '+')
+			const int got = g_newlines4(p + 1, e, nl);
+			if (got < 1) break;
+			nl1 = nl[0];
 			const unsigned char *s0 = nl1 + 1;
 			if (s0 >= e) break;
 			if (*s0 == '\n' || *s0 == '>' || *s0 == '+' || *s0 == '@') return false;
-			if (!(nl2 = (const unsigned char *)memchr(s0, '\n', (size_t)(e - s0)))) break;
+			if (got < 2) break;
+			nl2 = nl[1];
 			if (nl2 + 1 >= e) break;
 			if (nl2[1] != '+') return false;                 // multi-line sequence, FASTA, ...
-			if (!(nl3 = (const unsigned char *)memchr(nl2 + 2, '\n', (size_t)(e - nl2 - 2)))) break;
+			if (got < 3) break;
+			nl3 = nl[2];
 			const unsigned char *q0 = nl3 + 1;
-			if (!(nl4 = (const unsigned char *)memchr(q0, '\n', (size_t)(e - q0)))) break;
+			if (got < 4) break;
+			nl4 = nl[3];
 			complete = true;
 			size_t sl = (size_t)(nl2 - s0), ql = (size_t)(nl4 - q0);
 			if (sl > 1 && s0[sl - 1] == '\r') --sl;          // kseq.h:141, applied per appended line
@@ -231,6 +324,16 @@ extern "C" int ntsm_reader_open(ntsm_reader **out, const char *path)
 	}
 	*out = h;
 	return NTSM_OK;
+}
+
+extern "C" const char *ntsm_scan_isa(const char *force)
+{
+	if (force) {
+		if (*force) setenv("NTSM_SCAN_ISA", force, 1);
+		else unsetenv("NTSM_SCAN_ISA");
+		ntsm::fastx_rescan_isa();
+	}
+	return ntsm::fastx_scan_isa();
 }
 
 extern "C" int ntsm_reader_open2(ntsm_reader **out, const char *path, int helpers)

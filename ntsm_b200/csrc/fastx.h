@@ -68,4 +68,7 @@ private:
 	size_t fast_name_len_ = 0;
 };
 
+void fastx_rescan_isa();               // re-read NTSM_SCAN_ISA (tests)
+const char *fastx_scan_isa();          // "avx512" | "avx2" | "memchr": the line scanner of the FASTQ fast path
+
 }  // namespace ntsm

@@ -100,7 +100,18 @@ def test_reader_matches_oracle_reader(L, oracle, name):
         assert _lib_records(L, f) == oracle.read_records(f), f
 
 
-def test_reader_fuzz(L, oracle, tmp_path):
+@pytest.fixture(params=["memchr", "avx2", "avx512"])
+def scan_isa(L, request):
+    """every newline scanner of the reader's FASTQ fast path (fastx.cpp), skipping what the CPU lacks"""
+    got = L.ntsm_scan_isa(request.param.encode()).decode()
+    if got != request.param:
+        L.ntsm_scan_isa(b"")
+        pytest.skip("CPU has no %s" % request.param)
+    yield got
+    L.ntsm_scan_isa(b"")
+
+
+def test_reader_fuzz(L, oracle, tmp_path, scan_isa):
     from test_oracle import _rand_fastx
     rng = random.Random(5)
     wins = ["ACGTTGCATGCATGCAAGCTT", "CCACGTAGCACTGCACCCCCAT"]
@@ -113,7 +124,7 @@ def test_reader_fuzz(L, oracle, tmp_path):
         assert _lib_records(L, str(f)) == oracle.read_records(str(f))
 
 
-def test_reader_fast_path_across_window_refills(L, oracle, tmp_path):
+def test_reader_fast_path_across_window_refills(L, oracle, tmp_path, scan_isa):
     """Several MiB of mostly regular 4-line FASTQ (the zero-copy fast path) with irregular records
     mixed in (CRLF, multi-line, FASTA, short/long quality, '@' quality lines), in plain and gz
     form: records that straddle the 1 MiB window and every hand-over between the fast path and the
