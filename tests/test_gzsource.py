@@ -299,3 +299,48 @@ def test_reference_fixture_bases_through_the_reader(case, helpers):
             tk += run >= 19
     L.ntsm_reader_close(h)
     assert (bases, tk) == (want_bases, want_tk)
+
+
+def test_bgzf_close_while_helpers_are_busy(tmp_path):
+    """-m stops reading in the middle of a file: closing a block-parallel source right after opening it,
+    after one byte, or half way must neither hang nor crash, however often it is done"""
+    rng = random.Random(21)
+    data = fastq(rng, 12000)
+    p = tmp_path / "b.fq.gz"
+    p.write_bytes(bgzf(data))
+    buf = C.create_string_buffer(1 << 16)
+    for i in range(120):
+        h = C.c_void_p()
+        assert L.ntsm_gz_open(C.byref(h), str(p).encode(), 1 + i % 4) == 0
+        want = [0, 1, 70000, len(data) // 2][i % 4]
+        got = 0
+        while got < want:
+            r = L.ntsm_gz_read(h, buf, min(len(buf), want - got))
+            assert r > 0
+            assert buf.raw[:r] == data[got:got + r]
+            got += r
+        L.ntsm_gz_close(h)
+
+
+def test_many_sources_at_once(tmp_path):
+    """one source per parser thread, as ntsm_count_files runs them: eight files of three kinds read
+    concurrently (ctypes releases the GIL), each with helpers, each byte-exact"""
+    import threading
+    rng = random.Random(22)
+    files = []
+    for i in range(8):
+        data = fastq(rng, 4000 + 500 * i)
+        blob = [member(data), bgzf(data), member(data[:len(data) // 3]) + member(data[len(data) // 3:], level=1)][i % 3]
+        p = tmp_path / ("f%d.gz" % i)
+        p.write_bytes(blob)
+        files.append((p, data))
+    out = [None] * len(files)
+
+    def work(j):
+        out[j] = read_all(files[j][0], helpers=2, chunk=50000 + j)
+
+    th = [threading.Thread(target=work, args=(j,)) for j in range(len(files))]
+    for t in th: t.start()
+    for t in th: t.join()
+    for j, (p, data) in enumerate(files):
+        assert out[j][:2] == (data, 0), j
