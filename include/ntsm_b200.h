@@ -222,6 +222,7 @@ int ntsm_gz_open(ntsm_gz **out, const char *path, int helpers);
 int ntsm_gz_read(ntsm_gz *g, void *dst, unsigned n);   /* gzread's contract: short only at the end, 0 = end, -1 = error */
 const char *ntsm_gz_mode(const ntsm_gz *g);
 int ntsm_gz_fell_back(const ntsm_gz *g);
+uint64_t ntsm_gz_parallel_chunks(const ntsm_gz *g);   /* chunks of single gzip members inflated by helper threads and accepted so far */
 void ntsm_gz_close(ntsm_gz *g);
 uint32_t ntsm_crc32(uint32_t crc, const void *buf, uint64_t len);   /* the CRC-32 of gzip trailers (carry-less multiply when available) */
 int ntsm_reader_open2(ntsm_reader **out, const char *path, int helpers);

@@ -89,6 +89,7 @@ _SIGS = {
     "ntsm_gz_read": (C.c_int, [_P, C.c_void_p, C.c_uint]),
     "ntsm_gz_mode": (C.c_char_p, [_P]),
     "ntsm_gz_fell_back": (C.c_int, [_P]),
+    "ntsm_gz_parallel_chunks": (C.c_uint64, [_P]),
     "ntsm_gz_close": (None, [_P]),
     "ntsm_crc32": (C.c_uint32, [C.c_uint32, C.c_void_p, C.c_uint64]),
     "ntsm_count_files": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_int)]),

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "inflate.h"
+#include "pargz.h"
 
 namespace ntsm {
 
@@ -219,6 +220,11 @@ struct GzSource::Impl {
 	uint8_t *out = nullptr;
 	const uint8_t *hist = nullptr;
 	uint32_t crc = 0, isize = 0;
+	// a large single member is cut between worker threads (pargz.h); what they confirm arrives here in order
+	std::unique_ptr<ParallelInflate> par;
+	int par_workers = 0;
+	size_t par_min = 16u << 20, par_chunk = 2u << 20;
+	uint64_t par_chunks = 0;              // chunks accepted from workers so far (introspection)
 
 	// ---- zlib inflate() over the mapping: takes over at a member the fast modes found irregular --
 	z_stream zs;
@@ -245,6 +251,7 @@ struct GzSource::Impl {
 
 	void shutdown()
 	{
+		par.reset();
 		stop_helpers();
 		if (gz) gzclose(gz);
 		gz = nullptr;
@@ -385,6 +392,40 @@ struct GzSource::Impl {
 				member_produced = 0;
 				member_gstart = produced;
 				in_member = true;
+				if (par_workers > 0 && size - (member_off + hdr) >= par_min)
+					par.reset(new ParallelInflate(map, size, member_off + hdr, par_workers, par_chunk));
+			}
+			if (par) {
+				const uint8_t *pp = nullptr;
+				size_t pn = 0;
+				if (par->next(&pp, &pn)) {
+					crc = crc32_fast(crc, pp, pn);
+					isize += (uint32_t)pn;
+					member_produced += pn;
+					set_segment(pp, pn);
+					risk_base = unit_start(member_gstart, member_produced);
+					return true;
+				}
+				par_chunks += par->chunks_accepted();
+				if (par->end() == ParallelInflate::kStreamEnd) {
+					const uint8_t *t = map + par->end_byte();
+					par.reset();
+					if ((size_t)(map + size - t) < 8 || le32(t) != crc || le32(t + 4) != isize) {
+						fallback(member_off, member_produced);
+						return false;
+					}
+					member_off = (size_t)(t + 8 - map);
+					in_member = false;
+					risk_base = produced;                      // the member is complete and checked
+					continue;
+				}
+				// the workers stopped at a confirmed block boundary: one thread carries on from that bit
+				const std::vector<uint8_t> &w = par->window();
+				if (!w.empty()) memcpy(win.data(), w.data(), w.size());
+				hist = win.data();
+				out = win.data() + w.size();
+				inf->begin_bits(map, par->resume_bit(), map + size);
+				par.reset();
 			}
 			if (out >= limit) {                               // the window is full (and handed over): keep the history, rewind
 				const size_t keep = std::min<size_t>(kHist, (size_t)(out - hist));
@@ -595,6 +636,7 @@ const char *GzSource::mode() const
 
 bool GzSource::fell_back() const { return p_ && p_->fell_back; }
 bool GzSource::bad() const { return p_ && p_->failed; }
+uint64_t GzSource::parallel_chunks() const { return p_ ? p_->par_chunks + (p_->par ? p_->par->chunks_accepted() : 0) : 0; }
 
 bool GzSource::open(const char *path, int helpers)
 {
@@ -641,6 +683,14 @@ bool GzSource::open(const char *path, int helpers)
 			s.held.reserve(4 * Impl::kRefRead);
 			size_t hdr = 0;
 			uint32_t bsize = 0;
+			if (const char *e = getenv("NTSM_PARGZ_MIN")) s.par_min = (size_t)strtoull(e, nullptr, 10);
+			if (const char *e = getenv("NTSM_PARGZ_CHUNK")) s.par_chunk = (size_t)strtoull(e, nullptr, 10);
+			const char *pgz = getenv("NTSM_PARALLEL_GZ");
+			// decoding with markers and resolving them costs ~2.2x the CPU of the plain decoder (measured), so
+			// cutting a member only pays with four workers or more
+			int min_workers = 4;
+			if (const char *e = getenv("NTSM_PARGZ_MIN_WORKERS")) min_workers = atoi(e);
+			if (helpers >= min_workers && helpers > 0 && !(pgz && !strcmp(pgz, "0")) && !(force && !strcmp(force, "serial"))) s.par_workers = helpers;
 			if (force && !strcmp(force, "zinflate")) s.fallback(0, 0);          // tests: zlib's inflate over the mapping from the start
 			else if (helpers > 0 && !(force && !strcmp(force, "serial")) && parse_member_header(s.map, s.size, &hdr, &bsize) == 0 && bsize != 0) {
 				s.mode = Impl::kBgzf;
@@ -741,5 +791,6 @@ extern "C" int ntsm_gz_open(ntsm_gz **out, const char *path, int helpers)
 extern "C" int ntsm_gz_read(ntsm_gz *g, void *dst, unsigned n) { return g ? g->s.read(dst, n) : -1; }
 extern "C" const char *ntsm_gz_mode(const ntsm_gz *g) { return g ? g->s.mode() : ""; }
 extern "C" int ntsm_gz_fell_back(const ntsm_gz *g) { return g && g->s.fell_back() ? 1 : 0; }
+extern "C" uint64_t ntsm_gz_parallel_chunks(const ntsm_gz *g) { return g ? g->s.parallel_chunks() : 0; }
 extern "C" void ntsm_gz_close(ntsm_gz *g) { delete g; }
 extern "C" uint32_t ntsm_crc32(uint32_t crc, const void *buf, uint64_t len) { return ntsm::crc32_fast(crc, (const uint8_t *)buf, (size_t)len); }

@@ -9,6 +9,9 @@
 //             file the other two modes gave up on;
 //   fast      the file memory-mapped and decoded by ntsm::Inflater (inflate.h), CRC-32 and ISIZE
 //             of every member checked before its last bytes are handed out;
+//             With helper threads, a large single member is cut into chunks that workers inflate
+//             speculatively from block starts they find themselves and that are accepted only if
+//             each starts at the bit where the one before it stopped (pargz.h);
 //   bgzf      a BGZF file (gzip members that carry their own size in a 'BC' extra field, as
 //             bgzip / htslib and the Illumina converters write) inflated block-parallel by helper
 //             threads -- the threads `-t` leaves idle when there are fewer files than threads,
@@ -46,6 +49,7 @@ public:
 	const char *mode() const;          // "zlib" | "fast" | "bgzf" -- what is producing bytes right now
 	bool fell_back() const;            // a fast mode handed the file over to zlib
 	bool bad() const;                  // a data error was met (read() returns -1 once the bytes before it are out)
+	uint64_t parallel_chunks() const;  // chunks of single members that worker threads inflated and the stitcher accepted
 
 private:
 	struct Impl;

@@ -131,6 +131,64 @@ void Inflater::begin(const uint8_t *in, const uint8_t *in_end)
 	final_ = false;
 	stored_left_ = 0;
 	err_ = "";
+	stop_base_ = nullptr;
+	stop_bit_ = ~0ull;
+}
+
+void Inflater::begin_bits(const uint8_t *base, uint64_t bitpos, const uint8_t *in_end)
+{
+	begin(base + bitpos / 8, in_end);
+	const unsigned skip = (unsigned)(bitpos & 7);
+	if (skip && in_ < in_end_) {                            // the rest of the byte the stream continues in
+		bitbuf_ = (uint64_t)*in_++ >> skip;
+		bitsleft_ = 8 - (int)skip;
+	}
+}
+
+// BTYPE = 2, HLIT <= 29, HDIST <= 29, and the code-length code complete (Kraft sum exactly 1): a few
+// shifts and four table lookups per bit position, passed by roughly one random position in a thousand.
+namespace {
+struct KraftLut {
+	uint16_t sum[1 << 15];                                  // five 3-bit code lengths -> their Kraft sum in 1/128ths
+	KraftLut()
+	{
+		for (uint32_t v = 0; v < (1u << 15); ++v) {
+			unsigned k = 0;
+			for (int i = 0; i < 5; ++i) {
+				const unsigned l = (v >> (3 * i)) & 7;
+				if (l) k += 128u >> l;
+			}
+			sum[v] = (uint16_t)k;
+		}
+	}
+};
+}  // namespace
+
+uint64_t Inflater::find_plausible_dynamic_header(const uint8_t *base, uint64_t from_bit, uint64_t to_bit, const uint8_t *end)
+{
+	static const KraftLut lut;
+	for (uint64_t bit = from_bit; bit < to_bit; ++bit) {
+		const uint8_t *p = base + bit / 8;
+		if (end - p < 24) return ~0ull;
+		const unsigned sh = (unsigned)(bit & 7);
+		const uint64_t lo = load64(p) >> sh;                // >= 56 bits
+		if (((lo >> 1) & 3) != 2) continue;
+		if (((lo >> 3) & 31) > 29 || ((lo >> 8) & 31) > 29) continue;
+		const unsigned hclen = (unsigned)((lo >> 13) & 15) + 4;
+		// the code-length code's lengths follow at bit 17: up to 57 bits
+		uint64_t v = (load64(p + 2) >> (sh + 1));           // bits from 17 on: >= 55 of them
+		v |= (uint64_t)p[10] << (63 - sh);                  // top them up to 64 - ... >= 63 bits
+		if (hclen < 19) v &= (1ull << (3 * hclen)) - 1;
+		else v &= (1ull << 57) - 1;
+		const unsigned kraft = lut.sum[v & 0x7FFF] + lut.sum[(v >> 15) & 0x7FFF] + lut.sum[(v >> 30) & 0x7FFF] + lut.sum[(v >> 45) & 0x7FFF];
+		if (kraft == 128) return bit;
+	}
+	return ~0ull;
+}
+
+bool Inflater::plausible_dynamic_header(const uint8_t *base, uint64_t bitpos, const uint8_t *end)
+{
+	return find_plausible_dynamic_header(base, bitpos, bitpos + 1, end) == bitpos;
 }
 
 // Invariant of the bit buffer: bits [0, bitsleft_) of bitbuf_ are the next unread bits of the stream
@@ -260,9 +318,9 @@ bool Inflater::read_block_header()
 // The symbol loop.  SAFE = false: at least 16 input bytes remain at every refill, so the buffer never
 // runs dry and no per-symbol check is needed; SAFE = true: the last bytes of the input, same code plus
 // the check that no more bits were consumed than the input had.
-template <bool SAFE> Inflater::Status Inflater::huffman_loop(const uint8_t *hist, uint8_t **outp, uint8_t *out_limit)
+template <bool SAFE, typename OutT> Inflater::Status Inflater::huffman_loop(const OutT *hist, OutT **outp, OutT *out_limit)
 {
-	uint8_t *out = *outp;
+	OutT *out = *outp;
 	const uint8_t *in = in_;
 	uint64_t bb = bitbuf_;
 	int bl = bitsleft_;
@@ -305,7 +363,7 @@ template <bool SAFE> Inflater::Status Inflater::huffman_loop(const uint8_t *hist
 			do {
 				bb >>= e & 0xFF;
 				bl -= (int)(e & 0xFF);
-				*out++ = (uint8_t)(e >> 12);
+				*out++ = (OutT)((e >> 12) & 0xFF);
 				if (bl < 15) break;
 				NTSM_LOOKUP(e, lit, kLitBits);
 			} while (e & kLit);
@@ -334,18 +392,30 @@ template <bool SAFE> Inflater::Status Inflater::huffman_loop(const uint8_t *hist
 		if (SAFE && bl < 0) { why = "truncated stream"; st = kError; break; }
 		const uint32_t off = ((d >> 12) & 0xFFFF) + (uint32_t)((saved >> ((d >> 8) & 15)) & ((1u << ((d & 0xFF) - ((d >> 8) & 15))) - 1));
 		if (off > (size_t)(out - hist)) { why = "invalid distance too far back"; st = kError; break; }
-		const uint8_t *src = out - off;
-		uint8_t *const end = out + len;
-		if (off >= 8) {
-			do {
-				memcpy(out, src, 8);
-				out += 8;
-				src += 8;
-			} while (out < end);
-		} else if (off == 1) {
-			memset(out, *src, len);
+		const OutT *src = out - off;
+		OutT *const end = out + len;
+		if (sizeof(OutT) == 1) {
+			if (off >= 8) {
+				do {
+					memcpy(out, src, 8);
+					out += 8;
+					src += 8;
+				} while (out < end);
+			} else if (off == 1) {
+				memset(out, (int)*src, len);
+			} else {
+				do { *out++ = *src++; } while (out < end);
+			}
 		} else {
-			do { *out++ = *src++; } while (out < end);
+			if (off >= 4) {                                    // four 16-bit symbols per move
+				do {
+					memcpy(out, src, 8);
+					out += 4;
+					src += 4;
+				} while (out < end);
+			} else {
+				do { *out++ = *src++; } while (out < end);
+			}
 		}
 		out = end;
 	}
@@ -359,12 +429,16 @@ template <bool SAFE> Inflater::Status Inflater::huffman_loop(const uint8_t *hist
 	return st;
 }
 
-Inflater::Status Inflater::run(const uint8_t *hist, uint8_t **out, uint8_t *out_limit)
+Inflater::Status Inflater::run(const uint8_t *hist, uint8_t **out, uint8_t *out_limit) { return run_t<uint8_t>(hist, out, out_limit); }
+Inflater::Status Inflater::run16(const uint16_t *hist, uint16_t **out, uint16_t *out_limit) { return run_t<uint16_t>(hist, out, out_limit); }
+
+template <typename OutT> Inflater::Status Inflater::run_t(const OutT *hist, OutT **out, OutT *out_limit)
 {
 	for (;;) {
 		if (state_ == kDone) return kStreamEnd;
 		if (*out >= out_limit) return kNeedOutput;
 		if (state_ == kBlockHeader) {
+			if (stop_bit_ != ~0ull && bit_position(stop_base_) >= stop_bit_) return kBlockBoundary;
 			if (!read_block_header()) return kError;
 			continue;
 		}
@@ -372,7 +446,9 @@ Inflater::Status Inflater::run(const uint8_t *hist, uint8_t **out, uint8_t *out_
 			size_t n = stored_left_;
 			if (n > (size_t)(out_limit - *out)) n = (size_t)(out_limit - *out);
 			if (n > (size_t)(in_end_ - in_)) return fail("truncated stored block");
-			memcpy(*out, in_, n);
+			if (sizeof(OutT) == 1) memcpy(*out, in_, n);
+			else
+				for (size_t i = 0; i < n; ++i) (*out)[i] = (OutT)in_[i];
 			*out += n;
 			in_ += n;
 			stored_left_ -= (uint32_t)n;
@@ -381,7 +457,7 @@ Inflater::Status Inflater::run(const uint8_t *hist, uint8_t **out, uint8_t *out_
 			continue;
 		}
 		// Huffman block: the fast loop while plenty of input remains, the careful one for the tail
-		Status st = in_end_ - in_ >= 16 ? huffman_loop<false>(hist, out, out_limit) : huffman_loop<true>(hist, out, out_limit);
+		Status st = in_end_ - in_ >= 16 ? huffman_loop<false, OutT>(hist, out, out_limit) : huffman_loop<true, OutT>(hist, out, out_limit);
 		if (st == kError) return kError;
 		if (st == kStreamEnd) {                                 // end-of-block symbol
 			state_ = final_ ? kDone : kBlockHeader;

@@ -25,7 +25,7 @@ namespace ntsm {
 
 class Inflater {
 public:
-	enum Status { kNeedOutput, kStreamEnd, kError };
+	enum Status { kNeedOutput, kStreamEnd, kError, kBlockBoundary };
 
 	// start a new raw DEFLATE stream whose first byte is at `in`
 	void begin(const uint8_t *in, const uint8_t *in_end);
@@ -35,6 +35,25 @@ public:
 	//   out:       in/out, next byte to write
 	//   out_limit: stop once *out >= out_limit; the buffer must extend kSlack bytes past out_limit
 	Status run(const uint8_t *hist, uint8_t **out, uint8_t *out_limit);
+
+	// ---- for decoding one stream on several threads (pargz.h) ----
+	// start in the middle of a byte: the stream continues at bit `bitpos` counted from `base`
+	void begin_bits(const uint8_t *base, uint64_t bitpos, const uint8_t *in_end);
+	// make run()/run16() return kBlockBoundary in front of the first block header at or after `bitpos`
+	void stop_at_block_boundary(const uint8_t *base, uint64_t bitpos)
+	{
+		stop_base_ = base;
+		stop_bit_ = bitpos;
+	}
+	// next unread bit, counted from `base`
+	uint64_t bit_position(const uint8_t *base) const { return (uint64_t)(in_ - base) * 8 - (uint64_t)bitsleft_; }
+	// the same decoder writing 16-bit symbols: bytes as 0-255; a caller that does not know the 32 KiB
+	// before its starting point pre-fills them with markers 256 + i and resolves what got copied later
+	Status run16(const uint16_t *hist, uint16_t **out, uint16_t *out_limit);
+	// cheap test whether a dynamic-Huffman block header can start at this bit (used to look for block starts)
+	static bool plausible_dynamic_header(const uint8_t *base, uint64_t bitpos, const uint8_t *end);
+	// first such bit in [from_bit, to_bit), or ~0 if there is none
+	static uint64_t find_plausible_dynamic_header(const uint8_t *base, uint64_t from_bit, uint64_t to_bit, const uint8_t *end);
 
 	// first input byte not consumed (valid after kStreamEnd: the stream is byte-aligned there)
 	const uint8_t *in_pos() const { return in_; }
@@ -46,7 +65,8 @@ private:
 	static constexpr int kLitBits = 11, kDistBits = 9, kPreBits = 7;
 	static constexpr int kLitSize = (1 << kLitBits) + 288 * 16, kDistSize = (1 << kDistBits) + 32 * 64;
 
-	template <bool SAFE> Status huffman_loop(const uint8_t *hist, uint8_t **out, uint8_t *out_limit);
+	template <bool SAFE, typename OutT> Status huffman_loop(const OutT *hist, OutT **out, OutT *out_limit);
+	template <typename OutT> Status run_t(const OutT *hist, OutT **out, OutT *out_limit);
 	bool read_block_header();
 	bool read_dynamic_tables();
 	void refill();
@@ -62,6 +82,8 @@ private:
 	uint32_t stored_left_ = 0;
 	const uint32_t *lit_ = nullptr, *dist_ = nullptr;   // tables of the current block
 	const char *err_ = "";
+	const uint8_t *stop_base_ = nullptr;
+	uint64_t stop_bit_ = ~0ull;
 	uint32_t lit_dyn_[kLitSize], dist_dyn_[kDistSize];
 };
 

@@ -344,3 +344,88 @@ def test_many_sources_at_once(tmp_path):
     for t in th: t.join()
     for j, (p, data) in enumerate(files):
         assert out[j][:2] == (data, 0), j
+
+
+# ---------------------------------------------------------------- one member on several threads (pargz)
+@pytest.fixture
+def small_parallel_chunks(monkeypatch):
+    """make the parallel single-member decoder kick in for test-sized files: 64 KiB chunks (zlib's blocks
+    of this kind of data are 30-60 KB compressed, and a worker searches three chunks for a start), no minimum"""
+    monkeypatch.setenv("NTSM_PARGZ_MIN", "0")
+    monkeypatch.setenv("NTSM_PARGZ_MIN_WORKERS", "1")
+    monkeypatch.setenv("NTSM_PARGZ_CHUNK", "65536")
+
+
+def _read_counting_chunks(path, helpers, rng=None):
+    h = C.c_void_p()
+    assert L.ntsm_gz_open(C.byref(h), str(path).encode(), helpers) == 0
+    out = bytearray()
+    buf = C.create_string_buffer(1 << 20)
+    while True:
+        n = rng.choice([1, 100, 4096, 65536, 1 << 20]) if rng else 1 << 20
+        r = L.ntsm_gz_read(h, buf, n)
+        if r <= 0:
+            rc = r
+            break
+        out += buf.raw[:r]
+    res = bytes(out), rc, L.ntsm_gz_parallel_chunks(h), L.ntsm_gz_fell_back(h)
+    L.ntsm_gz_close(h)
+    return res
+
+
+@pytest.mark.parametrize("level", [1, 6, 9])
+@pytest.mark.parametrize("helpers", [1, 2, 5])
+def test_single_member_on_several_threads(tmp_path, small_parallel_chunks, level, helpers):
+    """a FASTQ-like member cut into chunks: workers find block starts on their own, decode with markers
+    for the window they cannot know, and the stitcher accepts a chunk only where the previous one
+    stopped; the bytes are the original's and most chunks really came from workers"""
+    rng = random.Random(40 + level)
+    data = fastq(rng, 9000) + b">tail\n" + b"ACGTTGCA" * 3000 + b"\n"
+    p = tmp_path / "one.gz"
+    p.write_bytes(member(data, level=level, name=b"reads.fq"))
+    got, rc, chunks, fb = _read_counting_chunks(p, helpers, rng)
+    assert (got, rc, fb) == (data, 0, 0)
+    assert chunks >= 0.7 * (p.stat().st_size / 65536) and chunks >= 5
+
+
+def test_parallel_decoder_hands_back_to_one_thread_where_it_must(tmp_path, small_parallel_chunks):
+    """what the workers cannot line up -- stored blocks (incompressible data), fixed-Huffman blocks, one
+    block longer than the search range, several members in a row -- is decoded by the ordinary
+    decoder from the last confirmed block boundary (a bit offset, with the 32 KiB before it)"""
+    rng = random.Random(50)
+    fq = fastq(rng, 4000)
+    cases = {
+        "stored_in_the_middle": fq + rng.randbytes(200000) + fq,                       # deflate stores the random part
+        "fixed_blocks": fq,                                                              # Z_FIXED: no dynamic header anywhere
+        "zeros_one_long_block": fq[:50000] + bytes(3_000_000) + fq[:50000],
+        "tiny": b"@r\nACGT\n+\nFFFF\n",
+    }
+    for name, data in cases.items():
+        p = tmp_path / (name + ".gz")
+        strat = zlib.Z_FIXED if name == "fixed_blocks" else zlib.Z_DEFAULT_STRATEGY
+        p.write_bytes(member(data, strategy=strat) + member(fq[:30000], level=1) + member(b""))
+        got, rc, chunks, fb = _read_counting_chunks(p, 3, rng)
+        assert (got, rc, fb) == (data + fq[:30000], 0, 0), name
+
+
+def test_parallel_decoder_on_damaged_members_behaves_like_zlib(tmp_path, small_parallel_chunks, monkeypatch):
+    rng = random.Random(51)
+    base = [member(fastq(rng, 1500), level=lv) for lv in (1, 6)]
+    for trial in range(120):
+        blob = bytearray(b"".join(rng.sample(base, rng.randrange(1, 3))))
+        kind, pos = trial % 4, rng.randrange(len(blob))
+        if kind == 0:
+            blob = blob[:pos]
+        elif kind == 1:
+            blob[pos] ^= 1 << rng.randrange(8)
+        elif kind == 2:
+            blob[pos:pos + 20] = rng.randbytes(20)
+        else:
+            del blob[pos:pos + rng.randrange(1, 5)]
+        if len(blob) < 18:
+            continue
+        p = tmp_path / "d.gz"
+        p.write_bytes(bytes(blob))
+        want = zlib_mode(p, monkeypatch, chunk=50000)
+        got = read_all(p, helpers=3, chunk=50000)
+        assert got[:2] == want[:2], (trial, kind, pos)
