@@ -223,7 +223,7 @@ struct GzSource::Impl {
 	// a large single member is cut between worker threads (pargz.h); what they confirm arrives here in order
 	std::unique_ptr<ParallelInflate> par;
 	int par_workers = 0;
-	size_t par_min = 16u << 20, par_chunk = 2u << 20;
+	size_t par_min = 16u << 20, par_chunk = 1u << 20;
 	uint64_t par_chunks = 0;              // chunks accepted from workers so far (introspection)
 
 	// ---- zlib inflate() over the mapping: takes over at a member the fast modes found irregular --

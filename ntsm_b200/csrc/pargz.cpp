@@ -291,8 +291,8 @@ ParallelInflate::ParallelInflate(const uint8_t *base, size_t size, size_t deflat
 	s.n_chunks = (size - deflate_start + s.chunk - 1) / s.chunk;
 	s.expect_bit = (uint64_t)deflate_start * 8;
 	workers = std::max(1, workers);
-	s.max_resolving = (size_t)workers + 1;
-	const int n_tasks = 3 * workers + 2;
+	s.max_resolving = (size_t)workers / 2 + 1;
+	const int n_tasks = 2 * workers + 2;                       // each holds one chunk's symbols: ~10 MB at 1 MiB chunks of FASTQ
 	for (int i = 0; i < n_tasks; ++i) {
 		s.pool.emplace_back(new Task());
 		s.free_tasks.push_back(s.pool.back().get());
