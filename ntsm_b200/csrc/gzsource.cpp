@@ -398,8 +398,9 @@ struct GzSource::Impl {
 			if (par) {
 				const uint8_t *pp = nullptr;
 				size_t pn = 0;
-				if (par->next(&pp, &pn)) {
-					crc = crc32_fast(crc, pp, pn);
+				uint32_t pcrc = 0;
+				if (par->next(&pp, &pn, &pcrc)) {
+					crc = (uint32_t)crc32_combine(crc, pcrc, (z_off_t)pn);   // the workers hashed their chunks
 					isize += (uint32_t)pn;
 					member_produced += pn;
 					set_segment(pp, pn);

@@ -12,6 +12,7 @@
 #include <mutex>
 #include <thread>
 
+#include "gzsource.h"
 #include "inflate.h"
 
 namespace ntsm {
@@ -37,6 +38,7 @@ struct Task {
 	uint8_t window[kWin];
 	size_t window_have = 0;                    // valid bytes at the END of window[] (< kWin only near the stream's start)
 	bool resolved = false;
+	uint32_t crc = 0;                          // CRC-32 of the chunk's bytes, computed by the worker that resolved it
 	int job = 0;                               // what a worker is asked to do with it: 0 decode, 1 resolve
 };
 
@@ -110,6 +112,7 @@ struct ParallelInflate::Impl {
 		const uint16_t *sy = t.sym.get();
 		uint8_t *by = reinterpret_cast<uint8_t *>(t.sym.get());
 		for (size_t i = 0; i < t.n_sym; ++i) by[i] = lut[sy[i]];
+		t.crc = crc32_fast(0, by, t.n_sym);                        // the consumer only has to combine these
 	}
 
 	static void append(Task &t, const uint16_t *sy, size_t n)
@@ -310,7 +313,7 @@ uint64_t ParallelInflate::resume_bit() const { return p_->expect_bit; }
 const std::vector<uint8_t> &ParallelInflate::window() const { return p_->win_out; }
 uint64_t ParallelInflate::chunks_accepted() const { return p_->accepted; }
 
-bool ParallelInflate::next(const uint8_t **p, size_t *n)
+bool ParallelInflate::next(const uint8_t **p, size_t *n, uint32_t *crc)
 {
 	Impl &s = *p_;
 	std::unique_lock<std::mutex> g(s.mu);
@@ -337,6 +340,7 @@ bool ParallelInflate::next(const uint8_t **p, size_t *n)
 			s.lent = t;
 			*p = reinterpret_cast<const uint8_t *>(t->sym.get());
 			*n = t->n_sym;
+			if (crc) *crc = t->crc;
 			return true;
 		}
 		if (s.no_more_accepts || s.order.empty()) {

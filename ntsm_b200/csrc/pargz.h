@@ -37,8 +37,9 @@ public:
 	ParallelInflate(const ParallelInflate &) = delete;
 	ParallelInflate &operator=(const ParallelInflate &) = delete;
 
-	// The next run of decoded bytes, valid until the following call.  false = no more from here: see end().
-	bool next(const uint8_t **p, size_t *n);
+	// The next run of decoded bytes, valid until the following call, and (if asked) their own CRC-32,
+	// already computed by a worker.  false = no more from here: see end().
+	bool next(const uint8_t **p, size_t *n, uint32_t *crc = nullptr);
 	End end() const;
 	// kStreamEnd: first byte after the DEFLATE stream (the gzip trailer).
 	size_t end_byte() const;
