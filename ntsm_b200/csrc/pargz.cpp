@@ -20,7 +20,6 @@ namespace ntsm {
 namespace {
 
 constexpr size_t kWin = 32768;
-constexpr size_t kStep = 1u << 18;             // symbols decoded between two copies out of the sliding window
 constexpr uint64_t kSearchChunks = 3;          // look for a block start over at most this many chunks
 
 struct Task {
@@ -31,8 +30,8 @@ struct Task {
 	bool ok = false, stream_end = false;
 	uint64_t start_bit = 0, end_bit = 0;
 	size_t end_byte = 0;
-	std::unique_ptr<uint16_t[]> sym;           // decoded symbols: 0-255 bytes, 256 + w = byte w of the unknown 32 KiB before the chunk
-	size_t sym_cap = 0, n_sym = 0;
+	std::unique_ptr<uint16_t[]> sym;           // [n_prefix markers] + decoded symbols: 0-255 bytes, 256 + w = byte w of the unknown 32 KiB before the chunk
+	size_t sym_cap = 0, n_prefix = 0, n_sym = 0;
 	bool decoded = false;
 	// resolve: symbols -> bytes, in place at the front of `sym`, through the window that the stitcher supplies
 	uint8_t window[kWin];
@@ -82,7 +81,6 @@ struct ParallelInflate::Impl {
 	void worker_main()
 	{
 		std::unique_ptr<Inflater> inf(new Inflater());
-		std::unique_ptr<uint16_t[]> wbuf(new uint16_t[kWin + kStep + Inflater::kSlack]);
 		for (;;) {
 			Task *t;
 			{
@@ -92,7 +90,7 @@ struct ParallelInflate::Impl {
 				t = todo.front();
 				todo.pop_front();
 			}
-			if (t->job == 0) decode(*inf, *t, wbuf.get());
+			if (t->job == 0) decode(*inf, *t);
 			else resolve(*t);
 			{
 				std::lock_guard<std::mutex> g(mu);
@@ -109,51 +107,39 @@ struct ParallelInflate::Impl {
 		uint8_t lut[256 + kWin];
 		for (int i = 0; i < 256; ++i) lut[i] = (uint8_t)i;
 		memcpy(lut + 256, t.window, kWin);
-		const uint16_t *sy = t.sym.get();
-		uint8_t *by = reinterpret_cast<uint8_t *>(t.sym.get());
+		const uint16_t *sy = t.sym.get() + t.n_prefix;
+		uint8_t *by = reinterpret_cast<uint8_t *>(t.sym.get() + t.n_prefix);
 		for (size_t i = 0; i < t.n_sym; ++i) by[i] = lut[sy[i]];
 		t.crc = crc32_fast(0, by, t.n_sym);                        // the consumer only has to combine these
 	}
 
-	static void append(Task &t, const uint16_t *sy, size_t n)
-	{
-		if (t.sym_cap < t.n_sym + n + 64) {
-			const size_t cap = std::max(t.sym_cap * 2, t.n_sym + n + 64);
-			std::unique_ptr<uint16_t[]> bigger(new uint16_t[cap]);
-			if (t.n_sym) memcpy(bigger.get(), t.sym.get(), t.n_sym * sizeof(uint16_t));
-			t.sym.swap(bigger);
-			t.sym_cap = cap;
-		}
-		memcpy(t.sym.get() + t.n_sym, sy, n * sizeof(uint16_t));
-		t.n_sym += n;
-	}
-
-	// One attempt from `bit`; false = this was not a block start (or the data is bad).  The symbols go
-	// through a small sliding window that stays in cache (decoding straight into a chunk-sized buffer
-	// costs twice the time in page faults and misses) and are copied out as they come.
-	bool attempt(Inflater &inf, Task &t, uint64_t bit, uint16_t *wbuf)
+	// One attempt from `bit`; false = this was not a block start (or the data is bad).  Decodes straight
+	// into the task's own symbol buffer, which is kept from chunk to chunk: a fresh buffer of this size
+	// costs more in page faults than the decoding itself, a warm one is the fastest place to decode to.
+	bool attempt(Inflater &inf, Task &t, uint64_t bit)
 	{
 		const uint8_t *end = base + size;
-		const size_t have = t.exact_start ? 0 : kWin;              // symbols in front of `out` a match may reach
-		for (size_t i = 0; i < have; ++i) wbuf[i] = (uint16_t)(256 + i);
-		if (t.sym_cap < chunk * 5) {
-			t.sym_cap = chunk * 5;
-			t.sym.reset(new uint16_t[t.sym_cap]);                  // uninitialised on purpose
+		t.n_prefix = t.exact_start ? 0 : kWin;                     // symbols in front of the output a match may reach
+		const size_t want = t.n_prefix + chunk * 5 + Inflater::kSlack;
+		if (t.sym_cap < want) {
+			t.sym.reset(new uint16_t[want]);                       // uninitialised on purpose
+			t.sym_cap = want;
 		}
-		t.n_sym = 0;
-		uint16_t *out = wbuf + have;
+		for (size_t i = 0; i < t.n_prefix; ++i) t.sym[i] = (uint16_t)(256 + i);
+		size_t pos = t.n_prefix;
 		inf.begin_bits(base, bit, end);
 		inf.stop_at_block_boundary(base, t.stop_bit);
 		for (;;) {
-			uint16_t *o = out;
-			const Inflater::Status st = inf.run16(wbuf, &o, wbuf + kWin + kStep);
+			uint16_t *o = t.sym.get() + pos;
+			const Inflater::Status st = inf.run16(t.sym.get(), &o, t.sym.get() + t.sym_cap - Inflater::kSlack);
+			pos = (size_t)(o - t.sym.get());
 			if (st == Inflater::kError) return false;
-			append(t, out, (size_t)(o - out));
-			if (t.n_sym >= 0x7FFFFFF0ull) return false;
-			if (st == Inflater::kNeedOutput) {                     // slide: keep the last 32 K symbols as history
-				const size_t keep = std::min<size_t>(kWin, (size_t)(o - wbuf));
-				memmove(wbuf, o - keep, keep * sizeof(uint16_t));
-				out = wbuf + keep;
+			if (pos >= 0x7FFFFFF0ull) return false;
+			if (st == Inflater::kNeedOutput) {                     // the data expands more than 5x: a bigger buffer
+				std::unique_ptr<uint16_t[]> bigger(new uint16_t[t.sym_cap * 2]);
+				memcpy(bigger.get(), t.sym.get(), pos * sizeof(uint16_t));
+				t.sym.swap(bigger);
+				t.sym_cap *= 2;
 				continue;
 			}
 			t.stream_end = st == Inflater::kStreamEnd;
@@ -161,15 +147,16 @@ struct ParallelInflate::Impl {
 			t.end_byte = (size_t)(inf.in_pos() - base);
 			break;
 		}
+		t.n_sym = pos - t.n_prefix;
 		t.start_bit = bit;
 		return true;
 	}
 
-	void decode(Inflater &inf, Task &t, uint16_t *wbuf)
+	void decode(Inflater &inf, Task &t)
 	{
 		t.ok = false;
 		if (t.exact_start) {
-			t.ok = attempt(inf, t, t.from_bit, wbuf);
+			t.ok = attempt(inf, t, t.from_bit);
 			return;
 		}
 		const uint8_t *end = base + size;
@@ -178,7 +165,7 @@ struct ParallelInflate::Impl {
 		for (uint64_t bit = t.from_bit; bit < limit; ++bit) {
 			bit = Inflater::find_plausible_dynamic_header(base, bit, limit, end);
 			if (bit == ~0ull) return;
-			if (attempt(inf, t, bit, wbuf)) {
+			if (attempt(inf, t, bit)) {
 				t.ok = true;
 				return;
 			}
@@ -233,7 +220,7 @@ struct ParallelInflate::Impl {
 			size_t n_tail = 0;
 			if (good) {
 				n_tail = std::min<size_t>(kWin, t->n_sym);
-				const uint16_t *sy = t->sym.get() + (t->n_sym - n_tail);
+				const uint16_t *sy = t->sym.get() + t->n_prefix + (t->n_sym - n_tail);
 				for (size_t i = 0; i < n_tail; ++i) {
 					const int b = resolve_one(sy[i], win, win_have);
 					if (b < 0) {
@@ -245,8 +232,9 @@ struct ParallelInflate::Impl {
 				// the body may also hold such references: they all point into the window's missing front
 				if (good && win_have < kWin) {
 					const uint16_t lim = (uint16_t)(256 + (kWin - win_have));
+					const uint16_t *body = t->sym.get() + t->n_prefix;
 					for (size_t i = 0; i + n_tail < t->n_sym; ++i)
-						if (t->sym[i] >= 256 && t->sym[i] < lim) {
+						if (body[i] >= 256 && body[i] < lim) {
 							good = false;
 							break;
 						}
@@ -338,7 +326,7 @@ bool ParallelInflate::next(const uint8_t **p, size_t *n, uint32_t *crc)
 				continue;
 			}
 			s.lent = t;
-			*p = reinterpret_cast<const uint8_t *>(t->sym.get());
+			*p = reinterpret_cast<const uint8_t *>(t->sym.get() + t->n_prefix);
 			*n = t->n_sym;
 			if (crc) *crc = t->crc;
 			return true;
