@@ -105,6 +105,15 @@ void ntsm_ctx_destroy(ntsm_ctx *ctx);
 int ntsm_load_sites(ntsm_ctx *ctx, const uint64_t *kmer_hash, const uint8_t *erased, uint32_t n_kmers,
                     const uint32_t *allele_off, uint32_t n_sites);  /* initCountsHash :490-564 */
 int ntsm_load_siteset(ntsm_ctx *ctx, const ntsm_sites *s);
+/* Measurement / test knobs, to be set before ntsm_load_sites; every setting gives the same counts (the
+ * pre-filters in front of the exact table only ever let too many windows through).  Names:
+ *   "kernel"       0 = generic kernel (one k-mer-bitmap probe per position), 1 = paired seeds (k >= 17), -1 = automatic
+ *   "pair_fold"    paired-seed table folded 2^n : 1 (0..4), -1 = automatic (1; 0 above 5 M site k-mers)
+ *   "filter_bits"  log2 of the k-mer bitmap's bits (10..32), 0 = automatic (~80 bits per site k-mer)
+ *   "launch_shape" pair kernel CTA shape: 0 = 1024x1, 1 = 1024x2 (default), 2 = 512x4, 3 = 256x8 per SM
+ *   "l2_persist"   1 (default) = launch with an L2 access-policy window that keeps the probe tables resident
+ *   "device_pack"  1 (default) = ntsm_insert_reads* from page-locked memory also feed ASCII to the GPU packer (may be set any time) */
+int ntsm_ctx_set_option(ntsm_ctx *ctx, const char *name, int value);
 
 /* ---------------- packed batches: the ProdCon bulk buffers (vendor/ProdConKseqRunner.hpp:34-46) */
 uint64_t ntsm_padded_positions(uint64_t n_pos); /* allocation/padding contract of a packed stream */
@@ -158,6 +167,15 @@ int ntsm_insert_reads(ntsm_ctx *const *ctxs, uint32_t n_ctx, const char *buf, co
 /* same for a dense matrix: read r = buf[r*stride .. r*stride + read_len) */
 int ntsm_insert_reads_fixed(ntsm_ctx *const *ctxs, uint32_t n_ctx, const char *buf, uint64_t read_len, uint64_t stride,
                             uint64_t n_reads, uint32_t threads);
+/* When `buf` of the two calls above lies in page-locked host memory (cudaMallocHost / cudaHostAlloc, or
+ * registered with ntsm_host_register), one extra feeder thread per ctx takes blocks of reads from the
+ * same queue as the `threads` host packers, DMAs their ASCII bytes to the GPU as they are and has the
+ * GPU decode + pack them (pack_ascii_kernel): no host core touches those bases.  `threads` == 0 then
+ * means "device packing only".  With pageable memory only the host packers run (threads >= 1).
+ * ntsm_host_register pins a caller's buffer (cudaHostRegister, portable); it costs ~0.2 s per GiB, so
+ * it pays for buffers that are filled more than once. */
+int ntsm_host_register(void *buf, uint64_t bytes);
+int ntsm_host_unregister(void *buf);
 
 /* m_totalKmers / m_totalCounts / m_totalBases / m_earlyTerm (:458-463) over COMPLETED batches;
  * non-blocking.  cap_reached = hits > max_counts at a batch boundary. */
@@ -171,6 +189,8 @@ int ntsm_set_stream(ntsm_ctx *ctx, void *cuda_stream);
 
 /* ---------------- multi-GPU: one ctx (process or thread) per GPU ---------------- */
 #define NTSM_NCCL_ID_BYTES 128
+/* Side effect, once per process before the first NCCL call: NCCL_DEBUG=VERSION is raised to WARN and
+ * NCCL_DEBUG_FILE defaults to /dev/stderr, so that NCCL's banner cannot land in a counts file on stdout. */
 int ntsm_nccl_unique_id(void *id_out);                         /* ncclGetUniqueId */
 int ntsm_comm_init(ntsm_ctx *ctx, const void *id, int rank, int n_ranks);
 /* sum counts (u32) and tallies (u64) over all ranks: ONE ncclAllReduce each, before the per-site max */
@@ -179,12 +199,30 @@ int ntsm_allreduce(ntsm_ctx *ctx);
  * then the per-site max/sum kernel.  ntsm_finalize calls it if it has not run yet. */
 int ntsm_reduce_async(ntsm_ctx *ctx);
 
+/* Several ctxs of ONE process (one per GPU, the CLI's --gpus N): drains them all, then ctx 0's GPU sums
+ * every ctx's private counts out of peer memory over NVLink inside the per-site reduce kernel (sums
+ * first, max afterwards) and sums the tallies -- no NCCL communicator.  Outputs as ntsm_finalize; the
+ * ctxs must hold the same site table; afterwards they need ntsm_reset_counts before counting again
+ * and ntsm_get_counts(ctxs[0]) returns the combined k-mer counts.  At most 16 ctxs. */
+int ntsm_group_finalize(ntsm_ctx *const *ctxs, uint32_t n_ctx, uint32_t *max_ref, uint32_t *max_var,
+                        uint32_t *sum_ref, uint32_t *sum_var, uint64_t totals[3]);
+
 /* ---------------- results: printOptionalHeader + printCountsMax (:261-311) ---------------- */
 /* drains, runs the per-site reduce kernel, copies out.  Arrays have n_sites entries;
  * totals = {total_kmers (#@TK), total_hits, total_bases}.  Any pointer may be NULL. */
 int ntsm_finalize(ntsm_ctx *ctx, uint32_t *max_ref, uint32_t *max_var, uint32_t *sum_ref, uint32_t *sum_var,
                   uint64_t totals[3]);
 int ntsm_get_counts(ntsm_ctx *ctx, uint32_t *counts /* [n_kmers] */);
+/* The three tallies {TK, hits, bases} as they stand on this ctx (drains; does not combine anything). */
+int ntsm_get_totals(ntsm_ctx *ctx, uint64_t totals[3]);
+/* Exact shard merge (replaces `ntsmEval --merge`'s sum of per-site maxima, src/CompareCounts.hpp:648-657):
+ * counts[i] += add[i] for every listed k-mer, tallies += totals; the per-site max is taken afterwards by
+ * ntsm_finalize, so merging shards equals counting the concatenated input. */
+int ntsm_add_counts(ntsm_ctx *ctx, const uint32_t *counts /* [n_kmers] */, const uint64_t totals[3]);
+/* k-mer count files ("NTSMKC1": k, n_kmers, digest of the site set, tallies, u32 counts[n_kmers]):
+ * save this ctx's k-mer-level result / add a saved one into this ctx (same site set and k required). */
+int ntsm_counts_save(ntsm_ctx *ctx, const ntsm_sites *s, const char *path);
+int ntsm_counts_load_add(ntsm_ctx *ctx, const ntsm_sites *s, const char *path);
 /* getSitesCoveredInSample (:389-413) from finalize()'s maxima */
 uint32_t ntsm_sites_covered(const uint32_t *max_ref, const uint32_t *max_var, uint32_t n_sites);
 /* writes "#@TK..#@KS..\n#locusID...\n" + rows exactly as the reference does; returns bytes written
@@ -200,6 +238,9 @@ uint64_t ntsm_ctx_launches(const ntsm_ctx *ctx);
 const char *ntsm_ctx_kernel_name(const ntsm_ctx *ctx);   /* the count kernel this ctx launches, as a profiler lists it */
 uint32_t ntsm_ctx_filter_bits(const ntsm_ctx *ctx);
 uint32_t ntsm_ctx_table_capacity(const ntsm_ctx *ctx);
+void ntsm_ctx_pcie_bytes(const ntsm_ctx *ctx, uint64_t *h2d, uint64_t *d2h); /* bytes this ctx's data path has copied host->device / device->host so far */
+int ntsm_ctx_l2_window(const ntsm_ctx *ctx);             /* 0 = no L2 access-policy window, else its hit ratio in percent */
+uint64_t ntsm_ctx_probe_bytes(const ntsm_ctx *ctx);      /* bytes of the probe tables (paired-seed table + k-mer bitmap) */
 
 /* ---------------- record reader: kseq_read (vendor/kseq.h:178-219) ---------------- */
 int ntsm_reader_open(ntsm_reader **out, const char *path);

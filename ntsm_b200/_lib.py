@@ -45,6 +45,13 @@ _SIGS = {
     "ntsm_ctx_destroy": (None, [_P]),
     "ntsm_load_sites": (C.c_int, [_P, _P, _P, C.c_uint32, _P, C.c_uint32]),
     "ntsm_load_siteset": (C.c_int, [_P, _P]),
+    "ntsm_ctx_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
+    "ntsm_host_register": (C.c_int, [_P, C.c_uint64]),
+    "ntsm_host_unregister": (C.c_int, [_P]),
+    "ntsm_group_finalize": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P, _P]),
+    "ntsm_ctx_pcie_bytes": (None, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "ntsm_ctx_l2_window": (C.c_int, [_P]),
+    "ntsm_ctx_probe_bytes": (C.c_uint64, [_P]),
     "ntsm_padded_positions": (C.c_uint64, [C.c_uint64]),
     "ntsm_acquire_batch": (C.c_int, [_P, C.POINTER(_P)]),
     "ntsm_batch_append": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]),
@@ -72,6 +79,10 @@ _SIGS = {
     "ntsm_allreduce": (C.c_int, [_P]),
     "ntsm_finalize": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "ntsm_get_counts": (C.c_int, [_P, _P]),
+    "ntsm_get_totals": (C.c_int, [_P, _P]),
+    "ntsm_add_counts": (C.c_int, [_P, _P, _P]),
+    "ntsm_counts_save": (C.c_int, [_P, _P, C.c_char_p]),
+    "ntsm_counts_load_add": (C.c_int, [_P, _P, C.c_char_p]),
     "ntsm_sites_covered": (C.c_uint32, [_P, _P, C.c_uint32]),
     "ntsm_format_counts": (C.c_int64, [_P, _P, _P, _P, _P, C.c_uint64, _P, C.c_size_t]),
     "ntsm_format_summary": (C.c_int64, [_P, _P, C.c_uint32, _P, C.c_size_t]),

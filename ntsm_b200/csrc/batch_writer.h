@@ -44,12 +44,15 @@ struct BatchWriter {
 	}
 
 	// FingerPrint::insertCount(seq, len) (src/FingerPrint.hpp:89) for this producer.  on_submit is
-	// called after every batch this read caused to be submitted (the -m check hooks in there); if it
-	// returns true the cap was reached by what is already submitted and the rest of this read is
-	// dropped (the reference stops before it, src/FingerPrint.hpp:67).
+	// called after every batch this read caused to be submitted (the -m check hooks in there).  If it
+	// returns true the cap was reached by what is already submitted: a read that has not begun is
+	// dropped (the reference stops before it, src/FingerPrint.hpp:67); a read longer than a batch that
+	// is part-way in is finished first, because the reference counts a whole read before it looks at
+	// the cap (processSingleRead, :473-487).
 	template <class F> bool append(const char *seq, uint64_t len, F &&on_submit)
 	{
 		uint64_t pos = 0;
+		bool finishing = false;
 		for (;;) {
 			if (!b) {
 				bctx = ctxs[next_batch->fetch_add(1) % n_ctx];
@@ -61,7 +64,10 @@ struct BatchWriter {
 			if (r == 1) return true;
 			ntsm_ctx *went = nullptr;
 			if (!submit(&went)) return false;
-			if (on_submit(went)) return true;
+			if (!finishing && on_submit(went)) {
+				if (pos == 0) return true;
+				finishing = true;
+			}
 		}
 	}
 	bool append(const char *seq, uint64_t len)

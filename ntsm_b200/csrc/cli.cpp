@@ -3,6 +3,10 @@
 // Additions (long options only, nothing the reference parses changes meaning):
 //   --gpus N          use N GPUs of this box (default 1; 0 = all)
 //   --batch-bases B   stream positions per pinned batch (default 2^25; 2^22 with -m)
+//   --dump-kmer-counts F    also write every k-mer's counter + the tallies to F (merge.cpp's format)
+//   --merge-kmer-counts     FILES are such dumps of shards of ONE sample: add them per k-mer, then print
+//                           the counts file -- the exact merge `ntsmEval --merge` is not
+//                           (src/CompareCounts.hpp:648-657 sums per-site maxima)
 #include <getopt.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -18,6 +22,7 @@
 #include <vector>
 
 #include "../../include/ntsm_b200.h"
+#include "internal.h"
 
 #define PROGRAM "ntsmCount"
 
@@ -55,7 +60,11 @@ const char kHelp[] =
     "  -v, --verbose          Display verbose output.\n"
     "      --version          Print version information.\n"
     "      --gpus = INT       GPUs of this box to use (0 = all). [1]\n"
-    "      --batch-bases = INT  positions per pinned batch. [2^25]\n";
+    "      --batch-bases = INT  positions per pinned batch. [2^25]\n"
+    "      --dump-kmer-counts = STR  also write k-mer level counts to\n"
+    "                         this file (for --merge-kmer-counts).\n"
+    "      --merge-kmer-counts  FILES are k-mer count dumps of shards\n"
+    "                         of one sample: merge them exactly.\n";
 
 }  // namespace
 
@@ -70,6 +79,8 @@ extern "C" int ntsm_main(int argc, char **argv)
 	int opt_version = 0;
 	int gpus = 1;
 	unsigned long long batch_bases = 0;
+	std::string dump_path;
+	int merge_mode = 0;
 
 	static struct option long_options[] = {
 	    {"threads", required_argument, NULL, 't'}, {"maxCov", required_argument, NULL, 'm'},
@@ -77,7 +88,8 @@ extern "C" int ntsm_main(int argc, char **argv)
 	    {"snp", required_argument, NULL, 's'},     {"kmer", required_argument, NULL, 'k'},
 	    {"help", no_argument, NULL, 'h'},          {"version", no_argument, &opt_version, 1},
 	    {"verbose", no_argument, NULL, 'v'},       {"gpus", required_argument, NULL, 1001},
-	    {"batch-bases", required_argument, NULL, 1002}, {NULL, 0, NULL, 0}};
+	    {"batch-bases", required_argument, NULL, 1002}, {"dump-kmer-counts", required_argument, NULL, 1003},
+	    {"merge-kmer-counts", no_argument, &merge_mode, 1}, {NULL, 0, NULL, 0}};
 	optind = 1;
 	int c, option_index = 0;
 	while ((c = getopt_long(argc, argv, "s:t:vhk:m:do:", long_options, &option_index)) != -1) {
@@ -92,6 +104,7 @@ extern "C" int ntsm_main(int argc, char **argv)
 		case 'v': verbose++; break;
 		case 1001: if (!parse(optarg, gpus)) { std::cerr << "Error - Invalid parameter gpus: " << optarg << std::endl; return 0; } break;
 		case 1002: if (!parse(optarg, batch_bases)) { std::cerr << "Error - Invalid parameter batch-bases: " << optarg << std::endl; return 0; } break;
+		case 1003: if (!parse(optarg, dump_path)) { std::cerr << "Error - Invalid parameter dump-kmer-counts: " << optarg << std::endl; return 0; } break;
 		case '?': die = true; break;
 		}
 	}
@@ -176,54 +189,51 @@ extern "C" int ntsm_main(int argc, char **argv)
 				return 1;
 			}
 	}
-	if (gpus > 1) {   // one NCCL communicator over the GPUs of this process; init must run concurrently
-		// whatever a library prints while the communicator comes up must not reach the counts file:
-		// file descriptor 1 points at stderr until it is done
-		fflush(stdout);
-		const int saved_out = dup(1);
-		if (saved_out >= 0) dup2(2, 1);
-		struct RestoreStdout {
-			int fd;
-			~RestoreStdout()
-			{
-				if (fd < 0) return;
-				fflush(stdout);
-				dup2(fd, 1);
-				close(fd);
-			}
-		} restore_stdout{saved_out};
-		char id[NTSM_NCCL_ID_BYTES];
-		if ((rc = ntsm_nccl_unique_id(id))) { std::cerr << PROGRAM ": " << ntsm_last_error(nullptr) << std::endl; return 1; }
-		std::vector<std::thread> th;
-		std::vector<int> rcs((size_t)gpus, 0);
-		for (int g = 0; g < gpus; ++g) th.emplace_back([&, g] { rcs[g] = ntsm_comm_init(ctxs[g], id, g, gpus); });
-		for (auto &t : th) t.join();
-		for (int g = 0; g < gpus; ++g)
-			if (rcs[g]) { std::cerr << PROGRAM ": " << ntsm_last_error(ctxs[g]) << std::endl; return 1; }
-	}
-
 	lap("CUDA context + device tables");
 	// fp.computeCounts(inputFiles);  (:178)
 	std::vector<const char *> paths;
 	for (auto &f : inputFiles) paths.push_back(f.c_str());
 	int early = 0;
-	rc = ntsm_count_files(ctxs.data(), (uint32_t)gpus, paths.data(), (uint32_t)paths.size(), threads, verbose, &early);
-	if (rc) { std::cerr << ntsm_last_error(nullptr) << std::endl; return 1; }
-	if (early) std::cerr << "Reached desired (-m) threshold" << std::endl;   // FingerPrint.hpp:84-86
-	lap("parse + pack + count");
+	if (merge_mode) {
+		// FILES are k-mer count dumps of shards of one sample: summed per k-mer on GPU 0, the per-site max comes after
+		for (const char *p : paths)
+			if ((rc = ntsm_counts_load_add(ctxs[0], sites, p))) {
+				std::cerr << PROGRAM ": " << (rc == NTSM_ERR_IO ? ntsm_last_error(nullptr) : ntsm_last_error(ctxs[0])) << std::endl;
+				return 1;
+			}
+		lap("merge k-mer count files");
+	} else {
+		rc = ntsm_count_files(ctxs.data(), (uint32_t)gpus, paths.data(), (uint32_t)paths.size(), threads, verbose, &early);
+		if (rc) { std::cerr << ntsm_last_error(nullptr) << std::endl; return 1; }
+		if (early) {
+			if (verbose > 0) {
+				// FingerPrint.hpp:477-484; m_totalReads only moves under -vvv (:70-72), so -v / -vv print 0 reads there too.
+				// (The "Current Total:" progress lines of -vvv, racy upstream, are not reproduced.)
+				uint64_t t[3] = {0, 0, 0}, reads = 0;
+				for (ntsm_ctx *x : ctxs) {
+					uint64_t u[3] = {0, 0, 0};
+					ntsm_get_totals(x, u);
+					t[0] += u[0]; t[1] += u[1]; t[2] += u[2];
+					reads += ntsm_ctx_reads(x);
+				}
+				std::cerr << "max count reached at " << (verbose > 2 ? reads : 0) << " reads, " << t[0] << " k-mers, " << t[1]
+				          << " total counts, and " << t[2] << " total bases " << std::endl;
+			}
+			std::cerr << "Reached desired (-m) threshold" << std::endl;   // FingerPrint.hpp:84-86
+		}
+		lap("parse + pack + count");
+	}
 
-	// combine the GPUs (k-mer level sums, then per-site max) and fetch the rows
+	// combine the GPUs and fetch the rows: GPU 0 sums every GPU's private k-mer counts out of peer
+	// memory over NVLink inside the per-site reduce kernel (sums first, max afterwards) -- no communicator
 	const uint32_t S = ntsm_sites_n_sites(sites);
 	std::vector<uint32_t> mr(S), mv(S), sr(S), sv(S);
 	uint64_t totals[3] = {0, 0, 0};
-	{
-		std::vector<std::thread> th;
-		std::vector<int> rcs((size_t)gpus, 0);
-		for (int g = 1; g < gpus; ++g) th.emplace_back([&, g] { rcs[g] = ntsm_finalize(ctxs[g], nullptr, nullptr, nullptr, nullptr, nullptr); });
-		rcs[0] = ntsm_finalize(ctxs[0], mr.data(), mv.data(), sr.data(), sv.data(), totals);
-		for (auto &t : th) t.join();
-		for (int g = 0; g < gpus; ++g)
-			if (rcs[g]) { std::cerr << PROGRAM ": " << ntsm_last_error(ctxs[g]) << std::endl; return 1; }
+	rc = ntsm_group_finalize(ctxs.data(), (uint32_t)gpus, mr.data(), mv.data(), sr.data(), sv.data(), totals);
+	if (rc) { std::cerr << PROGRAM ": " << ntsm_last_error(ctxs[0]) << std::endl; return 1; }
+	if (!dump_path.empty() && (rc = ntsm_counts_save(ctxs[0], sites, dump_path.c_str()))) {     // GPU 0 holds the combined k-mer counts now
+		std::cerr << PROGRAM ": " << (rc == NTSM_ERR_IO ? ntsm_last_error(nullptr) : ntsm_last_error(ctxs[0])) << std::endl;
+		return 1;
 	}
 
 	// fp.printOptionalHeader(); fp.printCountsMax();  (:179-180)

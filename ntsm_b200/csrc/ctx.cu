@@ -19,9 +19,8 @@
 #include "../../include/ntsm_b200.h"
 #include "internal.h"
 #include "kernels.cuh"
-#include "gate2.cuh"
-#include "seed.cuh"
 #include "pair.cuh"
+#include "devpack.cuh"
 #include "pack.h"
 
 using namespace ntsm;
@@ -35,6 +34,10 @@ struct ntsm_batch {
 	uint64_t *h_snap = nullptr;       // pinned {TK, hits} snapshot taken after this batch's kernel
 	uint2 *d_bases = nullptr;
 	uint32_t *d_mask = nullptr;
+	uint8_t *d_ascii = nullptr;       // device staging for reads that arrive as ASCII and are packed on the GPU (lazily allocated)
+	uint32_t *d_aux = nullptr;        // per-read input offsets + output positions of a variable-length ASCII batch
+	uint32_t *h_aux = nullptr;        // pinned twin of d_aux, filled by the feeder thread
+	uint64_t aux_cap = 0;             // reads d_aux / h_aux hold
 	cudaEvent_t copied = nullptr, done = nullptr;
 	Packer pk;
 	uint64_t cap_pos = 0;             // usable positions
@@ -52,17 +55,22 @@ struct ntsm_ctx {
 	int device = 0;
 	cudaStream_t copy_stream = nullptr, compute_stream = nullptr, own_compute = nullptr;
 	int sm_count = 148;
+	// options (ntsm_ctx_set_option, before ntsm_load_sites); -1 / 0 = decide from the panel
+	int opt_kernel = -1;                    // 0 generic (one k-mer-bitmap probe per position), 1 paired seeds
+	int opt_pair_fold = -1;                 // paired-seed table folded 2^fold : 1
+	int opt_filter_bits = 0;                // log2 bits of the k-mer bitmap
+	int opt_shape = 1;                      // pair kernel launch shape: 0 = 1024x1, 1 = 1024x2 (default), 2 = 512x4, 3 = 256x8
+	int opt_l2_persist = 1;                 // mark the probe tables as persisting in L2 when they fit the set-aside
+	int opt_device_pack = 1;                // bulk inserts from page-locked memory also feed ASCII to the GPU packer
 	// site table
 	uint32_t n_kmers = 0, n_sites = 0;
-	uint32_t *d_filter = nullptr;
-	uint32_t *d_level1 = nullptr;           // 4^M-bit minimizer bitmap of the k = 19 kernels (layout per variant)
-	uint32_t *d_level0 = nullptr;           // image of the gated kernels' shared-memory level-0 bitmap
-	int kernel_variant = 5;                 // k = 19: 0 plain, 1 minimizer, 2 smem-gated minimizer, 3 gate2, 4 strided seeds, 5 paired seeds (default)
-	int pair_fold = kPairFoldDefault;       // paired-seed table folded 2^pair_fold : 1 (NTSM_PAIR_FOLD)
-	int seed_cfg = 1;                       // seed kernel launch shape (NTSM_SEED_CFG): 0 = 1024x1, 1 = 1024x2 (default), 2 = 512x4, 3 = 256x8
-	int gate_m = 14;                        // M-mer length of gate2 (13 or 14)
-	int gate_threads = 1024;                // gate2 CTA size (NTSM_GATE_THREADS: 512 / 768 / 1024)
-	bool pool_tail = true;                  // gate2: warp-pooled level-2/exact tail (NTSM_TAIL_POOL=0 -> per-lane loop)
+	uint32_t *d_probe = nullptr;            // ONE allocation: paired-seed table, then the k-mer bitmap (one L2 access-policy window covers both)
+	uint32_t *d_pair = nullptr, *d_filter = nullptr;   // into d_probe
+	size_t probe_bytes = 0;
+	int kernel = 0;                         // what launch_count runs: 0 generic, 1 paired seeds
+	int pair_m = 0, pair_fold = 0;
+	bool l2_window = false;                 // launches carry an access-policy window over d_probe
+	float l2_hit_ratio = 1.0f;
 	uint32_t filter_bits = 0;
 	TableSlot *d_table = nullptr;
 	uint32_t table_cap = 0;
@@ -73,19 +81,24 @@ struct ntsm_ctx {
 	// batches
 	std::vector<ntsm_batch *> batches;
 	std::deque<ntsm_batch *> inflight;
-	std::mutex mu;
+	std::mutex mu;                          // batch states, the in-flight queue, the completed tallies
+	std::mutex submit_mu;                   // one producer at a time enqueues copy + kernel + snapshot (stream order = queue order)
 	std::condition_variable cv;
 	ntsm_batch *current = nullptr;          // ntsm_insert_count's open batch
 	// tallies
 	uint64_t done_kmers = 0, done_hits = 0, done_bases = 0;   // over completed batches
 	uint64_t submitted_bases = 0;
+	uint64_t submitted_reads = 0;           // reads begun in the packed batches submitted so far (m_totalReads, src/FingerPrint.hpp:72)
 	uint64_t launches = 0;
+	uint64_t h2d_bytes = 0, d2h_bytes = 0;  // copied over PCIe by this ctx's data path so far (batches, snapshots, result rows)
+	int async_error = 0;                    // a batch's event reported a device fault: sticky until the ctx is destroyed
 	// exact -m stop: the last batch submitted, a scratch tally, and what launch_count adds per hit
 	ntsm_batch *last_batch = nullptr;
 	unsigned long long *d_scratch_totals = nullptr;
 	uint32_t launch_delta = 1;
 	unsigned long long *launch_totals = nullptr;   // nullptr = d_totals
 	bool reduced = false;
+	cudaEvent_t drained = nullptr;          // ntsm_group_finalize: this ctx's counts are final
 	ncclComm_t comm = nullptr;
 	int rank = 0, n_ranks = 1;
 	std::string err;
@@ -133,9 +146,12 @@ extern "C" int ntsm_device_warmup(int device)
 }
 
 // ------------------------------------------------------------------ context
+extern "C" void ntsm_ctx_destroy(ntsm_ctx *c);
+
 extern "C" int ntsm_ctx_create(ntsm_ctx **out, const ntsm_cfg *cfg)
 {
 	if (!out || !cfg) return fail(nullptr, NTSM_ERR_ARG, "ntsm_ctx_create: null argument");
+	*out = nullptr;
 	if (cfg->k < 1 || cfg->k > 31) return fail(nullptr, NTSM_ERR_ARG, "k must be in 1..31 (got %u)", cfg->k);
 	int n_dev = 0;
 	cudaError_t e = cudaGetDeviceCount(&n_dev);
@@ -148,14 +164,26 @@ extern "C" int ntsm_ctx_create(ntsm_ctx **out, const ntsm_cfg *cfg)
 	if (c->cfg.n_buffers < 2) c->cfg.n_buffers = 2;
 	if (c->cfg.batch_bases == 0) c->cfg.batch_bases = 1ull << 25;
 	if (c->cfg.batch_bases < 4096) c->cfg.batch_bases = 4096;
+	// stream positions inside one batch are 32-bit (read ends recorded for the exact -m stop, the
+	// device packer's per-read offsets): 2^31 positions per batch is far beyond any useful size
+	if (c->cfg.batch_bases > (1ull << 31)) c->cfg.batch_bases = 1ull << 31;
 	c->device = cfg->device;
-	CU(c, cudaSetDevice(c->device));
-	CU(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
-	CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-	CU(c, cudaStreamCreateWithFlags(&c->own_compute, cudaStreamNonBlocking));
-	c->compute_stream = c->own_compute;
-	CU(c, cudaMalloc(&c->d_totals, 3 * sizeof(unsigned long long)));
-	CU(c, cudaMemset(c->d_totals, 0, 3 * sizeof(unsigned long long)));
+	auto init = [&]() -> int {
+		CU(c, cudaSetDevice(c->device));
+		CU(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+		CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+		CU(c, cudaStreamCreateWithFlags(&c->own_compute, cudaStreamNonBlocking));
+		c->compute_stream = c->own_compute;
+		CU(c, cudaEventCreateWithFlags(&c->drained, cudaEventDisableTiming));
+		CU(c, cudaMalloc(&c->d_totals, 3 * sizeof(unsigned long long)));
+		CU(c, cudaMemset(c->d_totals, 0, 3 * sizeof(unsigned long long)));
+		return NTSM_OK;
+	};
+	const int rc = init();
+	if (rc) {
+		ntsm_ctx_destroy(c);      // the text of the failure stays in this thread's last error
+		return rc;
+	}
 	*out = c;
 	return NTSM_OK;
 }
@@ -166,8 +194,11 @@ static void free_batch(ntsm_batch *b)
 	cudaFreeHost(b->h_bases);
 	cudaFreeHost(b->h_mask);
 	cudaFreeHost(b->h_snap);
+	cudaFreeHost(b->h_aux);
 	cudaFree(b->d_bases);
 	cudaFree(b->d_mask);
+	cudaFree(b->d_ascii);
+	cudaFree(b->d_aux);
 	if (b->copied) cudaEventDestroy(b->copied);
 	if (b->done) cudaEventDestroy(b->done);
 	delete b;
@@ -180,17 +211,32 @@ extern "C" void ntsm_ctx_destroy(ntsm_ctx *c)
 	cudaDeviceSynchronize();
 	if (c->comm) ncclCommDestroy(c->comm);
 	for (ntsm_batch *b : c->batches) free_batch(b);
-	cudaFree(c->d_filter);
-	cudaFree(c->d_level1);
-	cudaFree(c->d_level0);
+	cudaFree(c->d_probe);
 	cudaFree(c->d_table);
 	cudaFree(c->d_counts);
 	cudaFree(c->d_allele_off);
 	cudaFree(c->d_rows);
 	cudaFree(c->d_totals);
+	cudaFree(c->d_scratch_totals);
+	if (c->drained) cudaEventDestroy(c->drained);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	if (c->own_compute) cudaStreamDestroy(c->own_compute);
 	delete c;
+}
+
+// Measurement / test knobs, set before ntsm_load_sites (every setting gives the same counts: the
+// pre-filters only ever let too many windows through).  Replaces round 1's NTSM_* environment reads.
+extern "C" int ntsm_ctx_set_option(ntsm_ctx *c, const char *name, int value)
+{
+	if (!c || !name) return fail(c, NTSM_ERR_ARG, "ntsm_ctx_set_option: null argument");
+	if (!strcmp(name, "kernel")) c->opt_kernel = value < 0 ? -1 : (value ? 1 : 0);
+	else if (!strcmp(name, "pair_fold")) c->opt_pair_fold = value < 0 ? -1 : std::min(kPairFoldMax, value);
+	else if (!strcmp(name, "filter_bits")) c->opt_filter_bits = value <= 0 ? 0 : std::min(32, std::max(10, value));
+	else if (!strcmp(name, "launch_shape")) c->opt_shape = std::min(3, std::max(0, value));
+	else if (!strcmp(name, "l2_persist")) c->opt_l2_persist = value;
+	else if (!strcmp(name, "device_pack")) c->opt_device_pack = value;
+	else return fail(c, NTSM_ERR_ARG, "ntsm_ctx_set_option: unknown option '%s'", name);
+	return NTSM_OK;
 }
 
 // ------------------------------------------------------------------ site table
@@ -208,60 +254,68 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 	while (cap < 2 * live) cap <<= 1;
 	if (cap > (1ull << 31)) return fail(c, NTSM_ERR_ARG, "too many site k-mers (%llu)", (unsigned long long)live);
 
-	// which count kernel will run decides which pre-filter structures are built (NTSM_KERNEL / NTSM_GATE_M
-	// are measurement knobs: every variant gives the same counts)
-	int variant = k == 19 ? 5 : 0, gm = 14;
-	if (const char *e = getenv("NTSM_KERNEL")) variant = atoi(e);
-	if (const char *e = getenv("NTSM_GATE_M")) gm = atoi(e);
-	if (k != 19 || variant < 0 || variant > 5) variant = 0;
-	if (gm < 13 || gm > 14 || variant >= 4) gm = 14;
-	if (const char *e = getenv("NTSM_SEED_CFG")) c->seed_cfg = std::min(3, std::max(0, atoi(e)));
+	// which count kernel will run decides which pre-filter structures are built
+	int kernel = k >= (uint32_t)kPairMinK ? 1 : 0;
+	if (c->opt_kernel >= 0 && kernel) kernel = c->opt_kernel;
+	const int pm = pair_seed_len((int)k);
 	// panels far larger than the human one (cfg 5: 26 M k-mers) saturate a folded pair table and nothing
 	// stays in L2 anyway: measured 318 (unfolded) vs 241 Gbases/s (profiles/r01v12_sweep_cfg5.jsonl)
-	c->pair_fold = live > 5000000 ? 0 : kPairFoldDefault;
-	if (const char *e = getenv("NTSM_PAIR_FOLD")) c->pair_fold = std::min(kPairFoldMax, std::max(0, atoi(e)));
-	if (const char *e = getenv("NTSM_TAIL_POOL")) c->pool_tail = atoi(e) != 0;
-	if (const char *e = getenv("NTSM_GATE_THREADS")) c->gate_threads = atoi(e);
+	int fold = live > 5000000 ? 0 : kPairFoldDefault;
+	if (c->opt_pair_fold >= 0) fold = c->opt_pair_fold;
+	while (fold > 0 && (pair_words(pm) >> fold) < 1024) --fold;
 
-	// k-mer bitmap holding both orientations of every live k-mer
+	// k-mer bitmap holding both orientations of every live k-mer, two bits each: ~40 bits per key
 	uint32_t fbits = 16;
 	while (fbits < 30 && (1ull << fbits) < 40ull * 2ull * live) ++fbits;
-	if (const char *e = getenv("NTSM_FILTER_BITS")) fbits = (uint32_t)std::min(32, std::max(10, atoi(e)));
-	const size_t filter_words = (1ull << fbits) / 32;                 // layout depends on the variant
-	// minimizer bitmaps: level 1 = 4^M bits in global memory, level 0 = image of the shared-memory bitmap
-	const int mm_len = variant == 1 ? kMinimizerM : variant == 2 ? kGateM : gm;
-	const size_t level1_words = variant == 5 ? kPairWords >> c->pair_fold : variant ? (1ull << (2 * mm_len)) / 32 : 0;
-	const size_t level0_words = variant == 2 || variant == 3 ? kL0Words : 0;
+	if (c->opt_filter_bits) fbits = (uint32_t)c->opt_filter_bits;
+	const size_t filter_words = (1ull << fbits) / 32;
+	const size_t pair_n = kernel == 1 ? pair_words(pm) >> fold : 0;
 
-	cudaFree(c->d_filter); cudaFree(c->d_level1); cudaFree(c->d_level0); cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_allele_off); cudaFree(c->d_rows);
-	c->d_level1 = nullptr; c->d_level0 = nullptr; c->d_filter = nullptr; c->d_table = nullptr; c->d_counts = nullptr; c->d_allele_off = nullptr; c->d_rows = nullptr;
-	CU(c, cudaMalloc(&c->d_filter, filter_words * 4));
+	cudaFree(c->d_probe); cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_allele_off); cudaFree(c->d_rows);
+	c->d_probe = c->d_pair = c->d_filter = nullptr; c->d_table = nullptr; c->d_counts = nullptr; c->d_allele_off = nullptr; c->d_rows = nullptr;
+	{
+		// The pair probe forms addresses as {lo32(base) + offset, hi32(base)}: the table must not cross a
+		// 4 GiB line.  cudaMalloc hands out 2 MiB-aligned blocks, so a second try always fits.
+		const size_t bytes = (pair_n + filter_words) * 4;
+		std::vector<void *> rejected;
+		for (int attempt = 0; attempt < 8; ++attempt) {
+			CU(c, cudaMalloc(&c->d_probe, bytes));
+			const uintptr_t a = (uintptr_t)c->d_probe, z = a + std::max<size_t>(4, pair_n * 4) - 1;
+			if ((a >> 32) == (z >> 32)) break;
+			rejected.push_back(c->d_probe);
+			c->d_probe = nullptr;
+		}
+		for (void *r : rejected) cudaFree(r);
+		if (!c->d_probe) return fail(c, NTSM_ERR_CUDA, "could not place the paired-seed table inside one 4 GiB window");
+		c->probe_bytes = bytes;
+		c->d_pair = pair_n ? c->d_probe : nullptr;
+		c->d_filter = c->d_probe + pair_n;
+	}
 	CU(c, cudaMalloc(&c->d_table, cap * sizeof(TableSlot)));
 	CU(c, cudaMalloc(&c->d_counts, std::max<size_t>(1, n_kmers) * 4));
 	CU(c, cudaMalloc(&c->d_allele_off, (2 * (size_t)n_sites + 1) * 4));
 	CU(c, cudaMalloc(&c->d_rows, std::max<size_t>(1, n_sites) * 16));
-	if (level1_words) {
-		// gate2 forms probe addresses as {lo32(base) + offset, hi32(base)}: the bitmap must not cross a
-		// 4 GiB line.  cudaMalloc hands out 2 MiB-aligned blocks, so a second try always fits.
-		std::vector<void *> rejected;
-		for (int attempt = 0; attempt < 8; ++attempt) {
-			CU(c, cudaMalloc(&c->d_level1, level1_words * 4));
-			const uintptr_t a = (uintptr_t)c->d_level1, z = a + level1_words * 4 - 1;
-			if ((a >> 32) == (z >> 32)) break;
-			rejected.push_back(c->d_level1);
-			c->d_level1 = nullptr;
+
+	// L2 residency: the probe tables are hit at random by every warp while the packed reads stream
+	// through the same L2 once.  The reads are loaded with an evict-first hint (ld.global.cs); on top of
+	// that the count kernels are launched with an access-policy window that marks the probe tables as
+	// persisting, when the device's persisting set-aside can hold them (cfg 2: 48 MiB of tables).
+	c->l2_window = false;
+	if (c->opt_l2_persist) {
+		int max_persist = 0, max_window = 0;
+		cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+		cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+		if (max_persist > 0 && max_window > 0) {
+			const size_t want = std::min<size_t>(c->probe_bytes, (size_t)max_persist);
+			size_t have = 0;
+			cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize);
+			if (have < want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) cudaGetLastError();
+			cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize);
+			if (have > 0 && c->probe_bytes <= (size_t)max_window) {
+				c->l2_window = true;
+				c->l2_hit_ratio = (float)std::min(1.0, (double)have / (double)c->probe_bytes);
+			}
 		}
-		for (void *r : rejected) cudaFree(r);
-		if (!c->d_level1) return fail(c, NTSM_ERR_CUDA, "could not place the minimizer bitmap inside one 4 GiB window");
-	}
-	if (level0_words) {
-		CU(c, cudaMalloc(&c->d_level0, level0_words * 4));
-		CU(c, cudaFuncSetAttribute(count_kernel_gate<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
-		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 13, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
-		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 14, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
-		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 14, false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
-		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 14, true, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
-		CU(c, cudaFuncSetAttribute(count_kernel_gate2<19, 14, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kL0Words * 4)));
 	}
 
 	// Build on the device (initCountsHash's insert loop, src/FingerPrint.hpp:506-552, with the host
@@ -282,13 +336,11 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 		else CU(c, cudaMemsetAsync(d_erased, 0, std::max<size_t>(1, n_kmers), st));
 		CU(c, cudaMemsetAsync(d_err, 0, sizeof h_err, st));
 		CU(c, cudaMemsetAsync(c->d_table, 0xFF, cap * sizeof(TableSlot), st));          // key = kEmptyKey everywhere
-		CU(c, cudaMemsetAsync(c->d_filter, 0, filter_words * 4, st));
-		if (level1_words) CU(c, cudaMemsetAsync(c->d_level1, 0, level1_words * 4, st));
-		if (level0_words) CU(c, cudaMemsetAsync(c->d_level0, 0, level0_words * 4, st));
+		CU(c, cudaMemsetAsync(c->d_probe, 0, c->probe_bytes, st));
 		BuildParams B;
-		B.hash = d_hash; B.erased = d_erased; B.n_kmers = n_kmers; B.k = k; B.variant = variant; B.gate_m = gm;
+		B.hash = d_hash; B.erased = d_erased; B.n_kmers = n_kmers; B.k = k;
 		B.table = c->d_table; B.table_mask = (uint32_t)(cap - 1); B.filter = c->d_filter; B.filter_shift = 32 - fbits;
-		B.level1 = c->d_level1; B.level0 = c->d_level0; B.err = d_err; B.pair_word_mask = pair_word_mask(c->pair_fold);
+		B.pair = c->d_pair; B.pair_m = (uint32_t)pm; B.pair_word_mask = pair_word_mask(pm, fold); B.err = d_err;
 		if (n_kmers) {
 			build_tables_kernel<<<(n_kmers + 255) / 256, 256, 0, st>>>(B);
 			CU(c, cudaGetLastError());
@@ -304,8 +356,9 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 	if (brc) return brc;
 	if (h_err[0] == 1) return fail(c, NTSM_ERR_ARG, "k-mer hash %d out of range for k=%u", h_err[1], k);
 	if (h_err[0] == 2) return fail(c, NTSM_ERR_ARG, "duplicate k-mer hash at index %d", h_err[1]);
-	c->kernel_variant = variant;
-	c->gate_m = gm;
+	c->kernel = kernel;
+	c->pair_m = pm;
+	c->pair_fold = fold;
 	c->n_kmers = n_kmers;
 	c->n_sites = n_sites;
 	c->filter_bits = fbits;
@@ -327,7 +380,7 @@ static int reset_tallies(ntsm_ctx *c)
 	if (!c->inflight.empty()) return fail(c, NTSM_ERR_ARG, "reset with batches in flight; ntsm_sync first");
 	if (c->d_counts) CU(c, cudaMemsetAsync(c->d_counts, 0, std::max<size_t>(1, c->n_kmers) * 4, c->compute_stream));
 	CU(c, cudaMemsetAsync(c->d_totals, 0, 3 * sizeof(unsigned long long), c->compute_stream));
-	c->done_kmers = c->done_hits = c->done_bases = c->submitted_bases = 0;
+	c->done_kmers = c->done_hits = c->done_bases = c->submitted_bases = c->submitted_reads = 0;
 	c->reduced = false;
 	return NTSM_OK;
 }
@@ -360,61 +413,70 @@ extern "C" int ntsm_set_stream(ntsm_ctx *c, void *cuda_stream)
 }
 
 // ------------------------------------------------------------------ kernel launch
+template <class Kern>
+static cudaError_t launch_with_window(ntsm_ctx *c, Kern kern, unsigned grid, unsigned block, cudaStream_t st, const CountParams &P)
+{
+	cudaLaunchConfig_t lc = {};
+	lc.gridDim = dim3(grid);
+	lc.blockDim = dim3(block);
+	lc.stream = st;
+	cudaLaunchAttribute at[1];
+	if (c->l2_window) {
+		at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+		at[0].val.accessPolicyWindow.base_ptr = c->d_probe;
+		at[0].val.accessPolicyWindow.num_bytes = c->probe_bytes;
+		at[0].val.accessPolicyWindow.hitRatio = c->l2_hit_ratio;
+		at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+		at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+		lc.attrs = at;
+		lc.numAttrs = 1;
+	}
+	return cudaLaunchKernelEx(&lc, kern, P);
+}
+
 static int launch_count(ntsm_ctx *c, const uint2 *d_bases, const uint32_t *d_mask, uint64_t n_pos, cudaStream_t st)
 {
 	if (!c->d_table) return fail(c, NTSM_ERR_ARG, "no site table loaded");
-	if (c->reduced) return fail(c, NTSM_ERR_ARG, "counts were already all-reduced; ntsm_reset_counts first");
+	if (c->reduced) return fail(c, NTSM_ERR_ARG, "counts were already combined; ntsm_reset_counts first");
 	if (n_pos == 0) return NTSM_OK;
 	CountParams P;
 	P.bases = d_bases;
 	P.nmask = d_mask;
 	P.n_chunks = (n_pos + 31) / 32;
-	P.minimizer = c->d_level1;
-	P.minimizer2 = c->d_level1;
-	P.level0 = c->d_level0;
+	P.pair = c->d_pair;
+	P.pair_off_mask = pair_word_mask(c->pair_m, c->pair_fold) << 2;
+	P.pair_bshift = 2 * (uint32_t)c->pair_m;
 	P.filter = c->d_filter;
 	P.filter_shift = 32 - c->filter_bits;
 	P.table = c->d_table;
 	P.table_mask = c->table_cap - 1;
 	P.k = c->cfg.k;
-	P.four = 4;
-	P.pair_word_mask = pair_word_mask(c->pair_fold);
 	P.delta = c->launch_delta;
 	P.counts = c->d_counts;
 	P.totals = c->launch_totals ? c->launch_totals : c->d_totals;
-	const uint64_t tiles = (P.n_chunks + kCountThreads - 1) / kCountThreads;
-	const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)c->sm_count * 16);
-	const unsigned g2 = (unsigned)std::min<uint64_t>((P.n_chunks + kGateThreads - 1) / kGateThreads, (uint64_t)c->sm_count);
-	if (c->cfg.k == 19 && c->kernel_variant >= 4) {
+	cudaError_t le;
+	if (c->kernel == 1) {
 		// persistent: MINB CTAs per SM (fewer when the batch has fewer 31-chunk groups than that many CTAs have warps)
 		const uint64_t groups = (P.n_chunks + kGroupChunks - 1) / kGroupChunks;
 		static const int shape[4][2] = { { 1024, 1 }, { 1024, 2 }, { 512, 4 }, { 256, 8 } };
-		const int th = shape[c->seed_cfg][0], mb = shape[c->seed_cfg][1];
+		const int th = shape[c->opt_shape][0], mb = shape[c->opt_shape][1];
 		const uint64_t wpc = th / 32;
 		const unsigned gs = (unsigned)std::min<uint64_t>((groups + wpc - 1) / wpc, (uint64_t)c->sm_count * mb);
-		if (c->kernel_variant == 5) {
-			if (c->seed_cfg == 1) count_kernel_pair<19, 1024, 2><<<gs, 1024, 0, st>>>(P);
-			else if (c->seed_cfg == 2) count_kernel_pair<19, 512, 4><<<gs, 512, 0, st>>>(P);
-			else if (c->seed_cfg == 3) count_kernel_pair<19, 256, 8><<<gs, 256, 0, st>>>(P);
-			else count_kernel_pair<19, 1024, 1><<<gs, 1024, 0, st>>>(P);
-		} else if (c->seed_cfg == 1) count_kernel_seed<19, kSeedM, 1024, 2><<<gs, 1024, 0, st>>>(P);
-		else if (c->seed_cfg == 2) count_kernel_seed<19, kSeedM, 512, 4><<<gs, 512, 0, st>>>(P);
-		else if (c->seed_cfg == 3) count_kernel_seed<19, kSeedM, 256, 8><<<gs, 256, 0, st>>>(P);
-		else count_kernel_seed<19, kSeedM, 1024, 1><<<gs, 1024, 0, st>>>(P);
-	} else if (c->cfg.k == 19 && c->kernel_variant == 3) {
-		// one persistent CTA per SM (fewer when the batch has fewer 31-chunk groups than that many CTAs have warps)
-		const uint64_t groups = (P.n_chunks + kGroupChunks - 1) / kGroupChunks, wpc = (uint64_t)(c->gate_threads == 768 || c->gate_threads == 512 ? c->gate_threads : 1024) / 32;
-		const unsigned g3 = (unsigned)std::min<uint64_t>((groups + wpc - 1) / wpc, (uint64_t)c->sm_count);
-		if (c->gate_m == 13) count_kernel_gate2<19, 13, true, 1024><<<g3, 1024, kL0Words * 4, st>>>(P);
-		else if (!c->pool_tail) count_kernel_gate2<19, 14, false, 1024><<<g3, 1024, kL0Words * 4, st>>>(P);
-		else if (c->gate_threads == 768) count_kernel_gate2<19, 14, true, 768><<<g3, 768, kL0Words * 4, st>>>(P);
-		else if (c->gate_threads == 512) count_kernel_gate2<19, 14, true, 512><<<g3, 512, kL0Words * 4, st>>>(P);
-		else count_kernel_gate2<19, 14, true, 1024><<<g3, 1024, kL0Words * 4, st>>>(P);
-	} else if (c->cfg.k == 19 && c->kernel_variant == 2) count_kernel_gate<19><<<g2, kGateThreads, kL0Words * 4, st>>>(P);
-	else if (c->cfg.k == 19 && c->kernel_variant == 1) count_kernel_min<19, kMinimizerM><<<grid, kCountThreads, 0, st>>>(P);
-	else if (c->cfg.k == 19) count_kernel<19><<<grid, kCountThreads, 0, st>>>(P);
-	else count_kernel<0><<<grid, kCountThreads, 0, st>>>(P);
-	CU(c, cudaGetLastError());
+		if (c->cfg.k == 19) {
+			if (c->opt_shape == 1) le = launch_with_window(c, count_kernel_pair<19, 1024, 2>, gs, 1024, st, P);
+			else if (c->opt_shape == 2) le = launch_with_window(c, count_kernel_pair<19, 512, 4>, gs, 512, st, P);
+			else if (c->opt_shape == 3) le = launch_with_window(c, count_kernel_pair<19, 256, 8>, gs, 256, st, P);
+			else le = launch_with_window(c, count_kernel_pair<19, 1024, 1>, gs, 1024, st, P);
+		} else {
+			const unsigned g0 = (unsigned)std::min<uint64_t>((groups + 31) / 32, (uint64_t)c->sm_count * 2);
+			le = launch_with_window(c, count_kernel_pair<0, 1024, 2>, g0, 1024, st, P);
+		}
+	} else {
+		const uint64_t tiles = (P.n_chunks + kCountThreads - 1) / kCountThreads;
+		const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)c->sm_count * 16);
+		le = launch_with_window(c, count_kernel_generic, grid, kCountThreads, st, P);
+	}
+	if (le != cudaSuccess) return fail(c, NTSM_ERR_CUDA, "count kernel launch: %s", cudaGetErrorString(le));
 	c->launches++;
 	return NTSM_OK;
 }
@@ -437,6 +499,7 @@ extern "C" int ntsm_count_packed_device(ntsm_ctx *c, const uint32_t *d_bases2, c
 static int make_batch(ntsm_ctx *c, ntsm_batch **out)
 {
 	ntsm_batch *b = new ntsm_batch();
+	*out = b;                         // the caller frees it (free_batch) when any step below fails
 	b->ctx = c;
 	b->cap_pos = c->cfg.batch_bases & ~(kReadAlign - 1);
 	const uint64_t padded = padded_positions(b->cap_pos);
@@ -447,11 +510,11 @@ static int make_batch(ntsm_ctx *c, ntsm_batch **out)
 	CU(c, cudaMalloc(&b->d_mask, padded / 32 * 4));
 	CU(c, cudaEventCreateWithFlags(&b->copied, cudaEventDisableTiming));
 	CU(c, cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming));
-	*out = b;
 	return NTSM_OK;
 }
 
-// fold finished batches into the completed tallies; caller holds c->mu
+// fold finished batches into the completed tallies; caller holds c->mu.  A device fault reported by a
+// batch's event makes the ctx fail for good (async_error): the tallies of that batch are not taken.
 static void reap(ntsm_ctx *c, bool block_on_oldest)
 {
 	while (!c->inflight.empty()) {
@@ -459,12 +522,17 @@ static void reap(ntsm_ctx *c, bool block_on_oldest)
 		cudaError_t q = cudaEventQuery(b->done);
 		if (q == cudaErrorNotReady) {
 			if (!block_on_oldest) break;
-			cudaEventSynchronize(b->done);
+			q = cudaEventSynchronize(b->done);
 			block_on_oldest = false;
 		}
-		c->done_kmers = b->h_snap[0];      // d_totals is cumulative and kernels run in submit order
-		c->done_hits = b->h_snap[1];
-		c->done_bases += b->n_bases;
+		if (q != cudaSuccess) {
+			if (!c->async_error) fail(c, NTSM_ERR_CUDA, "a submitted batch failed on the device: %s", cudaGetErrorString(q));
+			c->async_error = NTSM_ERR_CUDA;
+		} else {
+			c->done_kmers = b->h_snap[0];      // d_totals is cumulative and kernels run in submit order
+			c->done_hits = b->h_snap[1];
+			c->done_bases += b->n_bases;
+		}
 		b->state = 0;
 		c->inflight.pop_front();
 	}
@@ -477,6 +545,7 @@ extern "C" int ntsm_acquire_batch(ntsm_ctx *c, ntsm_batch **out)
 	std::unique_lock<std::mutex> g(c->mu);
 	for (;;) {
 		reap(c, false);
+		if (c->async_error) return c->async_error;
 		for (ntsm_batch *b : c->batches)
 			if (b->state == 0) {
 				b->state = 1;
@@ -536,32 +605,201 @@ extern "C" uint64_t ntsm_batch_positions(const ntsm_batch *b) { return b->pk.pos
 extern "C" uint64_t ntsm_batch_bases(const ntsm_batch *b) { return b->n_bases; }
 extern "C" uint64_t ntsm_batch_reads(const ntsm_batch *b) { return b->n_reads; }
 
-// enqueue H2D of a packed stream (src_* = host memory holding at least padded/halo words) into the
-// batch's device buffers, the count kernel and the tally snapshot; caller holds no lock
+// Enqueue one batch: H2D of a packed stream (src_* = host memory holding at least copy_pos positions)
+// into the batch's device buffers -- or, when `ascii` is set, H2D of the reads' ASCII bytes and the
+// decode + pack kernel (devpack.cuh) -- then the count kernel and the tally snapshot.  One producer
+// at a time is in here (submit_mu): the order of the kernels on the compute stream is the order of
+// the in-flight queue; c->mu is only taken for the queue itself, so producers waiting in
+// ntsm_acquire_batch and pollers never wait behind CUDA calls.
+struct AsciiJob {
+	const void *src = nullptr;        // host bytes to copy (pinned)
+	uint64_t bytes = 0;
+	DevPackParams pp;                 // bases / mask / ascii pointers are filled in here
+	bool fixed = true;
+};
+
 static int enqueue_batch(ntsm_ctx *c, ntsm_batch *b, const void *src_bases, const void *src_mask, uint64_t n_pos,
-                         uint64_t copy_pos, uint64_t n_bases)
+                         uint64_t copy_pos, uint64_t n_bases, const AsciiJob *ascii = nullptr)
 {
-	std::lock_guard<std::mutex> g(c->mu);
-	if (n_pos == 0) {
+	auto give_back = [&]() {
+		std::lock_guard<std::mutex> g(c->mu);
 		b->state = 0;
 		c->cv.notify_all();
+	};
+	if (n_pos == 0) {
+		give_back();
 		return NTSM_OK;
 	}
-	CU(c, cudaMemcpyAsync(b->d_bases, src_bases, copy_pos / 32 * 8, cudaMemcpyHostToDevice, c->copy_stream));
-	CU(c, cudaMemcpyAsync(b->d_mask, src_mask, copy_pos / 32 * 4, cudaMemcpyHostToDevice, c->copy_stream));
-	CU(c, cudaEventRecord(b->copied, c->copy_stream));
-	CU(c, cudaStreamWaitEvent(c->compute_stream, b->copied, 0));
-	const int rc = launch_count(c, b->d_bases, b->d_mask, n_pos, c->compute_stream);
+	auto enqueue = [&]() -> int {
+		std::lock_guard<std::mutex> sg(c->submit_mu);
+		if (ascii) {
+			CU(c, cudaMemcpyAsync(b->d_ascii, ascii->src, ascii->bytes, cudaMemcpyHostToDevice, c->copy_stream));
+			c->h2d_bytes += ascii->bytes;
+			if (!ascii->fixed) {
+				CU(c, cudaMemcpyAsync(b->d_aux, b->h_aux, (2 * (uint64_t)ascii->pp.n_reads + 2) * 4, cudaMemcpyHostToDevice, c->copy_stream));
+				c->h2d_bytes += (2 * (uint64_t)ascii->pp.n_reads + 2) * 4;
+			}
+			CU(c, cudaEventRecord(b->copied, c->copy_stream));
+			CU(c, cudaStreamWaitEvent(c->compute_stream, b->copied, 0));
+			DevPackParams pp = ascii->pp;
+			pp.ascii = b->d_ascii;
+			pp.bases = b->d_bases;
+			pp.mask = b->d_mask;
+			const unsigned grid = (unsigned)std::min<uint64_t>((pp.n_chunks_out + 255) / 256, (uint64_t)c->sm_count * 8);
+			if (ascii->fixed) pack_ascii_kernel<true><<<grid, 256, 0, c->compute_stream>>>(pp);
+			else pack_ascii_kernel<false><<<grid, 256, 0, c->compute_stream>>>(pp);
+			CU(c, cudaGetLastError());
+			c->launches++;
+		} else {
+			CU(c, cudaMemcpyAsync(b->d_bases, src_bases, copy_pos / 32 * 8, cudaMemcpyHostToDevice, c->copy_stream));
+			CU(c, cudaMemcpyAsync(b->d_mask, src_mask, copy_pos / 32 * 4, cudaMemcpyHostToDevice, c->copy_stream));
+			c->h2d_bytes += copy_pos / 32 * 12;
+			CU(c, cudaEventRecord(b->copied, c->copy_stream));
+			CU(c, cudaStreamWaitEvent(c->compute_stream, b->copied, 0));
+		}
+		const int rc = launch_count(c, b->d_bases, b->d_mask, n_pos, c->compute_stream);
+		if (rc) return rc;
+		CU(c, cudaMemcpyAsync(b->h_snap, c->d_totals, 16, cudaMemcpyDeviceToHost, c->compute_stream));
+		c->d2h_bytes += 16;
+		CU(c, cudaEventRecord(b->done, c->compute_stream));
+		std::lock_guard<std::mutex> g(c->mu);
+		b->state = 2;
+		b->n_bases = n_bases;
+		b->n_pos = n_pos;
+		c->last_batch = b;
+		c->submitted_bases += n_bases;
+		c->submitted_reads += ascii ? ascii->pp.n_reads : b->n_reads;
+		c->inflight.push_back(b);
+		c->cv.notify_all();
+		return NTSM_OK;
+	};
+	const int rc = enqueue();
+	if (rc) give_back();              // the buffer returns to the ring; the error stays with the ctx
+	return rc;
+}
+
+// ASCII reads in PINNED host memory, decoded and packed on the device.  Fixed-length form: n_reads
+// rows of `stride` bytes, read_len of them bases.  The caller (bulk.cpp's feeder thread) sizes n_reads
+// with ntsm_ascii_capacity so that the packed result fits one batch.
+uint64_t ntsm_ascii_capacity_fixed(const ntsm_ctx *c, uint64_t read_len, uint64_t stride)
+{
+	const uint64_t cap_pos = c->cfg.batch_bases & ~(kReadAlign - 1);
+	const uint64_t by_pos = cap_pos / read_span(read_len);
+	const uint64_t by_bytes = (cap_pos + 4096) / std::max<uint64_t>(1, stride);      // d_ascii holds cap_pos + 4096 bytes
+	return std::min(by_pos, by_bytes);
+}
+
+static int ensure_ascii(ntsm_ctx *c, ntsm_batch *b, uint64_t n_reads_var)
+{
+	if (!b->d_ascii) CU(c, cudaMalloc(&b->d_ascii, b->cap_pos + 4096));
+	if (n_reads_var + 1 > b->aux_cap) {
+		cudaFree(b->d_aux);
+		cudaFreeHost(b->h_aux);
+		b->d_aux = b->h_aux = nullptr;
+		b->aux_cap = 0;
+		const uint64_t cap = std::max<uint64_t>(n_reads_var + 1, b->cap_pos / 64);
+		CU(c, cudaMalloc(&b->d_aux, (2 * cap + 2) * 4));
+		CU(c, cudaMallocHost(&b->h_aux, (2 * cap + 2) * 4));
+		b->aux_cap = cap;
+	}
+	return NTSM_OK;
+}
+
+int ntsm_submit_ascii_fixed(ntsm_ctx *c, const char *rows, uint64_t read_len, uint64_t stride, uint64_t n_reads)
+{
+	if (!c || !rows || n_reads == 0) return NTSM_OK;
+	if (n_reads > ntsm_ascii_capacity_fixed(c, read_len, stride)) return fail(c, NTSM_ERR_ARG, "ntsm_submit_ascii_fixed: block larger than a batch");
+	ntsm_batch *b = nullptr;
+	int rc = ntsm_acquire_batch(c, &b);
 	if (rc) return rc;
-	CU(c, cudaMemcpyAsync(b->h_snap, c->d_totals, 16, cudaMemcpyDeviceToHost, c->compute_stream));
-	CU(c, cudaEventRecord(b->done, c->compute_stream));
-	b->state = 2;
-	b->n_bases = n_bases;
-	b->n_pos = n_pos;
-	c->last_batch = b;
-	c->submitted_bases += n_bases;
-	c->inflight.push_back(b);
-	c->cv.notify_all();
+	if ((rc = ensure_ascii(c, b, 0))) { ntsm_release_batch(c, b); return rc; }
+	AsciiJob j;
+	j.src = rows;
+	j.bytes = (n_reads - 1) * stride + read_len;
+	j.fixed = true;
+	memset(&j.pp, 0, sizeof j.pp);
+	j.pp.read_len = (uint32_t)read_len;
+	j.pp.stride = (uint32_t)stride;
+	j.pp.span = (uint32_t)read_span(read_len);
+	j.pp.groups_per_read = j.pp.span / 8;
+	j.pp.n_reads = (uint32_t)n_reads;
+	j.pp.n_pos = n_reads * read_span(read_len);
+	j.pp.n_chunks_out = padded_positions(j.pp.n_pos) / 32;
+	return enqueue_batch(c, b, nullptr, nullptr, j.pp.n_pos, 0, n_reads * read_len, &j);
+}
+
+// Variable-length form: read r = buf[off[r], off[r+1]) for r in [0, n_reads); takes as many whole reads
+// from the front as fit one batch (at least one unless the first read alone is too long: returns 0 reads
+// taken, and the caller packs that read on the host, which splits long reads).  *taken = reads consumed.
+int ntsm_submit_ascii_var(ntsm_ctx *c, const char *buf, const uint64_t *off, uint64_t n_reads, uint64_t *taken)
+{
+	*taken = 0;
+	if (!c || !buf || !off || n_reads == 0) return NTSM_OK;
+	const uint64_t cap_pos = c->cfg.batch_bases & ~(kReadAlign - 1);
+	// how many reads fit: positions (spans) and staged bytes both bounded by the batch
+	uint64_t n = 0, pos = 0;
+	while (n < n_reads) {
+		const uint64_t len = off[n + 1] - off[n];
+		if (pos + read_span(len) > cap_pos || off[n + 1] - off[0] > cap_pos + 4096) break;
+		pos += read_span(len);
+		++n;
+	}
+	if (n == 0) return NTSM_OK;
+	ntsm_batch *b = nullptr;
+	int rc = ntsm_acquire_batch(c, &b);
+	if (rc) return rc;
+	if ((rc = ensure_ascii(c, b, n))) { ntsm_release_batch(c, b); return rc; }
+	uint32_t *in_off = b->h_aux, *out_pos = b->h_aux + (n + 1);
+	uint64_t p = 0;
+	for (uint64_t r = 0; r < n; ++r) {
+		in_off[r] = (uint32_t)(off[r] - off[0]);
+		out_pos[r] = (uint32_t)p;
+		p += read_span(off[r + 1] - off[r]);
+	}
+	in_off[n] = (uint32_t)(off[n] - off[0]);
+	out_pos[n] = (uint32_t)p;
+	AsciiJob j;
+	j.src = buf + off[0];
+	j.bytes = off[n] - off[0];
+	j.fixed = false;
+	memset(&j.pp, 0, sizeof j.pp);
+	j.pp.in_off = b->d_aux;
+	j.pp.out_pos = b->d_aux + (n + 1);
+	j.pp.n_reads = (uint32_t)n;
+	j.pp.n_pos = p;
+	j.pp.n_chunks_out = padded_positions(p) / 32;
+	*taken = n;
+	if (j.bytes == 0) {              // nothing but empty reads: no bases, no windows
+		ntsm_release_batch(c, b);
+		return NTSM_OK;
+	}
+	return enqueue_batch(c, b, nullptr, nullptr, p, 0, off[n] - off[0], &j);
+}
+
+// 1 when `p` points into page-locked host memory the DMA engines can read directly (cudaMallocHost /
+// cudaHostAlloc / cudaHostRegister), else 0
+int ntsm_ctx_device_pack(const ntsm_ctx *c) { return c->opt_device_pack; }
+
+int ntsm_host_is_pinned(const void *p)
+{
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return at.type == cudaMemoryTypeHost;
+}
+
+extern "C" int ntsm_host_register(void *p, uint64_t bytes)
+{
+	const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+	if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, NTSM_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e)); }
+	return NTSM_OK;
+}
+extern "C" int ntsm_host_unregister(void *p)
+{
+	const cudaError_t e = cudaHostUnregister(p);
+	if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, NTSM_ERR_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e)); }
 	return NTSM_OK;
 }
 
@@ -648,16 +886,16 @@ extern "C" int ntsm_sync(ntsm_ctx *c)
 {
 	if (!c) return NTSM_ERR_ARG;
 	CU(c, cudaSetDevice(c->device));
-	CU(c, cudaDeviceSynchronize());
-	std::lock_guard<std::mutex> g(c->mu);
-	reap(c, false);
-	c->cv.notify_all();
+	{   // every submitted batch, then whatever else sits on the ctx's two streams -- not the whole device
+		std::unique_lock<std::mutex> g(c->mu);
+		while (!c->inflight.empty()) reap(c, true);
+		c->cv.notify_all();
+		if (c->async_error) return c->async_error;
+	}
+	CU(c, cudaStreamSynchronize(c->copy_stream));
+	CU(c, cudaStreamSynchronize(c->compute_stream));
 	return NTSM_OK;
 }
-
-namespace ntsm {
-__global__ void set_u64_kernel(unsigned long long *p, unsigned long long v) { *p = v; }
-}  // namespace ntsm
 
 // ------------------------------------------------------------------ exact -m stop
 // The reference checks the cap after EVERY read (processSingleRead, src/FingerPrint.hpp:473-488): the
@@ -728,6 +966,7 @@ int ntsm_trim_to_cap(ntsm_ctx *c, uint64_t hits_elsewhere, uint64_t cap)
 	const uint64_t dropped = b->n_bases - b->read_bases[lo];
 	c->done_bases -= dropped;
 	c->submitted_bases -= dropped;
+	c->submitted_reads -= b->n_reads - (lo + 1);
 	b->read_end.clear();
 	return 1;
 }
@@ -738,9 +977,14 @@ int ntsm_trim_to_cap(ntsm_ctx *c, uint64_t hits_elsewhere, uint64_t cap)
 // NCCL_DEBUG=VERSION: raise that to WARN (which prints the same banner) so the file setting applies.
 static void nccl_banner_to_stderr()
 {
-	const char *lvl = getenv("NCCL_DEBUG");
-	if (lvl && !strcasecmp(lvl, "VERSION")) setenv("NCCL_DEBUG", "WARN", 1);
-	setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
+	// once per process, before the first NCCL call (setenv is not thread-safe and ntsm_comm_init is
+	// meant to run on one thread per GPU at once); documented in the header as a side effect
+	static std::once_flag once;
+	std::call_once(once, [] {
+		const char *lvl = getenv("NCCL_DEBUG");
+		if (lvl && !strcasecmp(lvl, "VERSION")) setenv("NCCL_DEBUG", "WARN", 1);
+		setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
+	});
 }
 
 extern "C" int ntsm_nccl_unique_id(void *id_out)
@@ -789,8 +1033,12 @@ extern "C" int ntsm_reduce_async(ntsm_ctx *c)
 	const uint32_t S = c->n_sites;
 	if (S) {
 		uint32_t *r = c->d_rows;
-		site_reduce_kernel<<<(S + 255) / 256, 256, 0, c->compute_stream>>>(c->d_counts, c->d_allele_off, S, r, r + S,
-		                                                                   r + 2 * (size_t)S, r + 3 * (size_t)S);
+		PeerCounts pc;
+		memset(&pc, 0, sizeof pc);
+		pc.counts[0] = c->d_counts;
+		pc.n_ranks = 1;
+		site_reduce_kernel<<<(S + 255) / 256, 256, 0, c->compute_stream>>>(pc, c->d_allele_off, S, r, r + S, r + 2 * (size_t)S,
+		                                                                   r + 3 * (size_t)S, nullptr);
 		CU(c, cudaGetLastError());
 		c->launches++;
 	}
@@ -811,6 +1059,84 @@ extern "C" int ntsm_allreduce(ntsm_ctx *c)
 	return NTSM_OK;
 }
 
+// ------------------------------------------------------------------ several GPUs of ONE process
+// Combine + per-site reduce for the ctxs of one process (the CLI's --gpus N: one ctx per GPU) without
+// NCCL: ctx 0's GPU reads every other ctx's private counts straight out of peer memory over NVLink
+// inside the per-site reduce kernel (site_reduce_kernel: sum over GPUs first, max afterwards), so the
+// all-reduce and the reduce that follows it are ONE kernel, nothing is staged, and no communicator has
+// to be brought up (ncclCommInitRank was most of a short run's wall time in round 1).  Each ctx's
+// stream records "my counts are final"; ctx 0's stream waits for all of them.  ctxs on the same
+// device (tests on a one-GPU box) simply read each other's arrays.
+extern "C" int ntsm_group_finalize(ntsm_ctx *const *ctxs, uint32_t n_ctx, uint32_t *max_ref, uint32_t *max_var,
+                                   uint32_t *sum_ref, uint32_t *sum_var, uint64_t totals[3])
+{
+	if (!ctxs || n_ctx == 0 || n_ctx > (uint32_t)kMaxPeers) return fail(nullptr, NTSM_ERR_ARG, "ntsm_group_finalize: 1..%d ctxs", kMaxPeers);
+	ntsm_ctx *c0 = ctxs[0];
+	if (n_ctx == 1) return ntsm_finalize(c0, max_ref, max_var, sum_ref, sum_var, totals);
+	for (uint32_t i = 0; i < n_ctx; ++i) {
+		ntsm_ctx *c = ctxs[i];
+		if (!c || !c->d_table || c->n_kmers != c0->n_kmers || c->n_sites != c0->n_sites || c->cfg.k != c0->cfg.k)
+			return fail(c0, NTSM_ERR_ARG, "ntsm_group_finalize: ctx %u does not hold the same site table", i);
+		if (c->reduced) return fail(c0, NTSM_ERR_ARG, "ntsm_group_finalize: ctx %u was already combined", i);
+	}
+	PeerCounts pc;
+	PeerTotals pt;
+	memset(&pc, 0, sizeof pc);
+	memset(&pt, 0, sizeof pt);
+	pc.n_ranks = pt.n_ranks = (int)n_ctx;
+	for (uint32_t i = 0; i < n_ctx; ++i) {
+		ntsm_ctx *c = ctxs[i];
+		int rc = ntsm_flush(c);
+		if (rc) return rc;
+		CU(c, cudaSetDevice(c->device));
+		{
+			std::unique_lock<std::mutex> g(c->mu);
+			while (!c->inflight.empty()) reap(c, true);
+			c->cv.notify_all();
+			if (c->async_error) return c->async_error;
+		}
+		set_u64_kernel<<<1, 1, 0, c->compute_stream>>>(c->d_totals + 2, (unsigned long long)c->submitted_bases);
+		CU(c, cudaGetLastError());
+		c->launches++;
+		CU(c, cudaEventRecord(c->drained, c->compute_stream));
+		pc.counts[i] = c->d_counts;
+		pt.totals[i] = c->d_totals;
+		c->reduced = true;
+	}
+	CU(c0, cudaSetDevice(c0->device));
+	for (uint32_t i = 1; i < n_ctx; ++i) {
+		if (ctxs[i]->device != c0->device) {
+			int can = 0;
+			CU(c0, cudaDeviceCanAccessPeer(&can, c0->device, ctxs[i]->device));
+			if (!can) return fail(c0, NTSM_ERR_CUDA, "GPU %d cannot read GPU %d's memory (no peer access)", c0->device, ctxs[i]->device);
+			const cudaError_t pe = cudaDeviceEnablePeerAccess(ctxs[i]->device, 0);
+			if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return fail(c0, NTSM_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(pe));
+			cudaGetLastError();
+		}
+		CU(c0, cudaStreamWaitEvent(c0->compute_stream, ctxs[i]->drained, 0));
+	}
+	const uint32_t S = c0->n_sites;
+	cudaStream_t st = c0->compute_stream;
+	if (S) {
+		uint32_t *r = c0->d_rows;
+		// the k-mer-level sums replace ctx 0's private counts (ntsm_get_counts on ctx 0 then returns the combined array)
+		site_reduce_kernel<<<(S + 255) / 256, 256, 0, st>>>(pc, c0->d_allele_off, S, r, r + S, r + 2 * (size_t)S, r + 3 * (size_t)S, c0->d_counts);
+		CU(c0, cudaGetLastError());
+		c0->launches++;
+	}
+	sum_totals_kernel<<<1, 32, 0, st>>>(pt, c0->d_totals);
+	CU(c0, cudaGetLastError());
+	c0->launches++;
+	uint32_t *dst[4] = { max_ref, max_var, sum_ref, sum_var };
+	for (int i = 0; i < 4 && S; ++i)
+		if (dst[i]) CU(c0, cudaMemcpyAsync(dst[i], c0->d_rows + (size_t)i * S, (size_t)S * 4, cudaMemcpyDeviceToHost, st));
+	unsigned long long t[3] = { 0, 0, 0 };
+	CU(c0, cudaMemcpyAsync(t, c0->d_totals, sizeof t, cudaMemcpyDeviceToHost, st));
+	CU(c0, cudaStreamSynchronize(st));
+	if (totals) { totals[0] = t[0]; totals[1] = t[1]; totals[2] = t[2]; }
+	return NTSM_OK;
+}
+
 // ------------------------------------------------------------------ results
 extern "C" int ntsm_finalize(ntsm_ctx *c, uint32_t *max_ref, uint32_t *max_var, uint32_t *sum_ref, uint32_t *sum_var,
                              uint64_t totals[3])
@@ -822,15 +1148,20 @@ extern "C" int ntsm_finalize(ntsm_ctx *c, uint32_t *max_ref, uint32_t *max_var, 
 		std::unique_lock<std::mutex> g(c->mu);
 		while (!c->inflight.empty()) reap(c, true);
 		c->cv.notify_all();
+		if (c->async_error) return c->async_error;
 	}
 	rc = ntsm_reduce_async(c);
 	if (rc) return rc;
 	const uint32_t S = c->n_sites;
 	uint32_t *dst[4] = { max_ref, max_var, sum_ref, sum_var };
 	for (int i = 0; i < 4 && S; ++i)
-		if (dst[i]) CU(c, cudaMemcpyAsync(dst[i], c->d_rows + (size_t)i * S, (size_t)S * 4, cudaMemcpyDeviceToHost, c->compute_stream));
+		if (dst[i]) {
+			CU(c, cudaMemcpyAsync(dst[i], c->d_rows + (size_t)i * S, (size_t)S * 4, cudaMemcpyDeviceToHost, c->compute_stream));
+			c->d2h_bytes += (size_t)S * 4;
+		}
 	unsigned long long t[3] = { 0, 0, 0 };
 	CU(c, cudaMemcpyAsync(t, c->d_totals, sizeof t, cudaMemcpyDeviceToHost, c->compute_stream));
+	c->d2h_bytes += sizeof t;
 	CU(c, cudaStreamSynchronize(c->compute_stream));
 	if (totals) { totals[0] = t[0]; totals[1] = t[1]; totals[2] = t[2]; }
 	return NTSM_OK;
@@ -843,12 +1174,68 @@ extern "C" int ntsm_get_counts(ntsm_ctx *c, uint32_t *counts)
 	if (rc) return rc;
 	rc = ntsm_sync(c);
 	if (rc) return rc;
-	CU(c, cudaMemcpy(counts, c->d_counts, (size_t)c->n_kmers * 4, cudaMemcpyDeviceToHost));
+	CU(c, cudaMemcpyAsync(counts, c->d_counts, (size_t)c->n_kmers * 4, cudaMemcpyDeviceToHost, c->compute_stream));
+	CU(c, cudaStreamSynchronize(c->compute_stream));
+	return NTSM_OK;
+}
+
+// A shard's k-mer-level result joins this context's: counts[i] += add[i], tallies += totals.  This is the
+// exact merge: shards are summed per k-mer and the per-site max is taken afterwards by
+// ntsm_finalize, where `ntsmEval --merge` sums per-site maxima (src/CompareCounts.hpp:648-657).
+extern "C" int ntsm_add_counts(ntsm_ctx *c, const uint32_t *counts, const uint64_t totals[3])
+{
+	if (!c || !counts || !totals) return fail(c, NTSM_ERR_ARG, "ntsm_add_counts: null argument");
+	if (!c->d_table) return fail(c, NTSM_ERR_ARG, "no site table loaded");
+	if (c->reduced) return fail(c, NTSM_ERR_ARG, "counts were already combined; ntsm_reset_counts first");
+	int rc = ntsm_flush(c);
+	if (rc) return rc;
+	if ((rc = ntsm_sync(c))) return rc;
+	uint32_t *d_add = nullptr;
+	const uint32_t n = c->n_kmers;
+	if (n) {
+		CU(c, cudaMalloc(&d_add, (size_t)n * 4));
+		cudaError_t e = cudaMemcpyAsync(d_add, counts, (size_t)n * 4, cudaMemcpyHostToDevice, c->compute_stream);
+		if (e == cudaSuccess) {
+			add_counts_kernel<<<(n + 255) / 256, 256, 0, c->compute_stream>>>(c->d_counts, d_add, n);
+			e = cudaGetLastError();
+		}
+		if (e == cudaSuccess) e = cudaStreamSynchronize(c->compute_stream);
+		cudaFree(d_add);
+		if (e != cudaSuccess) return fail(c, NTSM_ERR_CUDA, "ntsm_add_counts: %s", cudaGetErrorString(e));
+		c->launches++;
+		c->h2d_bytes += (size_t)n * 4;
+	}
+	add_totals_kernel<<<1, 1, 0, c->compute_stream>>>(c->d_totals, (unsigned long long)totals[0], (unsigned long long)totals[1]);
+	CU(c, cudaGetLastError());
+	CU(c, cudaStreamSynchronize(c->compute_stream));
+	c->launches++;
+	std::lock_guard<std::mutex> g(c->mu);
+	c->done_kmers += totals[0];
+	c->done_hits += totals[1];
+	c->done_bases += totals[2];
+	c->submitted_bases += totals[2];
+	return NTSM_OK;
+}
+
+// the three tallies as they stand, without combining anything (ntsm_counts_save)
+extern "C" int ntsm_get_totals(ntsm_ctx *c, uint64_t totals[3])
+{
+	if (!c || !totals) return NTSM_ERR_ARG;
+	int rc = ntsm_flush(c);
+	if (rc) return rc;
+	if ((rc = ntsm_sync(c))) return rc;
+	unsigned long long t[3] = { 0, 0, 0 };
+	CU(c, cudaMemcpyAsync(t, c->d_totals, sizeof t, cudaMemcpyDeviceToHost, c->compute_stream));
+	CU(c, cudaStreamSynchronize(c->compute_stream));
+	totals[0] = t[0];
+	totals[1] = t[1];
+	totals[2] = c->reduced ? t[2] : c->submitted_bases;      // the base tally joins the device tallies when the result is combined
 	return NTSM_OK;
 }
 
 // library-internal helpers (not part of the public header)
 uint64_t ntsm_ctx_max_counts(const ntsm_ctx *c) { return c->cfg.max_counts; }
+uint64_t ntsm_ctx_reads(const ntsm_ctx *c) { return c->submitted_reads; }
 uint64_t ntsm_ctx_batch_bases(const ntsm_ctx *c) { return c->cfg.batch_bases; }
 void ntsm_set_thread_error(const char *text) { t_last_error = text; }
 
@@ -856,18 +1243,17 @@ extern "C" uint64_t ntsm_ctx_launches(const ntsm_ctx *c) { return c ? c->launche
 extern "C" const char *ntsm_ctx_kernel_name(const ntsm_ctx *c)
 {
 	if (!c) return "";
-	if (c->cfg.k != 19 || c->kernel_variant == 0) return c->cfg.k == 19 ? "count_kernel<19>" : "count_kernel<0>";
-	if (c->kernel_variant == 1) return "count_kernel_min<19,13>";
-	if (c->kernel_variant == 2) return "count_kernel_gate<19>";
-	if (c->kernel_variant == 5) {
-		static const char *names[4] = { "count_kernel_pair<19,1024,1>", "count_kernel_pair<19,1024,2>", "count_kernel_pair<19,512,4>", "count_kernel_pair<19,256,8>" };
-		return names[c->seed_cfg];
-	}
-	if (c->kernel_variant == 4) {
-		static const char *names[4] = { "count_kernel_seed<19,14,1024,1>", "count_kernel_seed<19,14,1024,2>", "count_kernel_seed<19,14,512,4>", "count_kernel_seed<19,14,256,8>" };
-		return names[c->seed_cfg];
-	}
-	return c->gate_m == 13 ? "count_kernel_gate2<19,13,1>" : c->pool_tail ? "count_kernel_gate2<19,14,1>" : "count_kernel_gate2<19,14,0>";
+	if (c->kernel == 0) return "count_kernel_generic";
+	if (c->cfg.k != 19) return "count_kernel_pair<0,1024,2>";
+	static const char *names[4] = { "count_kernel_pair<19,1024,1>", "count_kernel_pair<19,1024,2>", "count_kernel_pair<19,512,4>", "count_kernel_pair<19,256,8>" };
+	return names[c->opt_shape];
 }
+extern "C" void ntsm_ctx_pcie_bytes(const ntsm_ctx *c, uint64_t *h2d, uint64_t *d2h)
+{
+	if (h2d) *h2d = c ? c->h2d_bytes : 0;
+	if (d2h) *d2h = c ? c->d2h_bytes : 0;
+}
+extern "C" int ntsm_ctx_l2_window(const ntsm_ctx *c) { return c && c->l2_window ? (int)(c->l2_hit_ratio * 100.0f + 0.5f) : 0; }
+extern "C" uint64_t ntsm_ctx_probe_bytes(const ntsm_ctx *c) { return c ? c->probe_bytes : 0; }
 extern "C" uint32_t ntsm_ctx_filter_bits(const ntsm_ctx *c) { return c ? c->filter_bits : 0; }
 extern "C" uint32_t ntsm_ctx_table_capacity(const ntsm_ctx *c) { return c ? c->table_cap : 0; }

@@ -56,8 +56,13 @@ private:
 
 	GzSource src_;
 	bool open_ = false;
-	std::vector<unsigned char> buf_;
+	std::vector<unsigned char> own_;   // the 1 MiB window when the source has to be read()
+	unsigned char *buf_ = nullptr;     // window base: own_.data(), or the source's own mapping (read-only then: nothing writes to it)
+	size_t cap_ = 0;                   // window capacity
 	size_t beg_ = 0, end_ = 0;
+	bool mapped_ = false;              // the window IS the whole input (GzSource "mapped")
+	size_t populated_ = 0;             // mapped: page tables are set up for [0, populated_)
+	void populate_ahead();
 	bool eof_ = false, err_ = false, src_err_ = false;
 	int last_ = 0;                     // header byte already consumed by the previous record
 	std::string name_;

@@ -5,8 +5,10 @@
 // trailing garbage after a member is ignored, an error ends the file.  For gzip'd FASTQ that call
 // is the whole cost of ingest (cfg 4 of BASELINE.json), so GzSource
 // produces the same bytes three ways:
-//   zlib      gzread itself: anything that is not a regular gzip file, and the continuation of any
-//             file the other two modes gave up on;
+//   zlib      gzread itself: pipes and other non-regular files, and the continuation of any
+//             file the other modes gave up on;
+//   mapped    a regular file that is not gzip at all (gzread's transparent mode): memory-mapped, the
+//             reader scans the page cache's pages in place -- no read() copy;
 //   fast      the file memory-mapped and decoded by ntsm::Inflater (inflate.h), CRC-32 and ISIZE
 //             of every member checked before its last bytes are handed out;
 //             With helper threads, a large single member is cut into chunks that workers inflate
@@ -46,7 +48,10 @@ public:
 	// gzread's contract: the number of bytes delivered, short only at the end of the input;
 	// 0 at the end; -1 on a read/format error (after the bytes that preceded it were delivered)
 	int read(void *dst, unsigned n);
-	const char *mode() const;          // "zlib" | "fast" | "bgzf" -- what is producing bytes right now
+	const char *mode() const;          // "zlib" | "fast" | "bgzf" | "mapped" -- what is producing bytes right now
+	// "mapped": a plain (not gzip) regular file, memory-mapped; the whole input is [*base, *base + *size) and
+	// a reader may scan it in place instead of calling read()
+	bool mapped(const uint8_t **base, size_t *size) const;
 	bool fell_back() const;            // a fast mode handed the file over to zlib
 	bool bad() const;                  // a data error was met (read() returns -1 once the bytes before it are out)
 	uint64_t parallel_chunks() const;  // chunks of single members that worker threads inflated and the stitcher accepted

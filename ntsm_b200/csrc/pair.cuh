@@ -1,36 +1,36 @@
-// pair.cuh -- paired-seed count kernel (sm_100a): the production path for k = 19.
+// pair.cuh -- paired-seed count kernel (sm_100a): the production path for 17 <= k <= 31.
 //
-// The strided-seed kernel (seed.cuh) probes one 14-mer per W = 6 positions and runs at the chip's
-// random-request rate into L2: ncu has l1tex__m_l1tex2xbar_req_cycles_active at 97 % with the ALU
-// pipe at 48 % (profiles/r01v7_*), and the microbenchmark (tools/microbench.cu, profiles/
-// r01v8_microbench.txt) shows that wall is one 128-byte LINE request per clock per SM, however few
-// of the line's bytes are wanted -- and that thread-block-cluster DSMEM probes are slower still.
-// The only way left to go faster is to ask fewer questions per position.
+// One probe per position into an L2-resident bitmap runs at the chip's random-request rate: ncu has
+// l1tex__m_l1tex2xbar_req_cycles_active at 97 % (profiles/r01_*, r01v7_*), and the microbenchmark
+// (tools/microbench.cu, profiles/r01v8_microbench.txt) shows that wall is one 128-byte LINE request
+// per clock per SM, however few of the line's bytes are wanted -- and that thread-block-cluster
+// DSMEM probes are slower still.  The only way to go faster is to ask fewer questions per position.
 //
-// Two seeds that start D = 2 positions apart share M - D = 12 bases.  Index a table by those 12
-// shared bases (4^12 words of 32 bits = 64 MiB, L2 resident) and let the word answer for BOTH
-// seeds: bits 0-15 say "the 14-mer made of <2 bases b0 b1> + <the 12 shared bases> is a site
-// seed" (role A, bit = b0 | b1 << 2), bits 16-31 say "<the 12 shared bases> + <2 bases b14 b15> is
-// a site seed" (role B, bit = 16 + (b14 | b15 << 2)).  Every 14-mer of every site k-mer (both read
-// orientations) is entered twice, once per role.  One 32-bit load then covers the windows of two
-// seeds: A (at stream position p) closes the windows starting in [p-5, p], B (at p+2) closes
-// [p-3, p+2] -- 8 windows, so the kernel probes one PAIR per 8 positions: 4 loads per 32-position
-// chunk instead of 5.33, pairs always at local positions 0, 8, 16, 24 (no phase arithmetic).  The
-// four windows that contain both seeds need both bits, which also makes the level-1 filter ~2x
-// more selective (fewer level-2 requests).  Windows that pass (~1 %) go on to the k-mer bitmap
-// (level 2) and the exact path (reference hash64 + table + atomicAdd), shared with gate2.cuh, which
-// is what produces the reference's counts (src/FingerPrint.hpp:89-103,
-// vendor/KseqHashIterator.hpp:87-139).
+// Seeds are M-mers with M = min(14, k - 5), so that a window of k bases contains at least 6 of them.
+// Two seeds that start D = 2 positions apart share M - 2 bases.  Index a table by those shared bases
+// (M = 14: 4^12 words of 32 bits = 64 MiB) and let the word answer for BOTH seeds: bits 0-15 say
+// "the M-mer made of <2 bases b0 b1> + <the shared bases> is a site seed" (role A, bit = b0 | b1 << 2),
+// bits 16-31 say "<the shared bases> + <2 bases> is a site seed" (role B).  Every M-mer of every site
+// k-mer (both read orientations) is entered twice, once per role.  One 32-bit load then covers the
+// windows of two seeds: A (at stream position p) closes the windows starting in [p-5, p], B (at p+2)
+// closes [p-3, p+2] -- 8 windows, so the kernel probes one PAIR per 8 positions: 4 loads per
+// 32-position chunk, pairs always at local positions 0, 8, 16, 24 (no phase arithmetic).  (For k > 19
+// a seed closes more windows than that; the geometry stays the k = 19 one, which is all a pair needs
+// to cover its 8.)  The four windows that contain both seeds need both bits, which also makes the
+// level-1 filter ~2x more selective.  Windows that pass (~2 %) go on to the k-mer bitmap (level 2)
+// and the exact path (reference hash64 + table + atomicAdd), which is what produces the reference's
+// counts (src/FingerPrint.hpp:89-103, vendor/KseqHashIterator.hpp:87-139).
 #pragma once
-#include "gate2.cuh"
+#include "kernels.cuh"
 
 namespace ntsm {
 
-constexpr int kPairM = 14;                                  // seed length
-constexpr int kPairD = 2;                                   // distance between the two seeds of a pair
-constexpr size_t kPairWords = (size_t)1 << (2 * (kPairM - kPairD));   // 4^12 words
+constexpr int kPairMaxM = 14;                               // seed length for k >= 19
+constexpr int kPairMinK = 17;                               // below that the k-mer bitmap is cut differently (2k <= 32): generic kernel
+NTSM_HD int pair_seed_len(int k) { return k - 5 < kPairMaxM ? k - 5 : kPairMaxM; }
+NTSM_HD size_t pair_words(int m) { return (size_t)1 << (2 * (m - 2)); }      // one 32-bit word per (M-2)-base core: M = 14 -> 4^12 words
 
-constexpr int kPairFoldDefault = 1;                         // table folded 2:1 by default (32 MiB), see below
+constexpr int kPairFoldDefault = 1;                         // table folded 2:1 by default (M = 14: 32 MiB), see below
 constexpr int kPairFoldMax = 4;
 
 // The full table is 64 MiB, and with the 16 MiB k-mer bitmap next to it that is more than ONE of the
@@ -39,22 +39,16 @@ constexpr int kPairFoldMax = 4;
 // `fold` bits of the word index (the high bit(s) of the last shared base: two cores that differ only
 // there share a word, their role bits ORed) -- half the footprint per fold bit for twice the
 // level-1 false-positive rate, at no instruction cost (the mask is a register either way).
-NTSM_HD uint32_t pair_word_mask(int fold) { return (uint32_t)(kPairWords >> fold) - 1u; }
-
-// the two table entries of stream-order 14-mer v (28 bits, first base in the low bits)
-NTSM_HD void pair_slots(uint32_t v, uint32_t word_mask, uint32_t &word_a, uint32_t &bit_a, uint32_t &word_b, uint32_t &bit_b)
-{
-	word_a = (v >> 4) & word_mask;      // role A: v's last 12 bases are the shared ones
-	bit_a = v & 15;
-	word_b = v & 0xFFFFFFu & word_mask; // role B: v's first 12 bases are the shared ones
-	bit_b = 16 + (v >> 24);
-}
+NTSM_HD uint32_t pair_word_mask(int m, int fold) { return (uint32_t)(pair_words(m) >> fold) - 1u; }
 
 // One pair probe.  x = the 16 bases starting at the pair's position (32 bits, stream order).  Returns,
 // for the 8 windows the pair closes (bit t <-> window p - 5 + t), which of them may still be a site
 // k-mer; 0 without issuing the load when need == 0.  The address is {base_lo + 4 * key, base_hi}: the
-// table never crosses a 4 GiB line (checked at load).
-__device__ __forceinline__ uint32_t pair_probe(uint32_t x, uint32_t need, uint32_t base_lo, uint32_t base_hi, uint32_t off_mask)
+// table never crosses a 4 GiB line (checked at load).  BSHIFT = 2 * M when M is a compile-time 14
+// (role B's bases are the top four bits of x, no mask needed), else taken from bshift at run time.
+template <int BSHIFT>
+__device__ __forceinline__ uint32_t pair_probe(uint32_t x, uint32_t need, uint32_t base_lo, uint32_t base_hi, uint32_t off_mask,
+                                               uint32_t bshift)
 {
 	uint32_t w;
 	asm("{\n\t"
@@ -72,13 +66,64 @@ __device__ __forceinline__ uint32_t pair_probe(uint32_t x, uint32_t need, uint32
 	    : "=r"(w)
 	    : "r"(x), "r"(need), "r"(base_lo), "r"(base_hi), "r"(off_mask));
 	const uint32_t a = 0u - ((w >> (x & 15u)) & 1u);               // all-ones if seed A is marked
-	const uint32_t b = 0u - ((w >> ((x >> 28) + 16u)) & 1u);       // all-ones if seed B is marked
+	const uint32_t bsel = BSHIFT == 28 ? (x >> 28) : ((x >> bshift) & 15u);
+	const uint32_t b = 0u - ((w >> (bsel + 16u)) & 1u);            // all-ones if seed B is marked
 	return (a | 0xC0u) & (b | 0x03u) & 0xFFu;                      // A closes t in [0,6), B closes t in [2,8)
 }
 
-// Work layout as in count_kernel_gate2 / count_kernel_seed: a warp takes groups of 31 chunks (lanes
-// 0-30; lane 31 holds the next chunk as halo), groups dealt round-robin over all warps of the grid,
-// each lane's words loaded one iteration ahead.
+constexpr int kCandSlots = 32;      // candidates one warp hands round per pass of its tail
+constexpr uint32_t kGroupChunks = 31;
+
+// Tail (level 2 + exact path).  About 2 % of positions pass level 1, in runs of 3-4 inside few lanes; a
+// per-lane loop walks them with ~2 lanes active and one L2 round trip per step (ncu, round 1: 36 %
+// of the long-scoreboard stalls on that one load).  The warp pools its candidates instead: an
+// inclusive scan gives every lane its slots, the owners write (lane, position) into 32 shared-memory
+// slots, and lane j takes candidate j -- fetching the owner's four words by shuffle -- so all level-2
+// probes of a group are in flight together.
+__device__ __forceinline__ void pooled_tail(const CountParams &P, const uint32_t (&w)[4], uint32_t pass, uint32_t lane,
+                                            uint16_t *cand, uint32_t wshift, uint32_t k, uint32_t &hits)
+{
+	const uint32_t cnt = __popc(pass);
+	uint32_t incl = cnt;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= (uint32_t)d) incl += t;
+	}
+	const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+	uint32_t idx = incl - cnt;                                // slot of this lane's next candidate
+	for (uint32_t r0 = 0; r0 < total; r0 += kCandSlots) {     // warp-uniform trip count, 1 almost always
+		while (pass && idx < r0 + kCandSlots) {
+			uint32_t i;
+			asm("bfind.u32 %0, %1;" : "=r"(i) : "r"(pass));  // highest set bit (one FLO)
+			pass ^= 1u << i;
+			cand[idx - r0] = (uint16_t)((lane << 5) | i);
+			++idx;
+		}
+		__syncwarp();
+		const bool mine = r0 + lane < total;
+		const uint32_t e = mine ? cand[lane] : (lane << 5);
+		const uint32_t src = e >> 5, i = e & 31;
+		const uint32_t y0 = __shfl_sync(0xffffffffu, w[0], src), y1 = __shfl_sync(0xffffffffu, w[1], src);
+		const uint32_t y2 = __shfl_sync(0xffffffffu, w[2], src), y3 = __shfl_sync(0xffffffffu, w[3], src);
+		if (mine) {
+			const bool up = i >= 16;
+			const uint32_t x0 = up ? y1 : y0, x1 = up ? y2 : y1, x2 = up ? y3 : y2;
+			const uint32_t lo = __funnelshift_r(x0, x1, 2 * i), hi = __funnelshift_r(x1, x2, 2 * i);
+			const uint32_t mix = lo * kMixA + hi * (kMixB << (64 - 2 * k));      // filter_mix for 2k > 32, unmasked words
+			if (filter_test(__ldg(P.filter + (mix >> wshift)), mix)) hits += resolve_one(P, lo, hi, k);
+		}
+		__syncwarp();
+	}
+}
+
+// Work layout.  A group is 31 chunks (992 positions) handled by lanes 0-30; lane 31 holds the chunk
+// after them, which is only the halo of lane 30 (a window reaches k-1 <= 30 positions past its
+// start).  That costs one idle lane (no extra issue slots) and buys a loop with no dependence
+// between a group and the next one's data, so every lane loads its words a whole iteration before
+// they are used.  Groups are dealt round-robin over all warps of the grid: at any moment the whole
+// grid reads one narrow band of the stream (contiguous per-warp runs were 15 % slower -- thousands of
+// separate streams cost TLB reach and DRAM page locality).
 //
 // Pair q of a chunk sits at local position 8 q and closes the windows starting at local positions
 // [8q - 5, 8q + 3): in "pair coordinates" t = i + 5 that is t in [8q, 8q + 8).  The five windows
@@ -86,15 +131,19 @@ __device__ __forceinline__ uint32_t pair_probe(uint32_t x, uint32_t need, uint32
 // whether pair 0 is needed at all); this lane's last five windows are closed by the next lane's
 // pair 0, whose answer comes over by shuffle.  Lane 31 therefore probes its pair 0 for lane 30, and
 // lane 0 of the warp that owns that chunk probes it again for its own windows 0-2.
+//
+// K = 19 is the compile-time instantiation of the reference's default; K = 0 takes 17 <= k <= 31 from
+// P.k at run time (seed length through P.pair_bshift / P.pair_off_mask), same code.
 template <int K, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) count_kernel_pair(const CountParams P)
 {
-	static_assert(K - kPairM + 1 == 6, "pair geometry (8 windows per pair, masks 0x3F / 0xFC) is written out for K - M = 5, D = 2");
-	static_assert(2 * K > 32 && K <= 31, "level 2 cuts the k-mer as one full word plus 2K-32 bits");
+	static_assert(K == 0 || (K >= 19 && K <= 31), "compile-time K uses the M = 14 probe");
 	__shared__ uint16_t s_cand[THREADS / 32][kCandSlots];
-	const uint32_t base_lo = (uint32_t)(uintptr_t)P.minimizer2, base_hi = (uint32_t)((uintptr_t)P.minimizer2 >> 32);
+	const uint32_t k = K ? (uint32_t)K : P.k;
+	const uint32_t base_lo = (uint32_t)(uintptr_t)P.pair, base_hi = (uint32_t)((uintptr_t)P.pair >> 32);
 	const uint32_t wshift = P.filter_shift + 5;
-	const uint32_t off_mask = P.pair_word_mask << 2;
+	const uint32_t off_mask = P.pair_off_mask, bshift = P.pair_bshift;
+	constexpr int BS = K ? 28 : 0;
 	const uint32_t lane = threadIdx.x & 31;
 	uint16_t *cand = s_cand[threadIdx.x >> 5];
 	uint32_t tk = 0, hits = 0;
@@ -128,7 +177,7 @@ __global__ void __launch_bounds__(THREADS, MINB) count_kernel_pair(const CountPa
 		const uint32_t m1 = __shfl_down_sync(0xffffffffu, m0, 1);
 		if (lane == 31 || c >= P.n_chunks) m0 = 0xFFFFFFFFu;    // lane 31 is halo only; nothing starts in the padding
 		const uint32_t w[4] = { own.x, own.y, nxt.x, nxt.y };
-		const uint32_t valid = valid_windows(m0, m1, K);
+		const uint32_t valid = valid_windows(m0, m1, k);
 		tk += __popc(valid);
 
 		// valid windows in pair coordinates, the previous lane's last five included
@@ -136,15 +185,15 @@ __global__ void __launch_bounds__(THREADS, MINB) count_kernel_pair(const CountPa
 		if (lane == 0) pv = 0;                                    // closed by lane 31 of the warp that owns that chunk
 		const uint32_t n5 = __funnelshift_l(pv, valid, 5);        // bit i + 5 <-> window i, i = -5 .. 26
 
-		const uint32_t r0 = pair_probe(own.x, n5 & 0xFFu, base_lo, base_hi, off_mask);
-		const uint32_t r1 = pair_probe(__funnelshift_r(own.x, own.y, 16), n5 & 0xFF00u, base_lo, base_hi, off_mask);
-		const uint32_t r2 = pair_probe(own.y, n5 & 0xFF0000u, base_lo, base_hi, off_mask);
-		const uint32_t r3 = pair_probe(__funnelshift_r(own.y, nxt.x, 16), n5 & 0xFF000000u, base_lo, base_hi, off_mask);
+		const uint32_t r0 = pair_probe<BS>(own.x, n5 & 0xFFu, base_lo, base_hi, off_mask, bshift);
+		const uint32_t r1 = pair_probe<BS>(__funnelshift_r(own.x, own.y, 16), n5 & 0xFF00u, base_lo, base_hi, off_mask, bshift);
+		const uint32_t r2 = pair_probe<BS>(own.y, n5 & 0xFF0000u, base_lo, base_hi, off_mask, bshift);
+		const uint32_t r3 = pair_probe<BS>(__funnelshift_r(own.y, nxt.x, 16), n5 & 0xFF000000u, base_lo, base_hi, off_mask, bshift);
 		const uint32_t nb = __shfl_down_sync(0xffffffffu, r0, 1);   // the next chunk's pair 0 closes windows 27-31
 		const uint32_t plo = r0 | (r1 << 8) | (r2 << 16) | (r3 << 24);
 		const uint32_t pass = __funnelshift_r(plo, nb, 5) & valid;
 
-		pooled_tail<K>(P, w, pass, lane, cand, wshift, hits);
+		pooled_tail(P, w, pass, lane, cand, wshift, k, hits);
 	}
 	flush_tallies(tk, hits, P.totals);
 }

@@ -1,6 +1,7 @@
 // sites.cpp -- host side of FingerPrint::initCountsHash (src/FingerPrint.hpp:490-564), laid out
 // the way MultiCount keeps it (src/MultiCount.hpp:208-209,247,268): every listed k-mer gets a
 // dense index in file order and the per-site lists become CSR offsets into one flat array.
+#include <sched.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -130,7 +131,14 @@ extern "C" int ntsm_sites_load(ntsm_sites **out, const char *path, uint32_t k, i
 	const uint64_t n_rec = seq_off.size() - 1;
 	s->n_records = (uint32_t)n_rec;
 
-	unsigned n_threads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+	// the cores this process may actually use (a cgroup / taskset can leave far fewer than the machine has)
+	unsigned avail = std::max(1u, std::thread::hardware_concurrency());
+	{
+		cpu_set_t set;
+		CPU_ZERO(&set);
+		if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) avail = std::min<unsigned>(avail, (unsigned)CPU_COUNT(&set));
+	}
+	unsigned n_threads = std::min(16u, avail);
 	if (seqs.size() < (1u << 20)) n_threads = 1;           // small panels: not worth starting threads
 	if (const char *e = getenv("NTSM_SITES_THREADS")) n_threads = (unsigned)std::min(256, std::max(1, atoi(e)));
 

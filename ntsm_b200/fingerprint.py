@@ -88,7 +88,9 @@ def pack_reads(reads):
 class FingerPrint:
     """One GPU context with a loaded site table (the FingerPrint object of the reference)."""
 
-    def __init__(self, sites, k=19, dupes=False, cov_thresh=0.0, device=0, batch_bases=0, n_buffers=0):
+    def __init__(self, sites, k=19, dupes=False, cov_thresh=0.0, device=0, batch_bases=0, n_buffers=0, options=None):
+        """options: {name: int} for ntsm_ctx_set_option (measurement / test knobs: "kernel", "pair_fold",
+        "filter_bits", "launch_shape", "l2_persist", "device_pack"); every setting gives the same counts."""
         L = _lib.lib()
         self.sites = sites if isinstance(sites, SiteSet) else SiteSet(sites, k, dupes)
         self.k = self.sites.k
@@ -97,6 +99,9 @@ class FingerPrint:
         self.max_counts = cfg.max_counts
         self._ctx = C.c_void_p()
         check(L.ntsm_ctx_create(C.byref(self._ctx), C.byref(cfg)))
+        self.options = dict(options or {})
+        for name, value in self.options.items():
+            check(L.ntsm_ctx_set_option(self._ctx, name.encode(), int(value)), self._ctx)
         check(L.ntsm_load_siteset(self._ctx, self.sites._h), self._ctx)
         self.early_term = False
         self._rows = None
@@ -172,7 +177,25 @@ class FingerPrint:
         check(_lib.lib().ntsm_poll_totals(self._ctx, C.byref(a), C.byref(b), C.byref(c), C.byref(d)), self._ctx)
         return a.value, b.value, c.value, bool(d.value)
 
+    def set_option(self, name, value):
+        check(_lib.lib().ntsm_ctx_set_option(self._ctx, name.encode(), int(value)), self._ctx)
+
     # -- multi GPU --------------------------------------------------------------------
+    @staticmethod
+    def group_finalize(fps):
+        """Several FingerPrints of this process (one per GPU) combined without NCCL: fps[0]'s GPU sums the
+        others' counts out of peer memory inside the per-site reduce kernel (ntsm_group_finalize).
+        Returns the rows like finalize(); they are also what fps[0].counts_text() then prints."""
+        f0 = fps[0]
+        S = f0.sites.n_sites
+        a = [np.zeros(max(S, 1), np.uint32) for _ in range(4)]
+        t = np.zeros(3, np.uint64)
+        ctxs = (C.c_void_p * len(fps))(*[f._ctx for f in fps])
+        check(_lib.lib().ntsm_group_finalize(ctxs, len(fps), a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, a[3].ctypes.data,
+                                             t.ctypes.data), f0._ctx)
+        f0._rows = [x[:S] for x in a] + [t]
+        return f0._rows
+
     @staticmethod
     def nccl_unique_id():
         buf = C.create_string_buffer(128)
@@ -237,3 +260,19 @@ class FingerPrint:
     @property
     def filter_bits(self):
         return _lib.lib().ntsm_ctx_filter_bits(self._ctx)
+
+    @property
+    def pcie_bytes(self):
+        """(host->device, device->host) bytes this context's data path has copied so far."""
+        a, b = C.c_uint64(), C.c_uint64()
+        _lib.lib().ntsm_ctx_pcie_bytes(self._ctx, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    @property
+    def l2_window(self):
+        """0 = launches carry no L2 access-policy window, else the window's hit ratio in percent."""
+        return _lib.lib().ntsm_ctx_l2_window(self._ctx)
+
+    @property
+    def probe_bytes(self):
+        return _lib.lib().ntsm_ctx_probe_bytes(self._ctx)

@@ -172,3 +172,47 @@ def codes_to_reads(codes):
     c = codes.cpu().numpy() if isinstance(codes, torch.Tensor) else codes
     seq = ASCII[c]
     return [seq[i].tobytes() for i in range(c.shape[0])]
+
+
+def fastq_records(codes, first_index=0):
+    """codes uint8 [n, L] on any device -> FASTQ records as a uint8 tensor [n, 2L + 15] on the same
+    device: "@r<8 digits>\\n<seq>\\n+\\n<L x 'I'>\\n" (the layout bench.py's write_fastq_files makes with numpy)."""
+    n, L = codes.shape
+    dev = codes.device
+    rec = torch.empty((n, 2 * L + 15), dtype=torch.uint8, device=dev)
+    rec[:, 0] = ord("@")
+    rec[:, 1] = ord("r")
+    idx = torch.arange(first_index, first_index + n, device=dev, dtype=torch.int64)
+    for d in range(8):
+        rec[:, 2 + d] = ((idx // 10 ** (7 - d)) % 10 + 48).to(torch.uint8)
+    rec[:, 10] = 10
+    lut = torch.tensor(list(b"ACGTN"), dtype=torch.uint8, device=dev)
+    rec[:, 11:11 + L] = lut[codes.long()]
+    rec[:, 11 + L] = 10
+    rec[:, 12 + L] = ord("+")
+    rec[:, 13 + L] = 10
+    rec[:, 14 + L:14 + 2 * L] = ord("I")
+    rec[:, 14 + 2 * L] = 10
+    return rec
+
+
+def write_fastq_set(genome, n_reads, read_len, err, seed, n_files, outdir, prefix="part", chunk_reads=1 << 20):
+    """n_reads reads of the bench generator as n_files plain FASTQ files (records built on the device,
+    written chunk by chunk).  -> list of paths."""
+    os.makedirs(outdir, exist_ok=True)
+    per = (n_reads + n_files - 1) // n_files
+    paths = []
+    ci = 0
+    for fi in range(n_files):
+        p = os.path.join(outdir, "%s_%03d.fq" % (prefix, fi))
+        left = min(per, n_reads - fi * per)
+        with open(p, "wb") as fh:
+            done = 0
+            while done < left:
+                c = min(chunk_reads, left - done)
+                codes = sample_reads(genome, c, read_len, err, seed * 1000003 + ci)
+                fastq_records(codes, first_index=(fi * per + done) % 100_000_000).cpu().numpy().tofile(fh)
+                done += c
+                ci += 1
+        paths.append(p)
+    return paths

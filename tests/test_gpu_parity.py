@@ -114,14 +114,48 @@ def test_insert_count_vs_oracle_k19(oracle):
     assert ofp.total_counts > 3000
 
 
-@pytest.mark.parametrize("k", [1, 2, 5, 11, 15, 16, 17, 25, 31])
+@pytest.mark.parametrize("k", [1, 2, 5, 11, 15, 16, 17, 18, 20, 21, 22, 24, 25, 27, 29, 30, 31])
 def test_other_k_vs_oracle(oracle, k):
+    """Every -k the reference takes (vendor/KseqHashIterator.hpp:28-33): k < 17 runs the generic kernel,
+    17..31 the paired-seed kernel with k at run time (seed length min(14, k-5)); both against the oracle's
+    per-k-mer counters, with and without the pair kernel for the k it applies to."""
     name = "k%d" % k if os.path.isdir(os.path.join(GOLDEN, "cases", "k%d" % k)) else "k11"
     sites = os.path.join(GOLDEN, "cases", name, "sites.fa")
     rng = random.Random(k)
     wins = [w for w in _windows(sites)]
     reads = _reads(rng, wins, 800, "ACGTN", maxflank=40)
+    fp = ntsm_b200.FingerPrint(sites, k=k, dupes=True)
+    assert fp.kernel_name == ("count_kernel_generic" if k < 17 else "count_kernel_pair<0,1024,2>")
+    fp.close()
     _check_against_oracle(oracle, sites, reads, k=k, dupes=True)
+    if k >= 17:
+        _check_against_oracle(oracle, sites, reads, k=k, dupes=True, options={"kernel": 0})
+
+
+@pytest.mark.parametrize("k", [17, 18, 21, 25, 28, 31])
+def test_pair_kernel_other_k_on_a_large_panel(oracle, tmp_path, k):
+    """A 30 000-site synthetic panel k-merized AT k (k - 6 k-mers per allele, like the human panel at 19),
+    dense-hit reads made of its windows, N runs, both strands, odd batch sizes: count_kernel_pair<0> with
+    k at run time against the oracle's per-k-mer counters."""
+    from ntsm_b200 import synth_np
+    sites = str(tmp_path / "sites.fa")
+    win, n = synth_np.synthetic_panel(sites, 30000, 100 + k, k=k, flank=k - 4)
+    assert n > 29000
+    wins = ["".join("ACGT"[c] for c in win[i, a]) for i in range(0, 3000) for a in (0, 1)]
+    rng = random.Random(500 + k)
+    reads = []
+    for j in range(1500):
+        r = "".join(rng.choice(wins) for _ in range(rng.randrange(1, 6)))
+        if j % 3 == 0:
+            p = rng.randrange(len(r)); r = r[:p] + "N" * rng.randrange(1, 5) + r[p:]
+        if j % 4 == 0:
+            r = r[rng.randrange(0, 7):]
+        r = r.encode()
+        reads.append(revcomp(r) if rng.random() < 0.5 else r)
+    reads += [bytes(rng.choice(b"ACGT") for _ in range(rng.randrange(0, 300))) for _ in range(500)]
+    for bb in (40001, 1 << 18):
+        ofp = _check_against_oracle(oracle, sites, reads, k=k, batch_bases=bb)
+    assert ofp.total_counts > 5 * len(reads)
 
 
 def test_alphabet_and_edge_reads_vs_oracle(oracle):
@@ -391,24 +425,22 @@ def test_cfg3_ont_like_long_reads_vs_oracle(oracle):
 
 
 # ---------------------------------------------------------------- kernel variants
-@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4", "5"])
-def test_every_k19_kernel_variant_vs_oracle(oracle, monkeypatch, variant):
-    """NTSM_KERNEL picks the k = 19 count kernel (0 plain, 1 minimizer, 2 gated, 3 gate2, 4 strided
-    seeds, 5 paired seeds = default): each must give the oracle's per-k-mer counters on the same reads."""
-    monkeypatch.setenv("NTSM_KERNEL", variant)
-    rng = random.Random(1900 + int(variant))
+@pytest.mark.parametrize("opts", [{"kernel": 0}, {"kernel": 1}, {"kernel": 1, "launch_shape": 0}, {"kernel": 1, "launch_shape": 2},
+                                  {"kernel": 1, "launch_shape": 3}, {"kernel": 1, "l2_persist": 0}, {"kernel": 1, "filter_bits": 20}])
+def test_every_k19_kernel_variant_vs_oracle(oracle, opts):
+    """ntsm_ctx_set_option picks the count kernel (generic / paired seeds), its launch shape, the L2
+    access-policy window and the k-mer bitmap size: each must give the oracle's per-k-mer counters."""
+    rng = random.Random(1900 + sum(opts.values()))
     wins = _windows(PANEL, limit=8000)
     reads = _reads(rng, wins, 6000, "ACGTN") + [bytes(rng.choice(b"ACGT") for _ in range(rng.randrange(0, 400))) for _ in range(2000)]
-    _check_against_oracle(oracle, PANEL, reads, batch_bases=1 << 18)
+    _check_against_oracle(oracle, PANEL, reads, batch_bases=1 << 18, options=opts)
 
 
-@pytest.mark.parametrize("variant", ["4", "5"])
-def test_seed_kernel_dense_hits_and_every_phase(oracle, monkeypatch, variant):
-    """Stress for count_kernel_seed (seed.cuh) and count_kernel_pair (pair.cuh): reads that are nothing but site windows back to back
+def test_pair_kernel_dense_hits_and_every_phase(oracle):
+    """Stress for count_kernel_pair (pair.cuh): reads that are nothing but site windows back to back
     (nearly every seed marked, so the pooled tail runs several rounds per warp), read lengths that
     walk the read starts through every chunk phase and lane, N runs right before and after the
     seed positions, and batches of odd sizes so the last group is ragged."""
-    monkeypatch.setenv("NTSM_KERNEL", variant)
     rng = random.Random(77)
     wins = _windows(PANEL, limit=6000)
     reads = []
@@ -428,16 +460,126 @@ def test_seed_kernel_dense_hits_and_every_phase(oracle, monkeypatch, variant):
     assert ofp.total_counts > 3 * len(reads)
 
 
-@pytest.mark.parametrize("fold", ["0", "1", "2", "4"])
-def test_pair_table_fold_vs_oracle(oracle, monkeypatch, fold):
-    """NTSM_PAIR_FOLD folds the paired-seed table 2^fold : 1 (pair.cuh): a smaller level-1 table only
-    lets more windows through to the exact path, so the counters must not change."""
-    monkeypatch.setenv("NTSM_KERNEL", "5")
-    monkeypatch.setenv("NTSM_PAIR_FOLD", fold)
-    rng = random.Random(2100 + int(fold))
+@pytest.mark.parametrize("fold", [0, 1, 2, 4])
+def test_pair_table_fold_vs_oracle(oracle, fold):
+    """The paired-seed table folded 2^fold : 1 (pair.cuh): a smaller level-1 table only lets more
+    windows through to the exact path, so the counters must not change."""
+    rng = random.Random(2100 + fold)
     wins = _windows(PANEL, limit=8000)
     reads = _reads(rng, wins, 5000, "ACGTN") + [bytes(rng.choice(b"ACGT") for _ in range(rng.randrange(0, 400))) for _ in range(1500)]
-    _check_against_oracle(oracle, PANEL, reads, batch_bases=1 << 18)
+    _check_against_oracle(oracle, PANEL, reads, batch_bases=1 << 18, options={"kernel": 1, "pair_fold": fold})
+
+
+# ---------------------------------------------------------------- reads packed on the device
+def _pinned_bytes(data: bytes):
+    import torch
+    t = torch.empty(max(1, len(data)), dtype=torch.uint8).pin_memory()
+    t[:len(data)] = torch.frombuffer(bytearray(data), dtype=torch.uint8) if data else t[:0]
+    return t
+
+
+@pytest.mark.parametrize("threads", [0, 2])
+def test_device_packed_reads_vs_oracle(oracle, threads):
+    """ntsm_insert_reads / ntsm_insert_reads_fixed from PAGE-LOCKED memory: a feeder thread DMAs the ASCII
+    bytes as they are and pack_ascii_kernel (devpack.cuh) decodes + packs them on the GPU; threads = 0 is
+    the device packer alone, threads = 2 races it against two host packers on the same queue of blocks.
+    Same counts as the oracle, for ragged reads (incl. empty ones, N runs, lower case, U, raw 0-3 bytes,
+    0xFF, a read longer than a batch) and for a strided matrix."""
+    sites = os.path.join(GOLDEN, "shared", "sites300.fa")
+    rng = random.Random(4242)
+    wins = _windows(sites)
+    reads = _reads(rng, wins, 5000, "ACGTN") + [b"", b"A", b"N" * 40, b"", wins[0].encode() * 300, wins[1].lower().encode(),
+                                                 wins[2].replace("T", "U").encode(), bytes("ACGT".index(c) for c in wins[3]),
+                                                 wins[4][:10].encode() + b"\xff" + wins[4][10:].encode(), b""]
+    ofp = oracle.fingerprint(sites, 19, False)
+    for r in reads:
+        ofp.insert(r)
+    buf = _pinned_bytes(b"".join(reads))
+    off = np.zeros(len(reads) + 1, np.uint64)
+    np.cumsum([len(r) for r in reads], out=off[1:])
+    for bb in (1 << 14, 5000, 1 << 20):
+        fp = ntsm_b200.FingerPrint(sites, batch_bases=bb, n_buffers=threads + 3)
+        l0 = fp.launches
+        check_rc = ntsm_b200._lib.lib().ntsm_insert_reads((ntsm_b200._lib.C.c_void_p * 1)(fp._ctx), 1, buf.data_ptr(), off.ctypes.data,
+                                                          len(reads), threads)
+        assert check_rc == 0, ntsm_b200._lib.lib().ntsm_last_error(None)
+        assert fp.counts_text() == ofp.counts_text() and fp.printInfoSummary() == ofp.summary()
+        assert fp.launches > l0
+        fp.close()
+    # dense matrix with a row stride, in pinned memory
+    L_, stride, n = 151, 160, 4000
+    mat = np.full((n, stride), ord("N"), np.uint8)
+    ofp2 = oracle.fingerprint(sites, 19, False)
+    for i in range(n):
+        w = rng.choice(wins).encode()
+        r = (bytes(rng.choice(b"ACGT") for _ in range(L_)) + w)[-L_:] if i % 3 else bytes(rng.choice(b"ACGTN") for _ in range(L_))
+        mat[i, :L_] = np.frombuffer(r, np.uint8)
+        ofp2.insert(r)
+    pm = _pinned_bytes(mat.tobytes())
+    for bb, stride_, ptr in ((1 << 15, stride, pm.data_ptr()), (3000, stride, pm.data_ptr())):
+        fp = ntsm_b200.FingerPrint(sites, batch_bases=bb, n_buffers=threads + 3)
+        fp.insertReadsFixed(ptr, L_, stride_, n, threads=threads)
+        assert fp.counts_text() == ofp2.counts_text() and fp.printInfoSummary() == ofp2.summary()
+        fp.close()
+    # the same bytes from pageable memory with device_pack off: host packers only, same answer
+    fp = ntsm_b200.FingerPrint(sites, batch_bases=1 << 15, n_buffers=4, options={"device_pack": 0})
+    fp.insertReadsFixed(pm.data_ptr(), L_, stride, n, threads=max(1, threads))
+    assert fp.counts_text() == ofp2.counts_text()
+    fp.close()
+
+
+def test_host_register_makes_a_buffer_device_packable(oracle):
+    sites = os.path.join(GOLDEN, "shared", "sites300.fa")
+    rng = random.Random(5)
+    wins = _windows(sites)
+    L_, n = 150, 3000
+    mat = np.empty((n, L_), np.uint8)
+    ofp = oracle.fingerprint(sites, 19, False)
+    for i in range(n):
+        r = (bytes(rng.choice(b"ACGT") for _ in range(L_)) + rng.choice(wins).encode())[-L_:]
+        mat[i] = np.frombuffer(r, np.uint8)
+        ofp.insert(r)
+    Lb = ntsm_b200._lib.lib()
+    assert Lb.ntsm_host_register(mat.ctypes.data, mat.nbytes) == 0
+    try:
+        fp = ntsm_b200.FingerPrint(sites, batch_bases=1 << 16)
+        l0 = fp.launches
+        fp.insertReadsFixed(mat.ctypes.data, L_, L_, n, threads=0)      # threads = 0: only the device packer can do the work
+        assert fp.counts_text() == ofp.counts_text()
+        assert fp.launches - l0 >= 2
+        fp.close()
+    finally:
+        assert Lb.ntsm_host_unregister(mat.ctypes.data) == 0
+
+
+# ---------------------------------------------------------------- several GPUs of one process, no NCCL
+@pytest.mark.parametrize("n_ctx", [2, 3])
+def test_group_finalize_equals_one_context(oracle, n_ctx):
+    """ntsm_group_finalize: ctx 0 sums the other ctxs' counts out of (peer) device memory inside the per-site
+    reduce kernel.  Reads dealt over n_ctx contexts -- on as many GPUs as the box has, wrapping around, so
+    a one-GPU box runs the same kernel over plain device pointers -- must give the oracle's counts file,
+    summary and per-k-mer counters for ALL the reads (sums before max: src/FingerPrint.hpp:277-294)."""
+    import torch
+    sites = os.path.join(GOLDEN, "shared", "sites300.fa")
+    rng = random.Random(31 + n_ctx)
+    reads = _reads(rng, _windows(sites), 6000, "ACGTN")
+    ofp = oracle.fingerprint(sites, 19, False)
+    for r in reads:
+        ofp.insert(r)
+    ndev = torch.cuda.device_count()
+    ss = ntsm_b200.SiteSet(sites, 19)
+    fps = [ntsm_b200.FingerPrint(ss, device=i % ndev, batch_bases=1 << 14) for i in range(n_ctx)]
+    for i, r in enumerate(reads):
+        fps[(i * 7) % n_ctx].insertCount(r)
+    rows = ntsm_b200.FingerPrint.group_finalize(fps)
+    assert (int(rows[4][0]), int(rows[4][1]), int(rows[4][2])) == (ofp.total_kmers, ofp.total_counts, ofp.total_bases)
+    assert fps[0].counts_text() == ofp.counts_text() and fps[0].printInfoSummary() == ofp.summary()
+    _, _, ocnt = ofp.lists()
+    assert np.array_equal(fps[0].kmer_counts(), ocnt)
+    # a per-GPU max summed afterwards is NOT the same thing (the ntsmEval --merge trap): make sure the reads were really split
+    assert all(int(f.poll_totals()[2]) > 0 for f in fps)
+    for f in fps:
+        f.close()
 
 
 # ---------------------------------------------------------------- the counts file's consumer

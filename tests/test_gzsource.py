@@ -231,7 +231,9 @@ def test_plain_and_tiny_files_pass_through(tmp_path):
     data = fastq(random.Random(16), 100)
     p.write_bytes(data)
     got, rc, mode, fb = read_all(p, chunk=1000)
-    assert (got, rc, mode) == (data, 0, "zlib")
+    assert (got, rc, mode) == (data, 0, "mapped")        # a plain regular file: mapped, same bytes as gzread's transparent mode
+    p.write_bytes(b"\x1f" + data)                        # starts like gzip but is not: still passed through byte for byte
+    assert read_all(p, chunk=7)[:2] == (b"\x1f" + data, 0)
     p.write_bytes(b"")
     assert read_all(p)[:3] == (b"", 0, "zlib")
     p.write_bytes(b"\x1f\x8b\x08")                # shorter than any gzip member: zlib's call
