@@ -458,12 +458,13 @@ def ours(args):
         runs = 1 + min(3, args.steps)
         return ms, rows, ((fp_a.launches - la) // runs,) + pcie_per_step(fp_a, pb, runs)
 
-    a_ms, a_rows, a_io = ascii_leg(1, host_threads)                 # hybrid: host packers + device packer
+    a_ms, a_rows, a_io = ascii_leg(-1, host_threads)                # the library's default: feeders when < 8 host packers serve each GPU
+    y_ms, y_rows, y_io = ascii_leg(1, host_threads)                 # hybrid forced: host packers + device packer
     h_ms, h_rows, h_io = ascii_leg(0, host_threads)                 # host packers only (round 1's path)
     d_ms, d_rows, d_io = ascii_leg(1, 0)                            # device packer only: no host core touches a base
-    fp_a.set_option("device_pack", 1)
-    log("rank %d: e2e ascii %.2f Gbases: hybrid %.1f ms, host packers only %.1f ms, device packer only %.1f ms (%d pack threads, %s)" %
-        (rank, a_bases / 1e9, a_ms, h_ms, d_ms, host_threads, ntsm_b200.lib().ntsm_pack_isa(None).decode()))
+    fp_a.set_option("device_pack", -1)
+    log("rank %d: e2e ascii %.2f Gbases: default %.1f ms, hybrid %.1f ms, host packers only %.1f ms, device packer only %.1f ms (%d pack threads, %s)" %
+        (rank, a_bases / 1e9, a_ms, y_ms, h_ms, d_ms, host_threads, ntsm_b200.lib().ntsm_pack_isa(None).decode()))
 
     # (c) the same reads, already packed, in pinned host memory (what PCIe alone allows)
     budget = min(phys_bytes, int(avail * 0.2 / max(1, local_world)), env_int("NTSM_BENCH_E2E_GB", 32) << 30)
@@ -494,13 +495,13 @@ def ours(args):
         fp.count_packed_host(hb.data_ptr(), hm.data_ptr(), c_reads * (READ_LEN + 1), c_reads * READ_LEN)
         want = fp.finalize()
         ascii_check = True
-        for dp, th in ((1, host_threads), (0, host_threads), (1, 0)):
+        for dp, th in ((-1, host_threads), (1, host_threads), (0, host_threads), (1, 0)):
             fp_a.set_option("device_pack", dp)
             fp_a.reset_async()
             fp_a.insertReadsFixed(host_ascii.data_ptr(), READ_LEN, READ_LEN, c_reads, threads=th)
             got = fp_a.finalize()
             ascii_check = ascii_check and all(np.array_equal(x, y) for x, y in zip(want, got))
-        fp_a.set_option("device_pack", 1)
+        fp_a.set_option("device_pack", -1)
     del hb, hm, host_ascii
 
     # ---- rank 0: CPU reference on a bounded sample + byte-for-byte parity of our whole pipeline on it ----
@@ -557,8 +558,10 @@ def ours(args):
             "cpu_baseline": cpu,
             "e2e": files,
             "e2e_gz": gz,
-            "e2e_ascii": ascii_obj(a_ms, a_io, "ntsm_insert_reads_fixed + ntsm_finalize, ASCII reads in pinned host memory: host packers "
-                                   "AND the device packer (DMA of ASCII + pack_ascii_kernel) on one queue of read blocks", host_threads),
+            "e2e_ascii": ascii_obj(a_ms, a_io, "ntsm_insert_reads_fixed + ntsm_finalize, ASCII reads in pinned host memory, library defaults: %d host "
+                                   "packer threads per GPU; the device packer (DMA of ASCII + pack_ascii_kernel) joins them on the same queue of "
+                                   "read blocks when fewer than 8 packers serve a GPU" % host_threads, host_threads),
+            "e2e_ascii_hybrid": ascii_obj(y_ms, y_io, "same, host packers AND the device packer forced on", host_threads),
             "e2e_ascii_host_pack_only": ascii_obj(h_ms, h_io, "same, device packer off (round 1's path)", host_threads),
             "e2e_ascii_device_pack_only": ascii_obj(d_ms, d_io, "same, zero host packers: every base goes over PCIe as ASCII and is packed on the GPU", 0),
             "e2e_packed": {"value": e2e_val, "unit": "Gbases/s", "h2d_bytes_per_step": p_h2d, "d2h_bytes_per_step": d2h_rows,

@@ -111,8 +111,9 @@ int ntsm_load_siteset(ntsm_ctx *ctx, const ntsm_sites *s);
  *   "pair_fold"    paired-seed table folded 2^n : 1 (0..4), -1 = automatic (1; 0 above 5 M site k-mers)
  *   "filter_bits"  log2 of the k-mer bitmap's bits (10..32), 0 = automatic (~80 bits per site k-mer)
  *   "launch_shape" pair kernel CTA shape: 0 = 1024x1, 1 = 1024x2 (default), 2 = 512x4, 3 = 256x8 per SM
- *   "l2_persist"   1 (default) = launch with an L2 access-policy window that keeps the probe tables resident
- *   "device_pack"  1 (default) = ntsm_insert_reads* from page-locked memory also feed ASCII to the GPU packer (may be set any time) */
+ *   "l2_persist"   1 = launch with an L2 access-policy window that marks the probe tables persisting (default 0: measured, no effect)
+ *   "device_pack"  ntsm_insert_reads* from page-locked memory also feed ASCII to the GPU packer: 1 on, 0 off,
+ *                  -1 (default) on when fewer than 8 host packer threads serve each GPU (may be set any time) */
 int ntsm_ctx_set_option(ntsm_ctx *ctx, const char *name, int value);
 
 /* ---------------- packed batches: the ProdCon bulk buffers (vendor/ProdConKseqRunner.hpp:34-46) */
@@ -139,6 +140,10 @@ int ntsm_release_batch(ntsm_ctx *ctx, ntsm_batch *b);
 const char *ntsm_pack_isa(const char *force);
 uint64_t ntsm_pack_reads(const char *buf, const uint64_t *off, uint64_t n_reads, uint32_t *bases2,
                          uint32_t *nmask, uint64_t *read_off /*nullable, n_reads+1*/);
+/* same; streaming != 0 (and both arrays 64-byte aligned) packs the way the library fills its pinned batches:
+ * through a cache-resident staging area, whole 64-byte lines leaving it with non-temporal stores */
+uint64_t ntsm_pack_reads2(const char *buf, const uint64_t *off, uint64_t n_reads, uint32_t *bases2,
+                          uint32_t *nmask, uint64_t *read_off /*nullable, n_reads+1*/, int streaming);
 
 /* Count a packed stream that is ALREADY in device memory (padding contract as above) on
  * `cuda_stream` (a cudaStream_t; NULL = the ctx's compute stream).  Adds n_bases to the base tally. */
@@ -171,7 +176,8 @@ int ntsm_insert_reads_fixed(ntsm_ctx *const *ctxs, uint32_t n_ctx, const char *b
  * registered with ntsm_host_register), one extra feeder thread per ctx takes blocks of reads from the
  * same queue as the `threads` host packers, DMAs their ASCII bytes to the GPU as they are and has the
  * GPU decode + pack them (pack_ascii_kernel): no host core touches those bases.  `threads` == 0 then
- * means "device packing only".  With pageable memory only the host packers run (threads >= 1).
+ * means "device packing only".  With pageable memory only the host packers run (threads >= 1).  By default
+ * the feeders start when fewer than 8 packer threads serve each GPU (option "device_pack").
  * ntsm_host_register pins a caller's buffer (cudaHostRegister, portable); it costs ~0.2 s per GiB, so
  * it pays for buffers that are filled more than once. */
 int ntsm_host_register(void *buf, uint64_t bytes);

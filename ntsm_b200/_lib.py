@@ -62,6 +62,7 @@ _SIGS = {
     "ntsm_release_batch": (C.c_int, [_P, _P]),
     "ntsm_pack_isa": (C.c_char_p, [C.c_char_p]),
     "ntsm_pack_reads": (C.c_uint64, [_P, _P, C.c_uint64, _P, _P, _P]),
+    "ntsm_pack_reads2": (C.c_uint64, [_P, _P, C.c_uint64, _P, _P, _P, C.c_int]),
     "ntsm_count_packed_device": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, _P]),
     "ntsm_count_packed_host": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64]),
     "ntsm_reset_counts_async": (C.c_int, [_P]),

@@ -18,6 +18,7 @@
 #include "../../include/ntsm_b200.h"
 #include "batch_writer.h"
 #include "internal.h"
+#include "numa.h"
 
 namespace {
 
@@ -41,6 +42,7 @@ struct Bulk {
 void feeder(Bulk &bk, uint32_t ci)
 {
 	ntsm_ctx *c = bk.ctxs[ci];
+	ntsm::run_on_node(ntsm_ctx_numa_node(c));           // the feeder only issues DMA, but its pinned aux tables are touched here
 	ntsm::BatchWriter bw(bk.ctxs, bk.n_ctx, &bk.next_batch);
 	auto fail = [&](int code, const char *text) {
 		std::lock_guard<std::mutex> g(bk.err_mu);
@@ -81,6 +83,8 @@ void feeder(Bulk &bk, uint32_t ci)
 
 void producer(Bulk &bk)
 {
+	// one GPU: the packers run on its node; several GPUs: batches go round-robin, any node is as good as another
+	if (bk.n_ctx == 1) ntsm::run_on_node(ntsm_ctx_numa_node(bk.ctxs[0]));
 	ntsm::BatchWriter bw(bk.ctxs, bk.n_ctx, &bk.next_batch);
 	for (;;) {
 		const uint64_t blk = bk.next_block.fetch_add(1);
@@ -112,14 +116,15 @@ int run(Bulk &bk, uint32_t threads, uint64_t total_bases)
 	bk.reads_per_block = std::max<uint64_t>(1, (cap - cap / 64) / avg);
 	const uint64_t n_blocks = (bk.n_reads + bk.reads_per_block - 1) / bk.reads_per_block;
 	// page-locked input: one feeder per GPU next to the host packers (threads == 0: feeders only)
-	const bool pinned = ntsm_ctx_device_pack(bk.ctxs[0]) && ntsm_host_is_pinned(bk.buf) != 0;
+	const bool pinned = ntsm_ctx_device_pack(bk.ctxs[0], threads / bk.n_ctx) && ntsm_host_is_pinned(bk.buf) != 0;
 	uint32_t nt = threads ? threads : (pinned ? 0 : 1);
 	if (nt > n_blocks) nt = (uint32_t)n_blocks;
 	std::vector<std::thread> pool;
 	if (pinned)
 		for (uint32_t g = 0; g < bk.n_ctx; ++g) pool.emplace_back(feeder, std::ref(bk), g);
-	for (uint32_t t = 1; t < nt; ++t) pool.emplace_back(producer, std::ref(bk));
-	if (nt) producer(bk);
+	// every producer runs on a thread of its own (they may pin themselves to the GPU's NUMA node; the
+	// caller's thread keeps its affinity)
+	for (uint32_t t = 0; t < nt; ++t) pool.emplace_back(producer, std::ref(bk));
 	for (auto &t : pool) t.join();
 	if (bk.error.load()) {
 		ntsm_set_thread_error(bk.err_text.c_str());

@@ -22,6 +22,7 @@
 #include "pair.cuh"
 #include "devpack.cuh"
 #include "pack.h"
+#include "numa.h"
 
 using namespace ntsm;
 
@@ -55,13 +56,14 @@ struct ntsm_ctx {
 	int device = 0;
 	cudaStream_t copy_stream = nullptr, compute_stream = nullptr, own_compute = nullptr;
 	int sm_count = 148;
+	int numa_node = -1;                     // the GPU's NUMA node when the host has more than one and says which (numa.h)
 	// options (ntsm_ctx_set_option, before ntsm_load_sites); -1 / 0 = decide from the panel
 	int opt_kernel = -1;                    // 0 generic (one k-mer-bitmap probe per position), 1 paired seeds
 	int opt_pair_fold = -1;                 // paired-seed table folded 2^fold : 1
 	int opt_filter_bits = 0;                // log2 bits of the k-mer bitmap
 	int opt_shape = 1;                      // pair kernel launch shape: 0 = 1024x1, 1 = 1024x2 (default), 2 = 512x4, 3 = 256x8
-	int opt_l2_persist = 1;                 // mark the probe tables as persisting in L2 when they fit the set-aside
-	int opt_device_pack = 1;                // bulk inserts from page-locked memory also feed ASCII to the GPU packer
+	int opt_l2_persist = 0;                 // launch with an L2 access-policy window over the probe tables (measured: no effect, see ntsm_load_sites)
+	int opt_device_pack = -1;               // bulk inserts from page-locked memory also feed ASCII to the GPU packer: -1 = when host packers are few
 	// site table
 	uint32_t n_kmers = 0, n_sites = 0;
 	uint32_t *d_probe = nullptr;            // ONE allocation: paired-seed table, then the k-mer bitmap (one L2 access-policy window covers both)
@@ -99,6 +101,10 @@ struct ntsm_ctx {
 	unsigned long long *launch_totals = nullptr;   // nullptr = d_totals
 	bool reduced = false;
 	cudaEvent_t drained = nullptr;          // ntsm_group_finalize: this ctx's counts are final
+	// ASCII (device-packed) batches are 2.7x the bytes of a packed one: at most two of their copies are queued at
+	// a time, so the host packers' small batches never wait behind a long line of them on the copy stream
+	cudaEvent_t ascii_ev[2] = { nullptr, nullptr };
+	uint64_t ascii_jobs = 0;
 	ncclComm_t comm = nullptr;
 	int rank = 0, n_ranks = 1;
 	std::string err;
@@ -171,10 +177,13 @@ extern "C" int ntsm_ctx_create(ntsm_ctx **out, const ntsm_cfg *cfg)
 	auto init = [&]() -> int {
 		CU(c, cudaSetDevice(c->device));
 		CU(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+		c->numa_node = gpu_numa_node(c->device);
 		CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
 		CU(c, cudaStreamCreateWithFlags(&c->own_compute, cudaStreamNonBlocking));
 		c->compute_stream = c->own_compute;
 		CU(c, cudaEventCreateWithFlags(&c->drained, cudaEventDisableTiming));
+		CU(c, cudaEventCreateWithFlags(&c->ascii_ev[0], cudaEventDisableTiming | cudaEventBlockingSync));
+		CU(c, cudaEventCreateWithFlags(&c->ascii_ev[1], cudaEventDisableTiming | cudaEventBlockingSync));
 		CU(c, cudaMalloc(&c->d_totals, 3 * sizeof(unsigned long long)));
 		CU(c, cudaMemset(c->d_totals, 0, 3 * sizeof(unsigned long long)));
 		return NTSM_OK;
@@ -219,6 +228,7 @@ extern "C" void ntsm_ctx_destroy(ntsm_ctx *c)
 	cudaFree(c->d_totals);
 	cudaFree(c->d_scratch_totals);
 	if (c->drained) cudaEventDestroy(c->drained);
+	for (cudaEvent_t e : c->ascii_ev) if (e) cudaEventDestroy(e);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	if (c->own_compute) cudaStreamDestroy(c->own_compute);
 	delete c;
@@ -264,9 +274,10 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 	if (c->opt_pair_fold >= 0) fold = c->opt_pair_fold;
 	while (fold > 0 && (pair_words(pm) >> fold) < 1024) --fold;
 
-	// k-mer bitmap holding both orientations of every live k-mer, two bits each: ~40 bits per key
+	// k-mer bitmap holding both orientations of every live k-mer, two bits each: 20-40 bits per key (8 MiB for
+	// the human panel; 2^24..2^28 bits measured within 3 % of each other, 2^26 best: profiles/r02e_sweep_filterbits.jsonl)
 	uint32_t fbits = 16;
-	while (fbits < 30 && (1ull << fbits) < 40ull * 2ull * live) ++fbits;
+	while (fbits < 30 && (1ull << fbits) < 20ull * 2ull * live) ++fbits;
 	if (c->opt_filter_bits) fbits = (uint32_t)c->opt_filter_bits;
 	const size_t filter_words = (1ull << fbits) / 32;
 	const size_t pair_n = kernel == 1 ? pair_words(pm) >> fold : 0;
@@ -297,9 +308,13 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 	CU(c, cudaMalloc(&c->d_rows, std::max<size_t>(1, n_sites) * 16));
 
 	// L2 residency: the probe tables are hit at random by every warp while the packed reads stream
-	// through the same L2 once.  The reads are loaded with an evict-first hint (ld.global.cs); on top of
-	// that the count kernels are launched with an access-policy window that marks the probe tables as
-	// persisting, when the device's persisting set-aside can hold them (cfg 2: 48 MiB of tables).
+	// through the same L2 once.  The reads are loaded with an evict-first hint (ld.global.cs), which is
+	// what keeps the tables in.  An access-policy window that marks the probe tables as persisting on
+	// top of that ("l2_persist", off by default) was measured and changes nothing for the human panel --
+	// same 83 % sector hit rate, same 3.51 vs 3.52 GB of DRAM reads per 6 Gbases, same 3.05 ms
+	// (profiles/r02d_count_ncu_persist{0,1}.txt): the misses that remain are capacity (48 MiB of tables
+	// against an L2 whose two halves each keep their own copy of far-die lines), not eviction by the
+	// stream -- and costs 7 % for the 10^6-site panel, whose tables do not fit the set-aside (296 vs 318 Gbases/s).
 	c->l2_window = false;
 	if (c->opt_l2_persist) {
 		int max_persist = 0, max_window = 0;
@@ -503,6 +518,7 @@ static int make_batch(ntsm_ctx *c, ntsm_batch **out)
 	b->ctx = c;
 	b->cap_pos = c->cfg.batch_bases & ~(kReadAlign - 1);
 	const uint64_t padded = padded_positions(b->cap_pos);
+	PreferNode on_gpu_node(c->numa_node);     // the ring's pages come from the GPU's own node (no-op on one-node hosts)
 	CU(c, cudaMallocHost(&b->h_bases, padded / 32 * 8));
 	CU(c, cudaMallocHost(&b->h_mask, padded / 32 * 4));
 	CU(c, cudaMallocHost(&b->h_snap, 16));
@@ -549,7 +565,7 @@ extern "C" int ntsm_acquire_batch(ntsm_ctx *c, ntsm_batch **out)
 		for (ntsm_batch *b : c->batches)
 			if (b->state == 0) {
 				b->state = 1;
-				b->pk.reset(b->h_bases, b->h_mask);
+				b->pk.reset_streaming(b->h_bases, b->h_mask);      // pinned, written once, read only by the DMA engine
 				b->n_bases = b->n_reads = 0;
 				b->read_end.clear();
 				b->read_bases.clear();
@@ -631,9 +647,15 @@ static int enqueue_batch(ntsm_ctx *c, ntsm_batch *b, const void *src_bases, cons
 		return NTSM_OK;
 	}
 	auto enqueue = [&]() -> int {
+		cudaEvent_t slot = nullptr;
+		if (ascii) {                      // one feeder per ctx calls this: wait until the ASCII copy before the last one is through
+			slot = c->ascii_ev[c->ascii_jobs++ & 1];
+			CU(c, cudaEventSynchronize(slot));
+		}
 		std::lock_guard<std::mutex> sg(c->submit_mu);
 		if (ascii) {
 			CU(c, cudaMemcpyAsync(b->d_ascii, ascii->src, ascii->bytes, cudaMemcpyHostToDevice, c->copy_stream));
+			CU(c, cudaEventRecord(slot, c->copy_stream));
 			c->h2d_bytes += ascii->bytes;
 			if (!ascii->fixed) {
 				CU(c, cudaMemcpyAsync(b->d_aux, b->h_aux, (2 * (uint64_t)ascii->pp.n_reads + 2) * 4, cudaMemcpyHostToDevice, c->copy_stream));
@@ -778,7 +800,15 @@ int ntsm_submit_ascii_var(ntsm_ctx *c, const char *buf, const uint64_t *off, uin
 
 // 1 when `p` points into page-locked host memory the DMA engines can read directly (cudaMallocHost /
 // cudaHostAlloc / cudaHostRegister), else 0
-int ntsm_ctx_device_pack(const ntsm_ctx *c) { return c->opt_device_pack; }
+// Should bulk inserts from page-locked memory start a feeder for this ctx?  The device packer moves 1 byte per
+// base over PCIe where a host-packed base costs 0.375: with many host packers per GPU (one GPU fed by 16
+// cores: 109 Gbases/s on their own) the feeder only competes for the link (106 with it), with few per GPU
+// (eight GPUs fed by 32 cores) it is most of the throughput.  Automatic = on when fewer than 8 packers serve this ctx.
+int ntsm_ctx_device_pack(const ntsm_ctx *c, uint32_t host_packers_per_ctx)
+{
+	if (c->opt_device_pack >= 0) return c->opt_device_pack;
+	return host_packers_per_ctx < 8;
+}
 
 int ntsm_host_is_pinned(const void *p)
 {
@@ -1236,6 +1266,7 @@ extern "C" int ntsm_get_totals(ntsm_ctx *c, uint64_t totals[3])
 // library-internal helpers (not part of the public header)
 uint64_t ntsm_ctx_max_counts(const ntsm_ctx *c) { return c->cfg.max_counts; }
 uint64_t ntsm_ctx_reads(const ntsm_ctx *c) { return c->submitted_reads; }
+int ntsm_ctx_numa_node(const ntsm_ctx *c) { return c->numa_node; }
 uint64_t ntsm_ctx_batch_bases(const ntsm_ctx *c) { return c->cfg.batch_bases; }
 void ntsm_set_thread_error(const char *text) { t_last_error = text; }
 

@@ -12,10 +12,10 @@ namespace ntsm {
 
 static constexpr size_t kWindow = 1u << 20;
 
-bool FastxReader::open(const char *path, int helpers)
+bool FastxReader::open(const char *path, int helpers, bool map_plain)
 {
 	close();
-	if (!src_.open(path, helpers)) return false;   // plain files pass through, like the reference's gzopen (FingerPrint.hpp:50)
+	if (!src_.open(path, helpers, map_plain)) return false;   // plain files pass through, like the reference's gzopen (FingerPrint.hpp:50)
 	open_ = true;
 	beg_ = end_ = 0;
 	eof_ = err_ = src_err_ = false;

@@ -648,7 +648,7 @@ bool GzSource::fell_back() const { return p_ && p_->fell_back; }
 bool GzSource::bad() const { return p_ && p_->failed; }
 uint64_t GzSource::parallel_chunks() const { return p_ ? p_->par_chunks + (p_->par ? p_->par->chunks_accepted() : 0) : 0; }
 
-bool GzSource::open(const char *path, int helpers)
+bool GzSource::open(const char *path, int helpers, bool map_plain)
 {
 	close();
 	p_.reset(new Impl());
@@ -719,13 +719,18 @@ bool GzSource::open(const char *path, int helpers)
 	// untouched (zlib's transparent mode, which the reference relies on for plain FASTA/FASTQ,
 	// src/FingerPrint.hpp:50) -- at the price of read() copying every byte out of the page cache, which is
 	// three quarters of the reader's time on cached files.  Map it instead: the reader scans the page
-	// cache's own pages (FastxReader takes the mapping as its window), nothing is copied.
+	// cache's own pages (FastxReader takes the mapping as its window), nothing is copied.  The price is
+	// page-table work per 4 KiB page, which is cheaper than copying the page for one reader (4.6 vs 2.8
+	// Gbases/s per thread on the GPU box) but does not scale inside one process: at 16 parser threads
+	// the mapped readers fall to 1.7 Gbases/s each and gzread's 2.4 win (profiles/r02e_hostpath.txt,
+	// r02f_hostpath.txt: every way of setting the mapping up lands on the same number).  So the caller
+	// says whether to map (map_plain): the file pipeline does for up to 6 parser threads.
 	{
 		struct stat sb2;
 		if (want_fast && fstat(fd, &sb2) == 0 && S_ISREG(sb2.st_mode) && sb2.st_size > 0 && !(magic[0] == 0x1f && magic[1] == 0x8b)) {
 			unsigned char m2[2] = { 0, 0 };
 			const bool is_gz = pread(fd, m2, 2, 0) == 2 && m2[0] == 0x1f && m2[1] == 0x8b;
-			void *m = is_gz ? MAP_FAILED : mmap(nullptr, (size_t)sb2.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+			void *m = is_gz || !map_plain ? MAP_FAILED : mmap(nullptr, (size_t)sb2.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
 			if (m != MAP_FAILED) {
 				madvise(m, (size_t)sb2.st_size, MADV_SEQUENTIAL);
 				s.map = (const uint8_t *)m;

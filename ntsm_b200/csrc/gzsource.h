@@ -43,7 +43,8 @@ public:
 
 	// helpers: extra threads this source may start for block-parallel inflate (0 = none).
 	// NTSM_INFLATE=zlib forces plain gzread (tests, comparisons).
-	bool open(const char *path, int helpers = 0);
+	// map_plain: plain (non-gzip) regular files are memory-mapped rather than pulled through gzread
+	bool open(const char *path, int helpers = 0, bool map_plain = true);
 	void close();
 	// gzread's contract: the number of bytes delivered, short only at the end of the input;
 	// 0 at the end; -1 on a read/format error (after the bytes that preceded it were delivered)

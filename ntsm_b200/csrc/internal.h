@@ -11,8 +11,9 @@ void ntsm_set_thread_error(const char *text);
 // exact -m stop after the batch just completed on ctx (ctx.cu); hits_elsewhere = hits on the other GPUs
 int ntsm_trim_to_cap(ntsm_ctx *c, uint64_t hits_elsewhere, uint64_t cap);
 // reads that arrive as ASCII in pinned host memory and are decoded + packed on the device (ctx.cu, devpack.cuh)
+int ntsm_ctx_numa_node(const ntsm_ctx *c);       // NUMA node of the ctx's GPU, -1 = unknown / one-node host
 int ntsm_host_is_pinned(const void *p);
-int ntsm_ctx_device_pack(const ntsm_ctx *c);
+int ntsm_ctx_device_pack(const ntsm_ctx *c, uint32_t host_packers_per_ctx);
 uint64_t ntsm_ascii_capacity_fixed(const ntsm_ctx *c, uint64_t read_len, uint64_t stride);   // rows one batch takes
 int ntsm_submit_ascii_fixed(ntsm_ctx *c, const char *rows, uint64_t read_len, uint64_t stride, uint64_t n_reads);
 int ntsm_submit_ascii_var(ntsm_ctx *c, const char *buf, const uint64_t *off, uint64_t n_reads, uint64_t *taken);

@@ -29,8 +29,8 @@ const uint8_t *code_table() { return g_code_init.t; }
 static void run_scalar(Packer &dst, const char *s, uint64_t n)
 {
 	const uint8_t *t = g_code_init.t;
-	uint8_t *ob = reinterpret_cast<uint8_t *>(dst.bases) + dst.pos / 4;
-	uint8_t *om = reinterpret_cast<uint8_t *>(dst.mask) + dst.pos / 8;
+	uint8_t *ob = dst.wb + dst.pos / 4;
+	uint8_t *om = dst.wm + dst.pos / 8;
 	const uint64_t span = read_span(n);
 	for (uint64_t i = 0; i < span; i += 8) {
 		unsigned bb = 0, mm = 0;
@@ -79,8 +79,8 @@ NTSM_TGT_AVX2 static inline void planes32_avx2(__m256i v, uint32_t *bit0, uint32
 NTSM_TGT_AVX2 static void run_avx2(Packer &dst, const char *s, uint64_t n)
 {
 	const uint64_t kEven = 0x5555555555555555ULL, kOdd = 0xAAAAAAAAAAAAAAAAULL;
-	uint8_t *ob = reinterpret_cast<uint8_t *>(dst.bases) + dst.pos / 4;
-	uint8_t *om = reinterpret_cast<uint8_t *>(dst.mask) + dst.pos / 8;
+	uint8_t *ob = dst.wb + dst.pos / 4;
+	uint8_t *om = dst.wm + dst.pos / 8;
 	uint64_t i = 0;
 	uint32_t b0, b1, va;
 	for (; i + 32 <= n; i += 32, ob += 8, om += 4) {
@@ -136,8 +136,8 @@ NTSM_TGT_AVX512 static inline __m128i pack64_avx512(__m512i v, __m512i tab_lo, _
 NTSM_TGT_AVX512 static void run_avx512(Packer &dst, const char *s, uint64_t n)
 {
 	const __m512i tab_lo = _mm512_load_si512(g_vbmi_tab.t), tab_hi = _mm512_load_si512(g_vbmi_tab.t + 64);
-	uint8_t *ob = reinterpret_cast<uint8_t *>(dst.bases) + dst.pos / 4;
-	uint8_t *om = reinterpret_cast<uint8_t *>(dst.mask) + dst.pos / 8;
+	uint8_t *ob = dst.wb + dst.pos / 4;
+	uint8_t *om = dst.wm + dst.pos / 8;
 	uint64_t i = 0, iv;
 	for (; i + 64 <= n; i += 64, ob += 16, om += 8) {
 		_mm_prefetch(s + i + kPrefetchAhead, _MM_HINT_T0);
@@ -188,12 +188,97 @@ const char *pack_isa()
 }
 void pack_reselect() { g_run = pick_run(); }
 
-void Packer::put_read(const char *s, uint64_t n) { g_run(*this, s, n); }
+// Completed blocks of the staging area -> the pinned arrays, as whole 64-byte lines that bypass the cache
+// (no read-for-ownership); what is left (less than a block, plus the packers' overrun) slides to the front.
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static void stream_out(uint8_t *dst, const uint8_t *src, size_t bytes)      // all 64-byte multiples / aligned
+{
+	for (size_t i = 0; i < bytes; i += 64) {
+		_mm256_stream_si256((__m256i *)(dst + i), _mm256_load_si256((const __m256i *)(src + i)));
+		_mm256_stream_si256((__m256i *)(dst + i + 32), _mm256_load_si256((const __m256i *)(src + i + 32)));
+	}
+}
+static const bool g_have_avx2 = __builtin_cpu_supports("avx2");
+#endif
+
+void Packer::flush_blocks(bool all)
+{
+	const uint64_t upto = all ? (pos + kBlockPos - 1) / kBlockPos * kBlockPos : pos / kBlockPos * kBlockPos;   // `all`: the ragged tail too (finish() pads it first)
+	const uint64_t n = upto - origin;
+	if (n) {
+		uint8_t *db = reinterpret_cast<uint8_t *>(bases) + origin / 4, *dm = reinterpret_cast<uint8_t *>(mask) + origin / 8;
+#if defined(__x86_64__)
+		if (g_have_avx2) {
+			stream_out(db, stage_b, n / 4);
+			stream_out(dm, stage_m, n / 8);
+		} else
+#endif
+		{
+			memcpy(db, stage_b, n / 4);
+			memcpy(dm, stage_m, n / 8);
+		}
+	}
+	// keep the unfinished block and the 64 positions the packers may already have written past pos
+	const uint64_t keep = pos + 64 > upto ? pos + 64 - upto : 0;
+	if (keep && n) {
+		memmove(stage_b, stage_b + n / 4, (keep + 3) / 4);
+		memmove(stage_m, stage_m + n / 8, (keep + 7) / 8);
+	}
+	origin = upto;
+	wb = stage_b - origin / 4;
+	wm = stage_m - origin / 8;
+}
+
+void Packer::put_read(const char *s, uint64_t n)
+{
+	if (streaming) {
+		const uint64_t span = read_span(n);
+		if (pos - origin + span + kSlackPos > kStagePos) {
+			flush_blocks(false);
+			if (span + kBlockPos + kSlackPos > kStagePos) {
+				// a read longer than the staging area (long-read data): the finished blocks are out, the open
+				// one goes out as it is, and this read is written in place with ordinary stores
+				const uint64_t tail = pos - origin;
+				memcpy(reinterpret_cast<uint8_t *>(bases) + origin / 4, stage_b, (tail + 3) / 4);
+				memcpy(reinterpret_cast<uint8_t *>(mask) + origin / 8, stage_m, (tail + 7) / 8);
+				wb = reinterpret_cast<uint8_t *>(bases);
+				wm = reinterpret_cast<uint8_t *>(mask);
+				g_run(*this, s, n);
+				// staging resumes at the block that holds the new pos: bring that block's finished part back in
+				origin = pos / kBlockPos * kBlockPos;
+				const uint64_t back = pos - origin;
+				memcpy(stage_b, reinterpret_cast<uint8_t *>(bases) + origin / 4, (back + 3) / 4);
+				memcpy(stage_m, reinterpret_cast<uint8_t *>(mask) + origin / 8, (back + 7) / 8);
+				wb = stage_b - origin / 4;
+				wm = stage_m - origin / 8;
+				return;
+			}
+		}
+	}
+	g_run(*this, s, n);
+}
 
 uint64_t Packer::finish()
 {
 	const uint64_t n = pos;                       // a multiple of 8: both planes end on a byte
 	const uint64_t end = padded_positions(n);
+	if (streaming) {
+		// pad the open block inside the staging area, send everything out, then pad the rest in place
+		const uint64_t blk_end = (n + kBlockPos - 1) / kBlockPos * kBlockPos;
+		memset(wb + n / 4, 0, (blk_end - n) / 4);
+		memset(wm + n / 8, 0xFF, (blk_end - n) / 8);
+		flush_blocks(true);
+		memset(reinterpret_cast<uint8_t *>(bases) + blk_end / 4, 0, (end - blk_end) / 4);
+		memset(reinterpret_cast<uint8_t *>(mask) + blk_end / 8, 0xFF, (end - blk_end) / 8);
+#if defined(__x86_64__)
+		_mm_sfence();                             // the streamed lines are globally visible before the batch is handed to the DMA engine
+#endif
+		streaming = false;
+		wb = reinterpret_cast<uint8_t *>(bases);
+		wm = reinterpret_cast<uint8_t *>(mask);
+		pos = end;
+		return n;
+	}
 	memset(reinterpret_cast<uint8_t *>(bases) + n / 4, 0, (end - n) / 4);
 	memset(reinterpret_cast<uint8_t *>(mask) + n / 8, 0xFF, (end - n) / 8);
 	pos = end;
@@ -219,8 +304,15 @@ extern "C" const char *ntsm_pack_isa(const char *force)
 extern "C" uint64_t ntsm_pack_reads(const char *buf, const uint64_t *off, uint64_t n_reads, uint32_t *bases2,
                                     uint32_t *nmask, uint64_t *read_off)
 {
+	return ntsm_pack_reads2(buf, off, n_reads, bases2, nmask, read_off, 0);
+}
+
+extern "C" uint64_t ntsm_pack_reads2(const char *buf, const uint64_t *off, uint64_t n_reads, uint32_t *bases2,
+                                     uint32_t *nmask, uint64_t *read_off, int streaming)
+{
 	ntsm::Packer p;
-	p.reset(reinterpret_cast<uint64_t *>(bases2), nmask);
+	if (streaming && ((uintptr_t)bases2 % 64 == 0) && ((uintptr_t)nmask % 64 == 0)) p.reset_streaming(reinterpret_cast<uint64_t *>(bases2), nmask);
+	else p.reset(reinterpret_cast<uint64_t *>(bases2), nmask);
 	for (uint64_t r = 0; r < n_reads; ++r) {
 		if (read_off) read_off[r] = p.pos;
 		p.put_read(buf + off[r], off[r + 1] - off[r]);

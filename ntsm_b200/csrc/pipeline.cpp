@@ -25,6 +25,7 @@ struct Shared {
 	int verbose;
 	uint64_t max_counts;
 	bool exact_cap = false;                     // one parser thread: the -m stop is trimmed to the deciding read
+	bool map_plain = true;                      // few parser threads: plain files are scanned in place through a mapping (gzsource.cpp)
 	uint32_t helpers = 0, helpers_extra = 0;    // idle -t threads lent to each parser for block-parallel inflate
 	std::atomic<uint32_t> next_file{0};
 	std::atomic<uint64_t> next_batch{0};
@@ -83,7 +84,7 @@ void worker(Shared &sh, uint32_t wi)
 	for (;;) {
 		const uint32_t fi = sh.next_file.fetch_add(1);
 		if (fi >= sh.n_paths || sh.error.load()) break;
-		if (!rd.open(sh.paths[fi], helpers)) {                               // FingerPrint.hpp:51-57
+		if (!rd.open(sh.paths[fi], helpers, sh.map_plain)) {                               // FingerPrint.hpp:51-57
 			set_error(NTSM_ERR_IO, std::string("file ") + sh.paths[fi] + " cannot be opened");
 			break;
 		}
@@ -117,6 +118,7 @@ extern "C" int ntsm_count_files(ntsm_ctx *const *ctxs, uint32_t n_ctx, const cha
 	if (nt > n_paths) nt = n_paths ? n_paths : 1;                   // the reference never uses more than #files (:47-48) ...
 	const uint32_t spare = (threads ? threads : 1) - nt;            // ... the rest of -t inflates BGZF blocks for the parsers (gzsource.h)
 	sh.exact_cap = nt == 1;
+	sh.map_plain = nt <= 6;
 	sh.helpers = spare / nt;
 	sh.helpers_extra = spare % nt;
 	std::vector<std::thread> pool;

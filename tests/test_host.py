@@ -4,6 +4,7 @@ fixtures: ABI surface, hash64 and its inverse, the kseq-grammar reader, the site
 No CUDA call is made here."""
 import ctypes as C
 import json
+import ctypes
 import os
 import random
 import re
@@ -237,6 +238,53 @@ def test_packer_isa_variants_agree(L):
         assert o[2] == ref[2] and np.array_equal(o[0], ref[0]) and np.array_equal(o[1], ref[1]), name
 
 
+def _aligned(n, dtype, fill):
+    """numpy array of n items whose data starts on a 64-byte boundary"""
+    raw = np.full(n * np.dtype(dtype).itemsize + 64, fill, np.uint8)
+    off = (-raw.ctypes.data) % 64
+    return raw[off:off + n * np.dtype(dtype).itemsize].view(dtype)
+
+
+@pytest.mark.parametrize("isa", [b"scalar", b"avx2", b"avx512"])
+def test_streaming_packer_writes_the_same_words(L, isa):
+    """The mode the pinned batches are filled in (staging area + non-temporal 64-byte lines, pack.h) against
+    the plain mode, word for word: many short reads (staging wraps many times), reads around the block and
+    staging sizes, a read far longer than the staging area in the middle and at the end, empty reads."""
+    rng = random.Random(77)
+    alphabet = b"ACGTacgtNnU\x00\x03\xff"
+    lens = [rng.choice([0, 1, 7, 8, 31, 150, 151, 152, 500, 503, 504, 511, 512, 513, 1000]) for _ in range(4000)]
+    lens[1000] = 200_000
+    lens[2500] = 65536 - 1024 - 512 - 8
+    lens[2501] = 65536 - 1024 - 512
+    lens[2502] = 65536 - 1024 - 512 + 8
+    lens[-1] = 70_001
+    reads = [bytes(rng.choice(alphabet) for _ in range(n)) if n < 5000 else bytes(rng.choice(b"ACGTN") for _ in range(1000)) * (n // 1000) + b"A" * (n % 1000)
+             for n in lens]
+    buf = b"".join(reads)
+    off = np.zeros(len(reads) + 1, np.uint64)
+    np.cumsum([len(r) for r in reads], out=off[1:])
+    n_pos_max = sum((len(r) + 8) & ~7 for r in reads)
+    padded = L.ntsm_padded_positions(n_pos_max)
+    cbuf = ctypes.create_string_buffer(buf, len(buf) + 1)
+    try:
+        L.ntsm_pack_isa(isa)
+        outs = []
+        for streaming in (0, 1):
+            b2 = _aligned(padded // 16, np.uint32, 0xAB)
+            mk = _aligned(padded // 32, np.uint32, 0xCD)
+            n = L.ntsm_pack_reads2(ctypes.cast(cbuf, ctypes.c_void_p), off.ctypes.data, len(reads), b2.ctypes.data, mk.ctypes.data, None, streaming)
+            assert n == n_pos_max
+            outs.append((b2.copy(), mk.copy()))
+    finally:
+        L.ntsm_pack_isa(b"")
+    assert np.array_equal(outs[0][1], outs[1][1])                     # N-mask plane: every word, padding included
+    # base codes under invalid positions are don't-care inside a read's padding; compare them where the mask says valid
+    valid = ~np.unpackbits(outs[0][1].view(np.uint8), bitorder="little").astype(bool)
+    c0 = np.unpackbits(outs[0][0].view(np.uint8), bitorder="little").reshape(-1, 2)
+    c1 = np.unpackbits(outs[1][0].view(np.uint8), bitorder="little").reshape(-1, 2)
+    assert np.array_equal(c0[valid], c1[valid])
+
+
 def test_packer_reads_nothing_past_a_page_edge(L):
     """A read that ends on the last byte before an unmapped page is packed without touching that page."""
     import mmap
@@ -333,3 +381,22 @@ def test_site_table_parallel_first_wins_with_many_duplicates(L, oracle, tmp_path
         out = subprocess.run([ref, "-d", "-s", str(p), str(reads)], capture_output=True, text=True)
         want = [l for l in out.stderr.splitlines() if "k-mer collision" in l]
         assert s.warnings == want
+
+
+def test_numa_helpers_parse_and_stay_out_of_the_way_on_one_node_hosts(L):
+    """numa.cpp: the cpulist parser (sysfs format) and the node count; with one node nothing is pinned or bound."""
+    import ctypes
+    L.ntsm_numa_parse_cpulist.restype = ctypes.c_int
+    L.ntsm_numa_parse_cpulist.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+    out = (ctypes.c_int * 64)()
+    n = L.ntsm_numa_parse_cpulist(b"0-3,8,10-11\n", out, 64)
+    assert list(out[:n]) == [0, 1, 2, 3, 8, 10, 11]
+    assert L.ntsm_numa_parse_cpulist(b"", out, 64) == 0
+    assert L.ntsm_numa_parse_cpulist(b"5", out, 64) == 1 and out[0] == 5
+    L.ntsm_numa_nodes.restype = ctypes.c_int
+    nodes = L.ntsm_numa_nodes()
+    want = len([d for d in os.listdir("/sys/devices/system/node") if re.fullmatch(r"node\d+", d)]) if os.path.isdir("/sys/devices/system/node") else 1
+    assert nodes == max(1, want)
+    before = os.sched_getaffinity(0)
+    # a bulk insert on a box without CUDA fails early; the calling thread's affinity must be untouched either way
+    assert os.sched_getaffinity(0) == before
