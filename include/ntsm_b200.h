@@ -107,7 +107,8 @@ int ntsm_load_sites(ntsm_ctx *ctx, const uint64_t *kmer_hash, const uint8_t *era
 int ntsm_load_siteset(ntsm_ctx *ctx, const ntsm_sites *s);
 /* Measurement / test knobs, to be set before ntsm_load_sites; every setting gives the same counts (the
  * pre-filters in front of the exact table only ever let too many windows through).  Names:
- *   "kernel"       0 = generic kernel (one k-mer-bitmap probe per position), 1 = paired seeds (k >= 17), -1 = automatic
+ *   "kernel"       0 = generic kernel (one k-mer-bitmap probe per position), 1 = paired seeds (k >= 17), 2 = wide paired
+ *                  seeds (k >= 19; a 1 GiB level-1 table sized for HBM, for panels of millions of k-mers), -1 = automatic
  *   "pair_fold"    paired-seed table folded 2^n : 1 (0..4), -1 = automatic (1; 0 above 5 M site k-mers)
  *   "filter_bits"  log2 of the k-mer bitmap's bits (10..32), 0 = automatic (~80 bits per site k-mer)
  *   "launch_shape" pair kernel CTA shape: 0 = 1024x1, 1 = 1024x2 (default), 2 = 512x4, 3 = 256x8 per SM

@@ -58,7 +58,7 @@ struct ntsm_ctx {
 	int sm_count = 148;
 	int numa_node = -1;                     // the GPU's NUMA node when the host has more than one and says which (numa.h)
 	// options (ntsm_ctx_set_option, before ntsm_load_sites); -1 / 0 = decide from the panel
-	int opt_kernel = -1;                    // 0 generic (one k-mer-bitmap probe per position), 1 paired seeds
+	int opt_kernel = -1;                    // 0 generic (one k-mer-bitmap probe per position), 1 paired seeds, 2 wide paired seeds (large panels)
 	int opt_pair_fold = -1;                 // paired-seed table folded 2^fold : 1
 	int opt_filter_bits = 0;                // log2 bits of the k-mer bitmap
 	int opt_shape = 1;                      // pair kernel launch shape: 0 = 1024x1, 1 = 1024x2 (default), 2 = 512x4, 3 = 256x8
@@ -239,7 +239,7 @@ extern "C" void ntsm_ctx_destroy(ntsm_ctx *c)
 extern "C" int ntsm_ctx_set_option(ntsm_ctx *c, const char *name, int value)
 {
 	if (!c || !name) return fail(c, NTSM_ERR_ARG, "ntsm_ctx_set_option: null argument");
-	if (!strcmp(name, "kernel")) c->opt_kernel = value < 0 ? -1 : (value ? 1 : 0);
+	if (!strcmp(name, "kernel")) c->opt_kernel = value < 0 ? -1 : std::min(2, value);
 	else if (!strcmp(name, "pair_fold")) c->opt_pair_fold = value < 0 ? -1 : std::min(kPairFoldMax, value);
 	else if (!strcmp(name, "filter_bits")) c->opt_filter_bits = value <= 0 ? 0 : std::min(32, std::max(10, value));
 	else if (!strcmp(name, "launch_shape")) c->opt_shape = std::min(3, std::max(0, value));
@@ -265,9 +265,11 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 	if (cap > (1ull << 31)) return fail(c, NTSM_ERR_ARG, "too many site k-mers (%llu)", (unsigned long long)live);
 
 	// which count kernel will run decides which pre-filter structures are built
+	// (k >= 17: paired seeds.  The wide table sized for HBM -- option kernel = 2, k >= 19 -- was built for panels of
+	// millions of k-mers and measured no faster than the 14-mer table there: 295 vs 319 Gbases/s, pair.cuh.)
 	int kernel = k >= (uint32_t)kPairMinK ? 1 : 0;
-	if (c->opt_kernel >= 0 && kernel) kernel = c->opt_kernel;
-	const int pm = pair_seed_len((int)k);
+	if (c->opt_kernel >= 0 && kernel) kernel = c->opt_kernel == 2 && k < 19 ? 1 : c->opt_kernel;
+	const int pm = kernel == 2 ? kWideM : pair_seed_len((int)k);
 	// panels far larger than the human one (cfg 5: 26 M k-mers) saturate a folded pair table and nothing
 	// stays in L2 anyway: measured 318 (unfolded) vs 241 Gbases/s (profiles/r01v12_sweep_cfg5.jsonl)
 	int fold = live > 5000000 ? 0 : kPairFoldDefault;
@@ -280,7 +282,7 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 	while (fbits < 30 && (1ull << fbits) < 20ull * 2ull * live) ++fbits;
 	if (c->opt_filter_bits) fbits = (uint32_t)c->opt_filter_bits;
 	const size_t filter_words = (1ull << fbits) / 32;
-	const size_t pair_n = kernel == 1 ? pair_words(pm) >> fold : 0;
+	const size_t pair_n = kernel == 2 ? kWideBytes / 4 : kernel == 1 ? pair_words(pm) >> fold : 0;
 
 	cudaFree(c->d_probe); cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_allele_off); cudaFree(c->d_rows);
 	c->d_probe = c->d_pair = c->d_filter = nullptr; c->d_table = nullptr; c->d_counts = nullptr; c->d_allele_off = nullptr; c->d_rows = nullptr;
@@ -292,7 +294,7 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 		for (int attempt = 0; attempt < 8; ++attempt) {
 			CU(c, cudaMalloc(&c->d_probe, bytes));
 			const uintptr_t a = (uintptr_t)c->d_probe, z = a + std::max<size_t>(4, pair_n * 4) - 1;
-			if ((a >> 32) == (z >> 32)) break;
+			if (kernel != 1 || (a >> 32) == (z >> 32)) break;
 			rejected.push_back(c->d_probe);
 			c->d_probe = nullptr;
 		}
@@ -355,7 +357,7 @@ extern "C" int ntsm_load_sites(ntsm_ctx *c, const uint64_t *kmer_hash, const uin
 		BuildParams B;
 		B.hash = d_hash; B.erased = d_erased; B.n_kmers = n_kmers; B.k = k;
 		B.table = c->d_table; B.table_mask = (uint32_t)(cap - 1); B.filter = c->d_filter; B.filter_shift = 32 - fbits;
-		B.pair = c->d_pair; B.pair_m = (uint32_t)pm; B.pair_word_mask = pair_word_mask(pm, fold); B.err = d_err;
+		B.pair = c->d_pair; B.wide = kernel == 2; B.pair_m = (uint32_t)pm; B.pair_word_mask = kernel == 1 ? pair_word_mask(pm, fold) : 0; B.err = d_err;
 		if (n_kmers) {
 			build_tables_kernel<<<(n_kmers + 255) / 256, 256, 0, st>>>(B);
 			CU(c, cudaGetLastError());
@@ -459,7 +461,7 @@ static int launch_count(ntsm_ctx *c, const uint2 *d_bases, const uint32_t *d_mas
 	P.nmask = d_mask;
 	P.n_chunks = (n_pos + 31) / 32;
 	P.pair = c->d_pair;
-	P.pair_off_mask = pair_word_mask(c->pair_m, c->pair_fold) << 2;
+	P.pair_off_mask = c->kernel == 1 ? pair_word_mask(c->pair_m, c->pair_fold) << 2 : 0;
 	P.pair_bshift = 2 * (uint32_t)c->pair_m;
 	P.filter = c->d_filter;
 	P.filter_shift = 32 - c->filter_bits;
@@ -470,7 +472,13 @@ static int launch_count(ntsm_ctx *c, const uint2 *d_bases, const uint32_t *d_mas
 	P.counts = c->d_counts;
 	P.totals = c->launch_totals ? c->launch_totals : c->d_totals;
 	cudaError_t le;
-	if (c->kernel == 1) {
+	if (c->kernel == 2) {
+		const uint64_t groups = (P.n_chunks + kGroupChunks - 1) / kGroupChunks;
+		// one CTA of 1024 threads per SM with up to 64 registers each: the eight probe loads of a chunk need their
+		// own registers to be in flight together (at 32 registers ptxas reuses them and the loads queue up)
+		const unsigned gs1 = (unsigned)std::min<uint64_t>((groups + 31) / 32, (uint64_t)c->sm_count);
+		le = launch_with_window(c, count_kernel_wide<1024, 1>, gs1, 1024, st, P);
+	} else if (c->kernel == 1) {
 		// persistent: MINB CTAs per SM (fewer when the batch has fewer 31-chunk groups than that many CTAs have warps)
 		const uint64_t groups = (P.n_chunks + kGroupChunks - 1) / kGroupChunks;
 		static const int shape[4][2] = { { 1024, 1 }, { 1024, 2 }, { 512, 4 }, { 256, 8 } };
@@ -1275,6 +1283,7 @@ extern "C" const char *ntsm_ctx_kernel_name(const ntsm_ctx *c)
 {
 	if (!c) return "";
 	if (c->kernel == 0) return "count_kernel_generic";
+	if (c->kernel == 2) return "count_kernel_wide<1024,1>";
 	if (c->cfg.k != 19) return "count_kernel_pair<0,1024,2>";
 	static const char *names[4] = { "count_kernel_pair<19,1024,1>", "count_kernel_pair<19,1024,2>", "count_kernel_pair<19,512,4>", "count_kernel_pair<19,256,8>" };
 	return names[c->opt_shape];

@@ -180,6 +180,7 @@ struct BuildParams {
 	uint32_t *filter;
 	uint32_t filter_shift;
 	uint32_t *pair;             // zeroed; nullptr when the generic kernel will run
+	int wide;                   // 1: `pair` is the wide table (64-byte entries, 16-mers 4 apart: pair.cuh)
 	uint32_t pair_m;            // seed length of the pair table
 	uint32_t pair_word_mask;    // words of the (folded) pair table - 1
 	int *err;                   // [0] 0 ok, 1 hash out of range, 2 duplicate; [1] the offending index
@@ -217,7 +218,15 @@ __global__ void build_tables_kernel(const BuildParams B)
 		uint32_t word, ra, rb;
 		filter_slots(filter_mix((uint32_t)s, (uint32_t)(s >> 32), B.k), B.filter_shift, word, ra, rb);
 		atomicOr(B.filter + word, (1u << ra) | (1u << rb));
-		if (B.pair) {
+		if (B.pair && B.wide) {
+			// wide table (pair.cuh): every 16-mer of the k-mer, once per role, into the 32-byte entry of its 12 shared bases
+			for (uint32_t j = 0; j + 16 <= B.k; ++j) {
+				const uint32_t v = (uint32_t)(s >> (2 * j));
+				const uint32_t a = v & 0x7Fu, b = (v >> 24) & 0x7Fu;
+				atomicOr(B.pair + (size_t)(v >> 8) * 8 + (a >> 5), 1u << (a & 31u));                    // role A: v's last 12 bases are shared
+				atomicOr(B.pair + (size_t)(v & 0xFFFFFFu) * 8 + 4 + (b >> 5), 1u << (b & 31u));        // role B: v's first 12 bases
+			}
+		} else if (B.pair) {
 			// paired-seed table (pair.cuh): every M-mer of the k-mer entered once per role
 			const uint32_t M = B.pair_m, vm = (uint32_t)((1ull << (2 * M)) - 1), core = (uint32_t)((1ull << (2 * (M - 2))) - 1);
 			for (uint32_t j = 0; j + M <= B.k; ++j) {

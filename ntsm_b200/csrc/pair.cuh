@@ -198,4 +198,134 @@ __global__ void __launch_bounds__(THREADS, MINB) count_kernel_pair(const CountPa
 	flush_tallies(tk, hits, P.totals);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Wide paired seeds: an EXPERIMENT for panels whose tables cannot stay in L2 anyway (BASELINE cfg 5:
+// 10^6 sites, 26 M k-mers, 64 M distinct seeds), kept as option "kernel" = 2 with its parity tests.
+// It is NOT the default for such panels: measured 295 Gbases/s against 319 for count_kernel_pair.
+//
+// ncu on that panel with the 14-mer table (profiles/r02a_cfg5_count_ncu_summary.txt): DRAM-bound --
+// 72 % of peak DRAM throughput, 18.5 bytes read per base, L2 sector hit rate 16 %.  Every level-1
+// word, level-2 word and exact-table slot is a random access that misses L2.  The idea here: a sparser
+// level 1 sized for HBM instead of L2, so that level 2 and the exact table all but vanish:
+//   seeds are 16-mers 4 apart (A at p, B at p + 4), sharing 12 bases; those index one 32-byte entry
+//   -- one sector: a 128-bit map of A's four leading bases and a 128-bit map of B's four trailing
+//   bases (8 selector bits folded to 7).  4^12 entries = 512 MiB, ~3 % full for 10^6 sites.  A closes
+//   the windows starting in [p-3, p], B closes [p+1, p+4]: 8 windows per entry, pairs at local
+//   positions 0, 8, 16, 24 as above.
+// What the three versions taught (profiles/r02h_cfg5_wide_ncu_summary.txt, r02i_cfg5_wide_ncu_summary.txt):
+//   1. 64-byte entries, the two maps in separate sectors, loads behind branches: 172 Gbases/s.  A thread
+//      had one load in flight instead of eight, and both sectors of an entry missed at once.
+//   2. predicated loads: eight predicates are more than a thread has; ptxas strings the loads out again.
+//   3. (this one) one sector per entry, unconditional loads (a probe nobody needs reads word 0): all eight
+//      in flight, L1 serves the second map of an entry (41 % L1 hit rate), L2 sector requests fall by 40 % --
+//      and DRAM bytes stay where they were: 69.8 GB against 73.8 GB per 4 Gbases.  An L2 miss costs a whole
+//      128-byte line of DRAM traffic here whichever sector was asked for (2.32 G sectors read by L2 for 0.63 G
+//      that missed; cudaLimitMaxL2FetchGranularity changes nothing, profiles/r02b_l2fetch_granularity.jsonl),
+//      so the wall for this panel is ~32 G random line fetches per second, ~4.5 per 32 positions with either
+//      table, and the wide kernel's 48 registers leave it half the warps to hide them with (63 vs 72 % of
+//      peak DRAM throughput).  Beating it needs fewer MISSES per position, i.e. a selective level 1 that is
+//      L2-resident, which 64 M seeds do not allow in ~48 MiB.
+// k >= 19 (a window must hold a 16-mer at 4 consecutive offsets).  Same tail, same exact path.
+constexpr int kWideM = 16;
+constexpr size_t kWideEntries = (size_t)1 << 24;            // 4^12 cores
+constexpr size_t kWideBytes = kWideEntries * 32;
+
+NTSM_HD void wide_slots_a(uint32_t v, uint32_t &word, uint32_t &bit)      // 16-mer v in role A: last 12 bases shared
+{
+	const uint32_t a = v & 0x7Fu;
+	word = (v >> 8) * 8 + (a >> 5);
+	bit = a & 31u;
+}
+NTSM_HD void wide_slots_b(uint32_t v, uint32_t &word, uint32_t &bit)      // 16-mer v in role B: first 12 bases shared
+{
+	const uint32_t b = (v >> 24) & 0x7Fu;
+	word = (v & 0xFFFFFFu) * 8 + 4 + (b >> 5);
+	bit = b & 31u;
+}
+
+// The four wide probes of a chunk.  x[q] = the 16 bases from pair q's position, t8[q] = the 4 bases after
+// them (8 bits), need = valid windows in pair coordinates (bit 8q + t <-> window 8q - 3 + t).  Returns
+// the windows that may still be site k-mers.  The table lives in HBM: a thread that waits for each DRAM
+// round trip in turn is eight times slower than one that has its eight loads in flight together.  So
+// nothing here is conditional -- a probe nobody needs reads word 0 of the table (always cached) instead
+// of being branched or predicated around (eight predicates are more than an SM has per thread, and
+// ptxas then strings the loads out again) -- and the answers are masked by `need` at the end.
+__device__ __forceinline__ uint32_t wide_probe4(const uint32_t (&x)[4], const uint32_t (&t8)[4], uint32_t need, const uint32_t *__restrict__ tab)
+{
+	uint32_t wa[4], wb[4];
+#pragma unroll
+	for (int q = 0; q < 4; ++q) {
+		const uint32_t entry = (x[q] >> 8) << 3;                       // word index of the 32-byte entry
+		const uint32_t ia = entry + ((x[q] & 0x7Fu) >> 5), ib = entry + 4u + ((t8[q] & 0x7Fu) >> 5);
+		wa[q] = __ldg(tab + ((need >> (8 * q)) & 0x0Fu ? ia : 0u));
+		wb[q] = __ldg(tab + ((need >> (8 * q)) & 0xF0u ? ib : 0u));
+	}
+	uint32_t r = 0;
+#pragma unroll
+	for (int q = 0; q < 4; ++q) {
+		const uint32_t ra = (0u - ((wa[q] >> (x[q] & 31u)) & 1u)) & 0x0Fu;       // bit (a & 31) of A's word, a = x & 0x7F
+		const uint32_t rb = (0u - ((wb[q] >> (t8[q] & 31u)) & 1u)) & 0xF0u;
+		r |= (ra | rb) << (8 * q);
+	}
+	return r & need;
+}
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) count_kernel_wide(const CountParams P)
+{
+	__shared__ uint16_t s_cand[THREADS / 32][kCandSlots];
+	const uint32_t k = P.k;
+	const uint32_t wshift = P.filter_shift + 5;
+	const uint32_t lane = threadIdx.x & 31;
+	uint16_t *cand = s_cand[threadIdx.x >> 5];
+	uint32_t tk = 0, hits = 0;
+
+	const uint64_t n_groups = (P.n_chunks + kGroupChunks - 1) / kGroupChunks;
+	const uint64_t n_warps = (uint64_t)gridDim.x * (THREADS / 32);
+	const uint64_t gw = (uint64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+
+	uint2 own_n = make_uint2(0, 0);
+	uint32_t m0_n = 0xFFFFFFFFu;
+	if (gw < n_groups && gw * kGroupChunks + lane <= P.n_chunks) {
+		own_n = __ldcs(P.bases + gw * kGroupChunks + lane);
+		m0_n = __ldcs(P.nmask + gw * kGroupChunks + lane);
+	}
+	for (uint64_t g = gw; g < n_groups; g += n_warps) {
+		const uint64_t c = g * kGroupChunks + lane;
+		const uint64_t cn = c + n_warps * kGroupChunks;
+		const uint2 own = own_n;
+		uint32_t m0 = m0_n;
+		own_n = make_uint2(0, 0);
+		m0_n = 0xFFFFFFFFu;
+		if (g + n_warps < n_groups && cn <= P.n_chunks) {
+			own_n = __ldcs(P.bases + cn);
+			m0_n = __ldcs(P.nmask + cn);
+		}
+		uint2 nxt;
+		nxt.x = __shfl_down_sync(0xffffffffu, own.x, 1);
+		nxt.y = __shfl_down_sync(0xffffffffu, own.y, 1);
+		const uint32_t m1 = __shfl_down_sync(0xffffffffu, m0, 1);
+		if (lane == 31 || c >= P.n_chunks) m0 = 0xFFFFFFFFu;
+		const uint32_t w[4] = { own.x, own.y, nxt.x, nxt.y };
+		const uint32_t valid = valid_windows(m0, m1, k);
+		tk += __popc(valid);
+
+		// pair q (local position 8q) closes the windows starting at [8q - 3, 8q + 5): in pair coordinates
+		// t = i + 3 that is t in [8q, 8q + 8).  The three windows before position 0 belong to the previous
+		// lane; this lane's last three are closed by the next lane's pair 0.
+		uint32_t pv = __shfl_up_sync(0xffffffffu, valid, 1);
+		if (lane == 0) pv = 0;
+		const uint32_t n3 = __funnelshift_l(pv, valid, 3);        // bit i + 3 <-> window i, i = -3 .. 28
+
+		const uint32_t xs[4] = { own.x, __funnelshift_r(own.x, own.y, 16), own.y, __funnelshift_r(own.y, nxt.x, 16) };
+		const uint32_t ts[4] = { own.y & 0xFFu, (own.y >> 16) & 0xFFu, nxt.x & 0xFFu, (nxt.x >> 16) & 0xFFu };
+		const uint32_t plo = wide_probe4(xs, ts, n3, P.pair);
+		const uint32_t nb = __shfl_down_sync(0xffffffffu, plo, 1);  // the next chunk's pair 0 closes windows 29-31
+		const uint32_t pass = __funnelshift_r(plo, nb, 3) & valid;
+
+		pooled_tail(P, w, pass, lane, cand, wshift, k, hits);
+	}
+	flush_tallies(tk, hits, P.totals);
+}
+
 }  // namespace ntsm

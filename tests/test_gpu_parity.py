@@ -155,6 +155,8 @@ def test_pair_kernel_other_k_on_a_large_panel(oracle, tmp_path, k):
     reads += [bytes(rng.choice(b"ACGT") for _ in range(rng.randrange(0, 300))) for _ in range(500)]
     for bb in (40001, 1 << 18):
         ofp = _check_against_oracle(oracle, sites, reads, k=k, batch_bases=bb)
+    if k >= 19:                     # the wide table (16-mers 4 apart) takes any k >= 19 too
+        _check_against_oracle(oracle, sites, reads, k=k, batch_bases=1 << 16, options={"kernel": 2})
     assert ofp.total_counts > 5 * len(reads)
 
 
@@ -426,7 +428,8 @@ def test_cfg3_ont_like_long_reads_vs_oracle(oracle):
 
 # ---------------------------------------------------------------- kernel variants
 @pytest.mark.parametrize("opts", [{"kernel": 0}, {"kernel": 1}, {"kernel": 1, "launch_shape": 0}, {"kernel": 1, "launch_shape": 2},
-                                  {"kernel": 1, "launch_shape": 3}, {"kernel": 1, "l2_persist": 0}, {"kernel": 1, "filter_bits": 20}])
+                                  {"kernel": 1, "launch_shape": 3}, {"kernel": 1, "l2_persist": 1}, {"kernel": 1, "filter_bits": 20},
+                                  {"kernel": 2}, {"kernel": 2, "filter_bits": 22}])
 def test_every_k19_kernel_variant_vs_oracle(oracle, opts):
     """ntsm_ctx_set_option picks the count kernel (generic / paired seeds), its launch shape, the L2
     access-policy window and the k-mer bitmap size: each must give the oracle's per-k-mer counters."""
@@ -436,8 +439,9 @@ def test_every_k19_kernel_variant_vs_oracle(oracle, opts):
     _check_against_oracle(oracle, PANEL, reads, batch_bases=1 << 18, options=opts)
 
 
-def test_pair_kernel_dense_hits_and_every_phase(oracle):
-    """Stress for count_kernel_pair (pair.cuh): reads that are nothing but site windows back to back
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_pair_kernel_dense_hits_and_every_phase(oracle, kernel):
+    """Stress for count_kernel_pair and count_kernel_wide (pair.cuh): reads that are nothing but site windows back to back
     (nearly every seed marked, so the pooled tail runs several rounds per warp), read lengths that
     walk the read starts through every chunk phase and lane, N runs right before and after the
     seed positions, and batches of odd sizes so the last group is ragged."""
@@ -456,7 +460,7 @@ def test_pair_kernel_dense_hits_and_every_phase(oracle):
         reads.append(revcomp(r) if rng.random() < 0.5 else r)
     reads += [wins[i % len(wins)][: 19 + i % 13].encode() for i in range(600)]        # 19..31-base reads: 1..13 windows each
     for bb in (1 << 12, 40001, 1 << 20):
-        ofp = _check_against_oracle(oracle, PANEL, reads, batch_bases=bb, n_buffers=3)
+        ofp = _check_against_oracle(oracle, PANEL, reads, batch_bases=bb, n_buffers=3, options={"kernel": kernel})
     assert ofp.total_counts > 3 * len(reads)
 
 
