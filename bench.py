@@ -295,6 +295,29 @@ def ours(args):
             dist.destroy_process_group()
         return
 
+    # ---- other regimes, kernel-resident, one GPU only (BASELINE cfg 1 and cfg 3 shapes; cfg 5 needs its 10^6-site
+    #      panel, 30 s to build: `--kernel-only --synthetic-sites 1000000`, numbers in DESIGN.md) ---------------
+    regimes = None
+    if world == 1 and not args.no_cpu:
+        regimes = {}
+        for name, gmb, rl, er, gb in (("cfg1_like_dense_hits_30Mb_genome", 30, READ_LEN, 0.01, 10.0), ("cfg3_like_20kb_reads_7.5pct_error", args.genome_mb, 20000, 0.075, 10.0)):
+            g2 = genome if gmb == args.genome_mb else synth.Genome(gmb * 1_000_000, wc, wl, 2, dev)
+            nr = int(gb * 1e9 / rl) // 32 * 32
+            b2, m2, np2, nb2 = synth.make_packed_shard(g2, nr, rl, er, seed=77, chunk_reads=(1 << 20) if rl == READ_LEN else max(32, ((1 << 27) // rl) // 32 * 32))
+            for _ in range(3):
+                fp.reset_async(); fp.count_packed_device(b2.data_ptr(), m2.data_ptr(), np2, nb2, stream.cuda_stream); fp.reduce_async()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(stream)
+            for _ in range(3):
+                fp.reset_async(); fp.count_packed_device(b2.data_ptr(), m2.data_ptr(), np2, nb2, stream.cuda_stream); fp.reduce_async()
+            r1.record(stream)
+            torch.cuda.synchronize()
+            rows2 = fp.finalize()
+            regimes[name] = {"value": nb2 / (r0.elapsed_time(r1) / 3 / 1000) / 1e9, "unit": "Gbases/s", "gbases": nb2 / 1e9,
+                             "hits_per_kilobase": 1000.0 * float(rows2[4][1]) / nb2}
+            del b2, m2, g2
+        torch.cuda.synchronize()
+
     # ---- strong scaling: the SAME 100-Gbase job cut N ways (this rank counts the first 1/N of its shard) ----
     strong = None
     if world > 1:
@@ -381,7 +404,8 @@ def ours(args):
         tg = time.time()
         fpaths = synth.write_fastq_set(genome, f_total, READ_LEN, 0.01, 7000 + rank, n_files, fdir)
         fbytes = sum(os.path.getsize(p) for p in fpaths)
-        f_passes = max(1, env_int("NTSM_BENCH_FILE_PASSES", 3))
+        # every file is read f_passes times per step: the box's whole file set is ~7 Gbases, a step should last ~1 s
+        f_passes = max(1, env_int("NTSM_BENCH_FILE_PASSES", 3 * min(4, local_world)))
         log("rank %d: %d FASTQ files, %.2f GB, written in %.1f s" % (rank, len(fpaths), fbytes / 1e9, time.time() - tg))
 
         def job_files():
@@ -421,7 +445,26 @@ def ours(args):
             g_ms, g_rows = timed_host_job(job_gz, steps=min(3, args.steps), warm=1)
             gz = {"value": float(g_rows[4][2]) / (g_ms / 1000) / 1e9, "unit": "Gbases/s", "ms_per_step": g_ms, "files": len(gpaths),
                   "gz_bytes": gbytes, "threads": host_threads,
-                  "api": "ntsm_count_files on 8 .fq.gz (gzip -6): own inflate, spare -t threads decode chunks of each single member in parallel"}
+                  "api": "ntsm_count_files on 8 .fq.gz (gzip -6), one parser thread per file with our own inflate (1 spare thread each: too few to cut members)"}
+            # two whole-run files and 16 threads: the reference (and any one-thread-per-file reader) leaves 14 cores idle;
+            # here 7 helper threads per file inflate chunks of the single gzip member in parallel (pargz.cpp).  Timed with and without.
+            two = gpaths[:2]
+
+            def job_gz2():
+                fp_a.reset()
+                fp_a.computeCounts(two, threads=host_threads)
+                return fp_a.finalize()
+
+            p_ms, p_rows = timed_host_job(job_gz2, steps=min(3, args.steps), warm=1)
+            os.environ["NTSM_PARALLEL_GZ"] = "0"
+            try:
+                s_ms, s_rows = timed_host_job(job_gz2, steps=min(3, args.steps), warm=1)
+            finally:
+                del os.environ["NTSM_PARALLEL_GZ"]
+            gz["two_files_16_threads"] = {"value": float(p_rows[4][2]) / (p_ms / 1000) / 1e9, "unit": "Gbases/s", "ms_per_step": p_ms,
+                                          "one_thread_per_member_value": float(s_rows[4][2]) / (s_ms / 1000) / 1e9,
+                                          "same_counts": bool(np.array_equal(p_rows[0], s_rows[0]) and int(p_rows[4][0]) == int(s_rows[4][0])),
+                                          "note": "2 .fq.gz, -t 16: each single gzip member inflated by 7 helper threads (pargz) vs one thread per member"}
     finally:
         shutil.rmtree(fdir, ignore_errors=True)
 
@@ -568,6 +611,7 @@ def ours(args):
                            "ms_per_step": e2e_ms, "gbases_per_step_per_gpu": e_bases / 1e9,
                            "api": "ntsm_count_packed_host + ntsm_finalize (pinned host stream already packed)"},
             "strong_scaling": strong,
+            "other_regimes_kernel_resident": regimes,
             "gpu_launches": int(launches), "clocks": clocks,
             "check": dict(check, e2e_TK=int(f_rows[4][0]), e2e_ascii_TK=int(a_rows[4][0]), e2e_packed_TK=e2e_check,
                           ascii_equals_packed=ascii_check, n_gpu_equals_1_gpu=n_equals_1),

@@ -115,9 +115,11 @@ int run(Bulk &bk, uint32_t threads, uint64_t total_bases)
 	const uint64_t avg = total_bases / bk.n_reads + 8;               // a read spans its bases + separator, rounded up to 8 positions
 	bk.reads_per_block = std::max<uint64_t>(1, (cap - cap / 64) / avg);
 	const uint64_t n_blocks = (bk.n_reads + bk.reads_per_block - 1) / bk.reads_per_block;
-	// page-locked input: one feeder per GPU next to the host packers (threads == 0: feeders only)
-	const bool pinned = ntsm_ctx_device_pack(bk.ctxs[0], threads / bk.n_ctx) && ntsm_host_is_pinned(bk.buf) != 0;
-	uint32_t nt = threads ? threads : (pinned ? 0 : 1);
+	// page-locked input: the GPUs can decode + pack it themselves (one feeder thread per GPU) -- instead of the host
+	// packers, next to them, or not at all: ntsm_ctx_device_pack (ctx.cu) holds the rule and the measurements behind it
+	const int mode = ntsm_host_is_pinned(bk.buf) ? ntsm_ctx_device_pack(bk.ctxs[0], threads / bk.n_ctx) : 0;
+	const bool pinned = mode != 0;
+	uint32_t nt = mode == 2 ? 0 : (threads ? threads : (pinned ? 0 : 1));
 	if (nt > n_blocks) nt = (uint32_t)n_blocks;
 	std::vector<std::thread> pool;
 	if (pinned)

@@ -1,7 +1,7 @@
 // cli.cpp -- ntsm_main: the ntsmCount command line, option for option
 // (src/ntSeqMatchCount.cpp:53-184, src/Options.h:20-61), driving the GPU path through the C ABI.
 // Additions (long options only, nothing the reference parses changes meaning):
-//   --gpus N          use N GPUs of this box (default 1; 0 = all)
+//   --gpus N          use N GPUs of this box (default 1; 0 = one per 16 parser threads)
 //   --batch-bases B   stream positions per pinned batch (default 2^25; 2^22 with -m)
 //   --dump-kmer-counts F    also write every k-mer's counter + the tallies to F (merge.cpp's format)
 //   --merge-kmer-counts     FILES are such dumps of shards of ONE sample: add them per k-mer, then print
@@ -13,6 +13,7 @@
 #include <string.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
 #include <fstream>
 #include <iostream>
@@ -59,7 +60,8 @@ const char kHelp[] =
     "  -h, --help             Display this dialog.\n"
     "  -v, --verbose          Display verbose output.\n"
     "      --version          Print version information.\n"
-    "      --gpus = INT       GPUs of this box to use (0 = all). [1]\n"
+    "      --gpus = INT       GPUs of this box to use (0 = one per 16\n"
+    "                         threads, as many as -t can feed). [1]\n"
     "      --batch-bases = INT  positions per pinned batch. [2^25]\n"
     "      --dump-kmer-counts = STR  also write k-mer level counts to\n"
     "                         this file (for --merge-kmer-counts).\n"
@@ -140,7 +142,10 @@ extern "C" int ntsm_main(int argc, char **argv)
 	std::vector<std::thread> warm;
 	{
 		const int nd = ntsm_device_count();
-		const int ng = gpus <= 0 || gpus > nd ? nd : gpus;
+		// --gpus 0 = as many as the parser threads can feed: file ingest is host-bound at ~2-4 Gbases/s per parser
+		// thread, one GPU takes 144 over PCIe, and every further CUDA context costs ~0.7 s to bring up (8 GPUs: 5.7 s)
+		if (gpus <= 0) gpus = (int)std::min<unsigned>((unsigned)std::max(1, nd), std::max(1u, (threads + 15) / 16));
+		const int ng = gpus > nd ? nd : gpus;
 		for (int g = 0; g < ng; ++g) warm.emplace_back([g] { ntsm_device_warmup(g); });
 	}
 	struct Joiner {
@@ -161,7 +166,7 @@ extern "C" int ntsm_main(int argc, char **argv)
 		std::cerr << PROGRAM ": no CUDA device found; this build has no CPU path" << std::endl;
 		return 1;
 	}
-	if (gpus <= 0 || gpus > n_dev) gpus = n_dev;
+	if (gpus <= 0 || gpus > n_dev) gpus = n_dev;            // (0 was resolved above; more than the box has = all)
 	ntsm_cfg cfg;
 	memset(&cfg, 0, sizeof cfg);
 	cfg.k = k;

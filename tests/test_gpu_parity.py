@@ -323,6 +323,40 @@ def test_m_cap_exact_vs_oracle_many_caps(oracle, tmp_path):
     assert n_early >= 3
 
 
+def test_m_cap_crossed_inside_a_read_longer_than_a_batch(oracle, tmp_path):
+    """-m with contig-sized reads: the cap is crossed by a piece of a read that spans several batches.  The
+    reference counts a whole read before it looks at the cap (processSingleRead, src/FingerPrint.hpp:473-487),
+    so the rest of that read is still counted -- and nothing after it."""
+    sites = os.path.join(GOLDEN, "shared", "sites300.fa")
+    rng = random.Random(23)
+    wins = _windows(sites)
+
+    def contig(n_parts):
+        parts = []
+        for _ in range(n_parts):
+            parts.append("".join(rng.choice("ACGT") for _ in range(rng.randrange(0, 300))))
+            parts.append(rng.choice(wins))
+        return "".join(parts).encode()
+
+    reads = [contig(3) for _ in range(20)] + [contig(400)] + [contig(3) for _ in range(20)] + [contig(700)] + [contig(5) for _ in range(50)]
+    assert max(map(len, reads)) > 100000
+    f = tmp_path / "contigs.fa"
+    f.write_bytes(b"".join(b">c%d\n%s\n" % (i, r) for i, r in enumerate(reads)))
+    n_early = 0
+    for cov, bb in ((0.1, 8192), (0.25, 8192), (0.25, 20000), (0.6, 8192), (0.9, 16384), (50.0, 8192)):
+        fp = ntsm_b200.FingerPrint(sites, cov_thresh=cov, batch_bases=bb)
+        fp.computeCounts([str(f)], threads=1)
+        o = oracle.fingerprint(sites, 19, False, cov)
+        o.count_file(str(f))
+        assert fp.printInfoSummary() == o.summary(), (cov, bb)
+        assert fp.counts_text() == o.counts_text(), (cov, bb)
+        assert np.array_equal(fp.kmer_counts(), o.lists()[2]), (cov, bb)
+        assert bool(fp.early_term) == o.early_term, (cov, bb)
+        n_early += o.early_term
+        fp.close()
+    assert n_early >= 4
+
+
 def test_m_cap_prefix_property(oracle, tmp_path):
     """-m, the weaker property that also holds where the stop stays batch-granular (several parser
     threads, where the reference itself is racy): whatever prefix of the file was consumed, the
