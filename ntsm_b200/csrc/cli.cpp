@@ -221,7 +221,8 @@ extern "C" int ntsm_main(int argc, char **argv)
 					t[0] += u[0]; t[1] += u[1]; t[2] += u[2];
 					reads += ntsm_ctx_reads(x);
 				}
-				std::cerr << "max count reached at " << (verbose > 2 ? reads : 0) << " reads, " << t[0] << " k-mers, " << t[1]
+				// (upstream bumps its read counter after the cap check, :67-72: the deciding read is not in it yet)
+				std::cerr << "max count reached at " << (verbose > 2 && reads ? reads - 1 : 0) << " reads, " << t[0] << " k-mers, " << t[1]
 				          << " total counts, and " << t[2] << " total bases " << std::endl;
 			}
 			std::cerr << "Reached desired (-m) threshold" << std::endl;   // FingerPrint.hpp:84-86

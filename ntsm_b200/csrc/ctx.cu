@@ -10,6 +10,7 @@
 #include <strings.h>
 
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -91,8 +92,8 @@ struct ntsm_ctx {
 	uint64_t done_kmers = 0, done_hits = 0, done_bases = 0;   // over completed batches
 	uint64_t submitted_bases = 0;
 	uint64_t submitted_reads = 0;           // reads begun in the packed batches submitted so far (m_totalReads, src/FingerPrint.hpp:72)
-	uint64_t launches = 0;
-	uint64_t h2d_bytes = 0, d2h_bytes = 0;  // copied over PCIe by this ctx's data path so far (batches, snapshots, result rows)
+	std::atomic<uint64_t> launches{0};
+	std::atomic<uint64_t> h2d_bytes{0}, d2h_bytes{0};  // copied over PCIe by this ctx's data path so far (batches, snapshots, result rows)
 	int async_error = 0;                    // a batch's event reported a device fault: sticky until the ctx is destroyed
 	// exact -m stop: the last batch submitted, a scratch tally, and what launch_count adds per hit
 	ntsm_batch *last_batch = nullptr;
@@ -1284,7 +1285,7 @@ int ntsm_ctx_numa_node(const ntsm_ctx *c) { return c->numa_node; }
 uint64_t ntsm_ctx_batch_bases(const ntsm_ctx *c) { return c->cfg.batch_bases; }
 void ntsm_set_thread_error(const char *text) { t_last_error = text; }
 
-extern "C" uint64_t ntsm_ctx_launches(const ntsm_ctx *c) { return c ? c->launches : 0; }
+extern "C" uint64_t ntsm_ctx_launches(const ntsm_ctx *c) { return c ? c->launches.load() : 0; }
 extern "C" const char *ntsm_ctx_kernel_name(const ntsm_ctx *c)
 {
 	if (!c) return "";
@@ -1296,8 +1297,8 @@ extern "C" const char *ntsm_ctx_kernel_name(const ntsm_ctx *c)
 }
 extern "C" void ntsm_ctx_pcie_bytes(const ntsm_ctx *c, uint64_t *h2d, uint64_t *d2h)
 {
-	if (h2d) *h2d = c ? c->h2d_bytes : 0;
-	if (d2h) *d2h = c ? c->d2h_bytes : 0;
+	if (h2d) *h2d = c ? c->h2d_bytes.load() : 0;
+	if (d2h) *d2h = c ? c->d2h_bytes.load() : 0;
 }
 extern "C" int ntsm_ctx_l2_window(const ntsm_ctx *c) { return c && c->l2_window ? (int)(c->l2_hit_ratio * 100.0f + 0.5f) : 0; }
 extern "C" uint64_t ntsm_ctx_probe_bytes(const ntsm_ctx *c) { return c ? c->probe_bytes : 0; }

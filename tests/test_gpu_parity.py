@@ -299,6 +299,25 @@ def test_m_cap_stops_after_the_same_read_as_the_reference(name, batch):
     assert keep(p.stderr.decode()) == keep(open(os.path.join(d, "stderr.txt")).read())
 
 
+@pytest.mark.parametrize("flag", ["-v", "-vvv"])
+def test_m_cap_verbose_line_matches_the_live_reference(ref_bin, flag):
+    """-v with -m prints "max count reached at R reads, K k-mers, C total counts, and B total bases" the moment the
+    cap is crossed (src/FingerPrint.hpp:477-484).  Compared with the reference binary run right here on the same
+    fixture; R only moves under -vvv upstream (:70-72), so -v prints 0 reads there and here."""
+    d, opts, files = _case_files("panel300_m1")
+    argv = json.load(open(os.path.join(d, "cmd.json")))["argv"]
+    ref = subprocess.run([ref_bin, flag] + argv, cwd=d, capture_output=True)
+    ours = subprocess.run([NTSMCOUNT, flag] + argv, cwd=d, capture_output=True)
+    assert ref.returncode == 0 and ours.returncode == 0
+    assert ours.stdout == ref.stdout
+    line = lambda t: [l.strip() for l in t.decode().splitlines() if l.startswith("max count reached")]
+    assert len(line(ref.stderr)) == 1
+    want, got = line(ref.stderr)[0], line(ours.stderr)[0]
+    assert got == want
+    order = [l.split()[0] for l in ours.stderr.decode().splitlines() if l.startswith(("Opening", "max", "Reached"))]
+    assert order == ["Opening", "Opening", "max", "Reached"]
+
+
 def test_m_cap_exact_vs_oracle_many_caps(oracle, tmp_path):
     """computeCounts with a cap, one thread: for a spread of caps and batch sizes the counts equal the
     oracle's read-by-read stop (src/FingerPrint.hpp:473-488), per k-mer."""
@@ -582,9 +601,11 @@ def test_host_register_makes_a_buffer_device_packable(oracle):
     try:
         fp = ntsm_b200.FingerPrint(sites, batch_bases=1 << 16)
         l0 = fp.launches
+        h0 = fp.pcie_bytes[0]
         fp.insertReadsFixed(mat.ctypes.data, L_, L_, n, threads=0)      # threads = 0: only the device packer can do the work
         assert fp.counts_text() == ofp.counts_text()
         assert fp.launches - l0 >= 2
+        assert fp.pcie_bytes[0] - h0 == mat.nbytes                       # every base crossed PCIe as one ASCII byte, nothing else did
         fp.close()
     finally:
         assert Lb.ntsm_host_unregister(mat.ctypes.data) == 0

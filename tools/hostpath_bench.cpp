@@ -1,7 +1,7 @@
 // hostpath_bench.cpp -- the host half of FingerPrint::computeCounts without a GPU: FastxReader -> Packer into a
 // reused buffer, one thread per file, to see what parse + pack cost per base.  Measurement tool.
 //   g++ -O3 -std=c++17 -pthread -I ntsm_b200/csrc tools/hostpath_bench.cpp ntsm_b200/csrc/{fastx,gzsource,inflate,pargz,pack}.cpp -lz -o /tmp/hostpath_bench
-//   /tmp/hostpath_bench [parse|pack] file...      (parse = reader only, pack = reader + packer)
+//   /tmp/hostpath_bench [parse|pack|packN] file...  (parse = reader only, pack = reader + packer, packN = with N helper threads per reader)
 #include <stdio.h>
 #include <string.h>
 
@@ -16,7 +16,8 @@
 int main(int argc, char **argv)
 {
 	if (argc < 3) return 1;
-	const bool do_pack = !strcmp(argv[1], "pack");
+	const bool do_pack = !strncmp(argv[1], "pack", 4);
+	const int helpers = argv[1][0] && argv[1][strlen(argv[1]) - 1] >= '1' && argv[1][strlen(argv[1]) - 1] <= '9' ? argv[1][strlen(argv[1]) - 1] - '0' : 0;   // "pack1": one helper thread per reader
 	const int nf = argc - 2;
 	std::atomic<uint64_t> bases{0}, reads{0};
 	const auto t0 = std::chrono::steady_clock::now();
@@ -24,7 +25,7 @@ int main(int argc, char **argv)
 	for (int i = 0; i < nf; ++i)
 		th.emplace_back([&, i] {
 			ntsm::FastxReader rd;
-			if (!rd.open(argv[2 + i], 0)) { fprintf(stderr, "cannot open %s\n", argv[2 + i]); return; }
+			if (!rd.open(argv[2 + i], helpers)) { fprintf(stderr, "cannot open %s\n", argv[2 + i]); return; }
 			const uint64_t cap = 1ull << 24;
 			std::vector<uint64_t> b(ntsm::padded_positions(cap) / 32 + 64);
 			std::vector<uint32_t> m(ntsm::padded_positions(cap) / 32 + 64);
