@@ -811,18 +811,19 @@ int ntsm_submit_ascii_var(ntsm_ctx *c, const char *buf, const uint64_t *off, uin
 // cudaHostAlloc / cudaHostRegister), else 0
 // Who packs a bulk of reads that lies in page-locked memory?  Returns 0 = the host packers, 1 = host packers and
 // a device feeder per GPU together, 2 = the feeders alone.  Measured (bench.py e2e_ascii legs, Gbases/s per box):
-//                          host packers   both    feeders alone
-//   1 GPU, 16 cores            109         106         51-54      (PCIe: a device-packed base costs 1 B of it, a host-packed one 0.375)
-//   2 GPUs, 16 cores each      112         113          95
-//   8 GPUs, 4 cores each       113         167         183        (host DRAM: 183 GB/s of DMA is all the box gives; packers only take from it)
+//                              host packers   both    feeders alone
+//   1 GPU,  16 cores per GPU       109         106         51-54     (PCIe: a device-packed base costs 1 B of it, a host-packed one 0.375)
+//   2 GPUs, 12 cores per GPU       112         130          95
+//   8 GPUs,  4 cores per GPU       113         167         183       (host DMA: 183 GB/s is all the box gives; packers only take from it)
 // The packers are bound by host DRAM (2.1 B of traffic per base) at ~110 Gbases/s per BOX however many GPUs there
-// are; the feeders by PCIe per GPU and by what the host can DMA in total.  Mixing the two never beat the better
-// one alone by more than 1 %, and loses 9 % where it matters, so automatic picks one: the feeders when fewer than
-// 8 packer threads would serve each GPU, else the packers.  Option "device_pack" forces 0 or 1 (= both).
+// are; the feeders by PCIe per GPU and by what the host can DMA in total, which the library cannot see.  What it
+// can see is how many packer threads the caller gives each GPU, and the three rows above say: 14 or more -- the
+// packers alone saturate the host; 6 to 13 -- both; fewer -- the feeders alone (the few packers would only take
+// DRAM bandwidth from the DMA engines).  Option "device_pack" forces 0 or 1 (= both); threads = 0 forces the feeders.
 int ntsm_ctx_device_pack(const ntsm_ctx *c, uint32_t host_packers_per_ctx)
 {
 	if (c->opt_device_pack >= 0) return c->opt_device_pack ? 1 : 0;
-	return host_packers_per_ctx < 8 ? 2 : 0;
+	return host_packers_per_ctx >= 14 ? 0 : host_packers_per_ctx >= 6 ? 1 : 2;
 }
 
 int ntsm_host_is_pinned(const void *p)

@@ -221,9 +221,9 @@ __global__ void __launch_bounds__(THREADS, MINB) count_kernel_pair(const CountPa
 //      and DRAM bytes stay where they were: 69.8 GB against 73.8 GB per 4 Gbases.  An L2 miss costs a whole
 //      128-byte line of DRAM traffic here whichever sector was asked for (2.32 G sectors read by L2 for 0.63 G
 //      that missed; cudaLimitMaxL2FetchGranularity changes nothing, profiles/r02b_l2fetch_granularity.jsonl),
-//      so the wall for this panel is ~32 G random line fetches per second, ~4.5 per 32 positions with either
-//      table, and the wide kernel's 48 registers leave it half the warps to hide them with (63 vs 72 % of
-//      peak DRAM throughput).  Beating it needs fewer MISSES per position, i.e. a selective level 1 that is
+//      so the wall for this panel is HBM bandwidth itself -- the pair kernel moves 5.9 TB/s, 91 % of the measured
+//      copy peak, ~46 G line fetches per second, ~4.5 per 32 positions with either table -- and the wide
+//      kernel's 48 registers leave it half the warps to hide the latency with (63 vs 72 % of nominal DRAM peak).  Beating it needs fewer MISSES per position, i.e. a selective level 1 that is
 //      L2-resident, which 64 M seeds do not allow in ~48 MiB.
 // k >= 19 (a window must hold a 16-mer at 4 consecutive offsets).  Same tail, same exact path.
 constexpr int kWideM = 16;

@@ -554,8 +554,9 @@ def test_device_packed_reads_vs_oracle(oracle, threads):
     buf = _pinned_bytes(b"".join(reads))
     off = np.zeros(len(reads) + 1, np.uint64)
     np.cumsum([len(r) for r in reads], out=off[1:])
+    both = {"device_pack": 1} if threads else {}          # threads = 2: force packers AND feeders (the default with 2 packers is feeders alone)
     for bb in (1 << 14, 5000, 1 << 20):
-        fp = ntsm_b200.FingerPrint(sites, batch_bases=bb, n_buffers=threads + 3)
+        fp = ntsm_b200.FingerPrint(sites, batch_bases=bb, n_buffers=threads + 3, options=both)
         l0 = fp.launches
         check_rc = ntsm_b200._lib.lib().ntsm_insert_reads((ntsm_b200._lib.C.c_void_p * 1)(fp._ctx), 1, buf.data_ptr(), off.ctypes.data,
                                                           len(reads), threads)
@@ -574,7 +575,7 @@ def test_device_packed_reads_vs_oracle(oracle, threads):
         ofp2.insert(r)
     pm = _pinned_bytes(mat.tobytes())
     for bb, stride_, ptr in ((1 << 15, stride, pm.data_ptr()), (3000, stride, pm.data_ptr())):
-        fp = ntsm_b200.FingerPrint(sites, batch_bases=bb, n_buffers=threads + 3)
+        fp = ntsm_b200.FingerPrint(sites, batch_bases=bb, n_buffers=threads + 3, options=both)
         fp.insertReadsFixed(ptr, L_, stride_, n, threads=threads)
         assert fp.counts_text() == ofp2.counts_text() and fp.printInfoSummary() == ofp2.summary()
         fp.close()
