@@ -115,7 +115,7 @@ int ntsm_load_siteset(ntsm_ctx *ctx, const ntsm_sites *s);
  *   "l2_persist"   1 = launch with an L2 access-policy window that marks the probe tables persisting (default 0: measured, no effect)
  *   "device_pack"  who packs ntsm_insert_reads* input that lies in page-locked memory: 0 = the host packer threads, 1 = they
  *                  and the GPUs' own packer together, -1 (default) = by the packer threads available per GPU: 14 or
- *                  more -- the host packers; 6 to 13 -- both; fewer -- the GPUs alone (may be set any time) */
+ *                  more -- the host packers; 10 to 13 -- both; fewer -- the GPUs alone (may be set any time) */
 int ntsm_ctx_set_option(ntsm_ctx *ctx, const char *name, int value);
 
 /* ---------------- packed batches: the ProdCon bulk buffers (vendor/ProdConKseqRunner.hpp:34-46) */
@@ -179,7 +179,7 @@ int ntsm_insert_reads_fixed(ntsm_ctx *const *ctxs, uint32_t n_ctx, const char *b
  * same queue as the `threads` host packers, DMAs their ASCII bytes to the GPU as they are and has the
  * GPU decode + pack them (pack_ascii_kernel): no host core touches those bases.  `threads` == 0 then
  * means "device packing only".  With pageable memory only the host packers run (threads >= 1).  By default
- * the split follows the packer threads available per GPU: 14 or more -- host packers only; 6 to 13 -- both; fewer --
+ * the split follows the packer threads available per GPU: 14 or more -- host packers only; 10 to 13 -- both; fewer --
  * the GPUs alone (measurements in ctx.cu at ntsm_ctx_device_pack; option "device_pack" forces either or both).
  * ntsm_host_register pins a caller's buffer (cudaHostRegister, portable); it costs ~0.2 s per GiB, so
  * it pays for buffers that are filled more than once. */

@@ -814,16 +814,17 @@ int ntsm_submit_ascii_var(ntsm_ctx *c, const char *buf, const uint64_t *off, uin
 //                              host packers   both    feeders alone
 //   1 GPU,  16 cores per GPU       109         106         51-54     (PCIe: a device-packed base costs 1 B of it, a host-packed one 0.375)
 //   2 GPUs, 12 cores per GPU       112         130          95
-//   8 GPUs,  4 cores per GPU       113         167         183       (host DMA: 183 GB/s is all the box gives; packers only take from it)
+//   4 GPUs,  8 cores per GPU       112         154         176
+//   8 GPUs,  4 cores per GPU       113         164-167     183-184   (host DMA: 183 GB/s is all the box gives; packers only take from it)
 // The packers are bound by host DRAM (2.1 B of traffic per base) at ~110 Gbases/s per BOX however many GPUs there
 // are; the feeders by PCIe per GPU and by what the host can DMA in total, which the library cannot see.  What it
-// can see is how many packer threads the caller gives each GPU, and the three rows above say: 14 or more -- the
-// packers alone saturate the host; 6 to 13 -- both; fewer -- the feeders alone (the few packers would only take
+// can see is how many packer threads the caller gives each GPU, and the four rows above say: 14 or more -- the
+// packers alone saturate the host; 10 to 13 -- both; fewer -- the feeders alone (the few packers would only take
 // DRAM bandwidth from the DMA engines).  Option "device_pack" forces 0 or 1 (= both); threads = 0 forces the feeders.
 int ntsm_ctx_device_pack(const ntsm_ctx *c, uint32_t host_packers_per_ctx)
 {
 	if (c->opt_device_pack >= 0) return c->opt_device_pack ? 1 : 0;
-	return host_packers_per_ctx >= 14 ? 0 : host_packers_per_ctx >= 6 ? 1 : 2;
+	return host_packers_per_ctx >= 14 ? 0 : host_packers_per_ctx >= 10 ? 1 : 2;
 }
 
 int ntsm_host_is_pinned(const void *p)

@@ -230,13 +230,14 @@ int main(int argc, char **argv)
 			CK(cudaMemcpy(d_b, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice));
 			CK(cudaMemcpy(d_m, hm.data(), hm.size() * 4, cudaMemcpyHostToDevice));
 		}
-		for (const char *cfgs : {"0:27", "1:27", "2:27", "2:28"}) {
+		// (round 1 swept its kernel generations here through NTSM_KERNEL; the library now takes options)
+		for (const char *cfgs : {"0:26", "1:26", "1:27", "2:26"}) {
 			char kv[2] = { cfgs[0], 0 };
 			const char *fb = cfgs + 2;
-			setenv("NTSM_KERNEL", kv, 1);
-			setenv("NTSM_FILTER_BITS", fb, 1);
 			ntsm_ctx *ctx; ntsm_cfg cfg; memset(&cfg, 0, sizeof cfg); cfg.k = 19;
 			if (ntsm_ctx_create(&ctx, &cfg)) { printf("ctx: %s\n", ntsm_last_error(NULL)); return 1; }
+			ntsm_ctx_set_option(ctx, "kernel", atoi(kv));          // 0 generic, 1 paired seeds, 2 wide paired seeds
+			ntsm_ctx_set_option(ctx, "filter_bits", atoi(fb));
 			if (ntsm_load_sites(ctx, hashes.data(), NULL, n_kmers, off.data(), n_sites)) { printf("load: %s\n", ntsm_last_error(ctx)); return 1; }
 			float best = 1e9;
 			for (int rep = 0; rep < 4; ++rep) {
