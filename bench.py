@@ -10,12 +10,15 @@ data/human_sites_n10.fa.gz planted once per haplotype; ~100 Gbases per GPU, pack
 One step = one whole counting job over the rank's shard: zero counts -> count kernel over the
 packed stream -> (N>1: one NCCL u32 all-reduce of counts + one u64 all-reduce of tallies) ->
 per-site max/sum kernel.  `value` times that with the packed shard resident in HBM (CUDA events,
-max over ranks).  `e2e` times the same job through the call a user of the reference makes --
-insertCount over ASCII reads in HOST memory (ntsm_insert_reads_fixed: decode + 2-bit/N-mask pack
-on the host cores into pinned batches, H2D, count) + ntsm_finalize (all-reduce, per-site reduce,
-D2H of the rows) -- wall clock between device syncs, max over ranks.  `e2e_packed` is the same
-job from an already packed pinned host stream (PCIe-bound), `e2e_files` the whole
-FingerPrint::computeCounts path from FASTQ files (parse + pack + count), for context.
+max over ranks); `roofline` is the count kernel alone against the measured HBM peak.
+`e2e` (headline) is what the reference arm does too: FingerPrint::computeCounts over plain FASTQ FILES
+(ntsm_count_files: parse + pack on the host cores into pinned batches, H2D, count) + ntsm_finalize
+(all-reduce, per-site reduce, D2H of the rows), wall clock between device syncs, max over ranks, copies
+counted by the library.  Beside it: `e2e_gz` (8 .fq.gz; 2 .fq.gz with single members cut between helper
+threads), `e2e_ascii*` (insertCount over ASCII reads in pinned host memory: host packers, the device
+packer, or both), `e2e_packed` (already packed pinned stream: what PCIe alone allows).  At N > 1 also
+`strong_scaling` (one 100-Gbase job cut N ways) and `check.n_gpu_equals_1_gpu`.  `cpu_baseline` and
+`--impl reference`: the unmodified reference binary on 1.5 Gbases of the same workload, 16 host threads.
 """
 import argparse
 import json
@@ -591,12 +594,12 @@ def ours(args):
         out = {
             "metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-            "data": "synthetic", "config": config_dict(args, n_bases / 1e9),
+            "data": "synthetic", "config": config_dict(args, args.gbases),      # the same dict the reference arm prints (exact shard size: roofline.gbases_per_launch)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic["dram_bytes_per_base"] * n_bases) if traffic else None,
                          "traffic_source": (traffic or {}).get("source"), "peak_source": peak_src,
                          "kernel": fp.kernel_name, "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": alg_bytes,
-                         "packed_bytes_per_launch": phys_bytes, "l2_window_pct": fp.l2_window,
+                         "packed_bytes_per_launch": phys_bytes, "gbases_per_launch": n_bases / 1e9, "l2_window_pct": fp.l2_window,
                          "note": "HBM fraction as BASELINE asks; the kernel is bound by L1->L2 probe requests, see DESIGN.md"},
             "cpu_baseline": cpu,
             "e2e": files,
