@@ -407,8 +407,9 @@ def ours(args):
         tg = time.time()
         fpaths = synth.write_fastq_set(genome, f_total, READ_LEN, 0.01, 7000 + rank, n_files, fdir)
         fbytes = sum(os.path.getsize(p) for p in fpaths)
-        # every file is read f_passes times per step: the box's whole file set is ~7 Gbases, a step should last ~1 s
-        f_passes = max(1, env_int("NTSM_BENCH_FILE_PASSES", 3 * min(4, local_world)))
+        # every file is read f_passes times per step: the box's whole file set is ~7 Gbases, a step should last >= 1 s
+        # (>= 40 Gbases per step per box)
+        f_passes = max(1, env_int("NTSM_BENCH_FILE_PASSES", 6 if local_world <= 2 else 12))
         log("rank %d: %d FASTQ files, %.2f GB, written in %.1f s" % (rank, len(fpaths), fbytes / 1e9, time.time() - tg))
 
         def job_files():
