@@ -4,6 +4,8 @@
 //   /tmp/hostpath_bench [parse|pack|packN] file...  (parse = reader only, pack = reader + packer, packN = with N helper threads per reader)
 #include <stdio.h>
 #include <string.h>
+#include <sys/wait.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <chrono>
@@ -21,6 +23,30 @@ int main(int argc, char **argv)
 	const int nf = argc - 2;
 	std::atomic<uint64_t> bases{0}, reads{0};
 	const auto t0 = std::chrono::steady_clock::now();
+	if (!strncmp(argv[1], "procs", 5)) {
+		// one PROCESS per file instead of one thread: separate address spaces, so page-table work for mapped
+		// files does not meet on one mm (is that what stops the mapped source from scaling in one process?)
+		for (int i = 0; i < nf; ++i)
+			if (fork() == 0) {
+				ntsm::FastxReader rd;
+				if (!rd.open(argv[2 + i], 0)) _exit(1);
+				const uint64_t cap = 1ull << 24;
+				std::vector<uint64_t> b(ntsm::padded_positions(cap) / 32 + 64);
+				std::vector<uint32_t> m(ntsm::padded_positions(cap) / 32 + 64);
+				ntsm::Packer pk;
+				pk.reset(b.data(), m.data());
+				int64_t l;
+				while ((l = rd.next()) >= 0) {
+					if (pk.pos + ntsm::read_span((uint64_t)l) > cap) pk.reset(b.data(), m.data());
+					if ((uint64_t)l < cap / 2) pk.put_read(rd.seq(), (uint64_t)l);
+				}
+				_exit(0);
+			}
+		while (wait(nullptr) > 0) {}
+		const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		printf("procs: %d file(s)/process(es) in %.3f s\n", nf, dt);
+		return 0;
+	}
 	std::vector<std::thread> th;
 	for (int i = 0; i < nf; ++i)
 		th.emplace_back([&, i] {
