@@ -113,6 +113,9 @@ int ntsm_load_siteset(ntsm_ctx *ctx, const ntsm_sites *s);
  *   "filter_bits"  log2 of the k-mer bitmap's bits (10..32), 0 = automatic (~80 bits per site k-mer)
  *   "launch_shape" pair kernel CTA shape: 0 = 1024x1, 1 = 1024x2 (default), 2 = 512x4, 3 = 256x8 per SM
  *   "l2_persist"   1 = launch with an L2 access-policy window that marks the probe tables persisting (default 0: measured, no effect)
+ *   "parser_procs" ntsm_count_files runs its parsers as worker processes (bin/ntsm_parse_worker; a mapped plain file is parsed
+ *                  in place without read()'s copy, which scales across processes but not across the threads of one):
+ *                  1 on, 0 off, -1 (default) when more than 6 parser threads read plain files and there is no -m cap
  *   "device_pack"  who packs ntsm_insert_reads* input that lies in page-locked memory: 0 = the host packer threads, 1 = they
  *                  and the GPUs' own packer together, -1 (default) = by the packer threads available per GPU: 14 or
  *                  more -- the host packers; 10 to 13 -- both; fewer -- the GPUs alone (may be set any time) */

@@ -64,6 +64,7 @@ struct ntsm_ctx {
 	int opt_filter_bits = 0;                // log2 bits of the k-mer bitmap
 	int opt_shape = 1;                      // pair kernel launch shape: 0 = 1024x1, 1 = 1024x2 (default), 2 = 512x4, 3 = 256x8
 	int opt_l2_persist = 0;                 // launch with an L2 access-policy window over the probe tables (measured: no effect, see ntsm_load_sites)
+	int opt_parser_procs = -1;              // file pipeline: parsers as worker processes (procpipe.h): -1 = beyond 6 parser threads on plain files
 	int opt_device_pack = -1;               // bulk inserts from page-locked memory also feed ASCII to the GPU packer: -1 = when host packers are few
 	// site table
 	uint32_t n_kmers = 0, n_sites = 0;
@@ -246,6 +247,7 @@ extern "C" int ntsm_ctx_set_option(ntsm_ctx *c, const char *name, int value)
 	else if (!strcmp(name, "launch_shape")) c->opt_shape = std::min(3, std::max(0, value));
 	else if (!strcmp(name, "l2_persist")) c->opt_l2_persist = value;
 	else if (!strcmp(name, "device_pack")) c->opt_device_pack = value;
+	else if (!strcmp(name, "parser_procs")) c->opt_parser_procs = value;
 	else return fail(c, NTSM_ERR_ARG, "ntsm_ctx_set_option: unknown option '%s'", name);
 	return NTSM_OK;
 }
@@ -877,6 +879,35 @@ extern "C" int ntsm_count_packed_host(ntsm_ctx *c, const uint32_t *h_bases2, con
 	}
 	return NTSM_OK;
 }
+
+// A packed batch that lies in page-locked memory the ctx does not own (a slot of the parser processes' shared
+// mapping, procpipe.h), padded by its packer up to padded_positions(n_pos): copy + count it through one of the ctx's
+// device buffers.  *out is the batch whose `copied` event tells when the slot may be reused (ntsm_batch_copy_done).
+int ntsm_submit_foreign(ntsm_ctx *c, const void *bases, const void *mask, uint64_t n_pos, uint64_t n_bases, uint64_t n_reads,
+                        ntsm_batch **out)
+{
+	*out = nullptr;
+	if (!c || !bases || !mask) return NTSM_ERR_ARG;
+	if (n_pos > (c->cfg.batch_bases & ~(kReadAlign - 1))) return fail(c, NTSM_ERR_ARG, "ntsm_submit_foreign: batch larger than the ctx's buffers");
+	ntsm_batch *b = nullptr;
+	int rc = ntsm_acquire_batch(c, &b);
+	if (rc) return rc;
+	b->n_reads = n_reads;
+	rc = enqueue_batch(c, b, bases, mask, n_pos, padded_positions(n_pos), n_bases);
+	if (rc == NTSM_OK && n_pos) *out = b;
+	return rc;
+}
+// 1 once the host-to-device copy of the batch last submitted through `b` has finished, 0 while it has not, < 0 on a device fault
+int ntsm_batch_copy_done(ntsm_batch *b)
+{
+	cudaSetDevice(b->ctx->device);
+	const cudaError_t q = cudaEventQuery(b->copied);
+	if (q == cudaSuccess) return 1;
+	if (q == cudaErrorNotReady) return 0;
+	return fail(b->ctx, NTSM_ERR_CUDA, "batch copy failed on the device: %s", cudaGetErrorString(q));
+}
+int ntsm_ctx_parser_procs(const ntsm_ctx *c) { return c->opt_parser_procs; }
+uint32_t ntsm_ctx_k(const ntsm_ctx *c) { return c->cfg.k; }
 
 extern "C" int ntsm_release_batch(ntsm_ctx *c, ntsm_batch *b)
 {

@@ -17,3 +17,9 @@ int ntsm_ctx_device_pack(const ntsm_ctx *c, uint32_t host_packers_per_ctx);
 uint64_t ntsm_ascii_capacity_fixed(const ntsm_ctx *c, uint64_t read_len, uint64_t stride);   // rows one batch takes
 int ntsm_submit_ascii_fixed(ntsm_ctx *c, const char *rows, uint64_t read_len, uint64_t stride, uint64_t n_reads);
 int ntsm_submit_ascii_var(ntsm_ctx *c, const char *buf, const uint64_t *off, uint64_t n_reads, uint64_t *taken);
+// parser worker processes (pipeline.cpp, procpipe.h): a packed batch in foreign page-locked memory -> copy + count
+int ntsm_submit_foreign(ntsm_ctx *c, const void *bases, const void *mask, uint64_t n_pos, uint64_t n_bases, uint64_t n_reads,
+                        ntsm_batch **out);
+int ntsm_batch_copy_done(ntsm_batch *b);
+int ntsm_ctx_parser_procs(const ntsm_ctx *c);
+uint32_t ntsm_ctx_k(const ntsm_ctx *c);

@@ -612,6 +612,74 @@ def test_host_register_makes_a_buffer_device_packable(oracle):
         assert Lb.ntsm_host_unregister(mat.ctypes.data) == 0
 
 
+# ---------------------------------------------------------------- parsers as worker processes
+@pytest.mark.parametrize("name", [n for n in golden_cases() if not n.startswith(("dupes_abort", "odd_sites"))])
+def test_abi_files_through_parser_processes_match_reference_fixture(name):
+    """computeCounts with the parsers run as worker PROCESSES (bin/ntsm_parse_worker over the shared, page-locked
+    mapping of procpipe.h; forced here, automatic beyond 6 parser threads on plain files): every fixture made by the
+    reference binary, byte for byte.  gzip inputs and -m runs fall back to the parser threads by design."""
+    d, opts, files = _case_files(name)
+    if opts["m"] > 0 and "Reached desired" in open(os.path.join(d, "stderr.txt")).read():
+        pytest.skip("-m early stop: the cap keeps the parsers in-process")
+    fp = ntsm_b200.FingerPrint(opts["sites"], k=opts["k"], dupes=opts["dupes"], cov_thresh=opts["m"], batch_bases=1 << 14,
+                               options={"parser_procs": 1})
+    fp.computeCounts(files, threads=max(2, opts["t"]))
+    assert fp.counts_text().encode() == open(os.path.join(d, "stdout.txt"), "rb").read()
+    assert fp.printInfoSummary() in open(os.path.join(d, "stderr.txt")).read()
+    fp.close()
+
+
+def test_parser_processes_many_files_long_reads_vs_oracle(oracle, tmp_path):
+    """Nine plain files (FASTA and FASTQ, reads up to 40 kb, N runs) over 1..8 parser processes and batches from 4 Ki to
+    1 Mi positions, two GPUs' worth of contexts: the oracle's per-k-mer counters; then a missing file: the reference's
+    error text, and the contexts stay usable."""
+    import torch
+    sites = os.path.join(GOLDEN, "shared", "sites300.fa")
+    rng = random.Random(61)
+    wins = _windows(sites)
+    ofp = oracle.fingerprint(sites, 19, False)
+    paths = []
+    for f in range(9):
+        recs = []
+        for i in range(rng.randrange(150, 400)):
+            parts = []
+            for _ in range(rng.choice([1, 1, 2, 5, 120 if f == 4 else 3])):
+                parts.append("".join(rng.choice("ACGT") for _ in range(rng.randrange(0, 300))))
+                parts.append(rng.choice(wins))
+                if rng.random() < 0.1:
+                    parts.append("N" * rng.randrange(1, 9))
+            r = "".join(parts).encode()
+            r = revcomp(r) if rng.random() < 0.5 else r
+            ofp.insert(r)
+            recs.append((b"@q%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r))) if f % 2 else (b">q%d\n%s\n" % (i, r)))
+        p = tmp_path / ("in%d.%s" % (f, "fq" if f % 2 else "fa"))
+        p.write_bytes(b"".join(recs))
+        paths.append(str(p))
+    ndev = torch.cuda.device_count()
+    ss = ntsm_b200.SiteSet(sites, 19)
+    for threads, bb, n_ctx in ((1, 1 << 14, 1), (4, 4096, 1), (8, 1 << 20, 1), (3, 30000, 2)):
+        fps = [ntsm_b200.FingerPrint(ss, device=i % ndev, batch_bases=bb, n_buffers=4, options={"parser_procs": 1}) for i in range(n_ctx)]
+        L = ntsm_b200.lib()
+        arr = (ntsm_b200._lib.C.c_char_p * len(paths))(*[os.fsencode(x) for x in paths])
+        ctxs = (ntsm_b200._lib.C.c_void_p * n_ctx)(*[f._ctx for f in fps])
+        early = ntsm_b200._lib.C.c_int(0)
+        assert L.ntsm_count_files(ctxs, n_ctx, arr, len(paths), threads, 0, ntsm_b200._lib.C.byref(early)) == 0
+        ntsm_b200.FingerPrint.group_finalize(fps)
+        assert fps[0].counts_text() == ofp.counts_text(), (threads, bb, n_ctx)
+        assert fps[0].printInfoSummary() == ofp.summary()
+        assert np.array_equal(fps[0].kmer_counts(), ofp.lists()[2])
+        for f in fps:
+            f.close()
+    fp = ntsm_b200.FingerPrint(ss, batch_bases=1 << 15, options={"parser_procs": 1})
+    with pytest.raises(FileNotFoundError) as e:
+        fp.computeCounts(paths[:3] + [str(tmp_path / "nope.fq")] + paths[3:], threads=3)
+    assert "file %s cannot be opened" % (tmp_path / "nope.fq") in str(e.value)
+    fp.reset()
+    fp.computeCounts(paths, threads=2)
+    assert fp.counts_text() == ofp.counts_text()
+    fp.close()
+
+
 # ---------------------------------------------------------------- several GPUs of one process, no NCCL
 @pytest.mark.parametrize("n_ctx", [2, 3])
 def test_group_finalize_equals_one_context(oracle, n_ctx):

@@ -400,3 +400,45 @@ def test_numa_helpers_parse_and_stay_out_of_the_way_on_one_node_hosts(L):
     before = os.sched_getaffinity(0)
     # a bulk insert on a box without CUDA fails early; the calling thread's affinity must be untouched either way
     assert os.sched_getaffinity(0) == before
+
+
+def test_parser_worker_processes_speak_the_shared_memory_protocol(tmp_path):
+    """bin/ntsm_parse_worker + procpipe.h without a GPU: tools/procpipe_selftest.cpp plays the owner (shared mapping,
+    spawn, slot hand-over) and tallies what the workers packed.  Reads, bases and valid positions must be what the
+    files hold -- several files and workers, FASTA + FASTQ, N runs, reads longer than a slot (split with a k-1 overlap),
+    an unreadable file (error text of src/FingerPrint.hpp:51-57, the other workers stop)."""
+    exe = str(tmp_path / "procpipe_selftest")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "ntsm_b200", "csrc"),
+                           os.path.join(ROOT, "tools", "procpipe_selftest.cpp"), "-o", exe])
+    worker = os.path.join(ROOT, "ntsm_b200", "bin", "ntsm_parse_worker")
+    assert os.access(worker, os.X_OK)
+    rng = random.Random(8)
+    valid_set = set(b"ACGTUacgtu\x00\x01\x02\x03")
+    paths, reads = [], []
+    for f in range(5):
+        p = tmp_path / ("f%d.%s" % (f, "fq" if f % 2 else "fa"))
+        recs = []
+        for i in range(rng.randrange(200, 600)):
+            n = rng.choice([0, 1, 18, 19, 40, 150, 151, 300, 5000 if f == 2 else 77])
+            s = bytes(rng.choice(b"ACGTNacgtR") for _ in range(n))
+            reads.append(s)
+            recs.append((b"@r%d\n%s\n+\n%s\n" % (i, s, b"I" * n)) if f % 2 else (b">r%d\n%s\n" % (i, s)))
+        p.write_bytes(b"".join(recs))
+        paths.append(str(p))
+    want_bases = sum(map(len, reads))
+    want_valid = sum(sum(c in valid_set for c in r) for r in reads)
+
+    def run(cap, workers, files):
+        out = subprocess.run([exe, worker, "19", str(cap), str(workers)] + files, capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        return json.loads(out.stdout)
+
+    for cap, workers in ((1 << 20, 1), (1 << 20, 3), (65536, 7)):
+        r = run(cap, workers, paths)
+        assert (r["reads"], r["bases"], r["valid"], r["error"], r["bad_exit"]) == (len(reads), want_bases, want_valid, 0, 0), (cap, workers)
+        assert r["positions"] == sum((len(x) + 8) & ~7 for x in reads)
+    r = run(4096, 4, paths)                # slots shorter than the 5000-base reads: split, k-1 bases packed twice at every cut
+    assert (r["reads"], r["bases"], r["error"], r["bad_exit"]) == (len(reads), want_bases, 0, 0)
+    assert r["valid"] > want_valid and r["batches"] > 50
+    r = run(65536, 3, paths[:2] + [str(tmp_path / "missing.fq")] + paths[2:])
+    assert r["error"] == -5 and r["error_text"] == "file %s cannot be opened" % (tmp_path / "missing.fq") and r["bad_exit"] == 0
