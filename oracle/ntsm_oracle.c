@@ -11,6 +11,7 @@
 
 #include <stdlib.h>
 #include <string.h>
+#include <sys/types.h>
 #include <zlib.h>
 #ifdef _OPENMP
 #include <omp.h>
@@ -536,6 +537,340 @@ void ntsm_oracle_fp_lists(const ntsm_oracle_fp *fp, uint64_t *hashes, uint32_t *
 		}
 	}
 	if (allele_off) allele_off[2 * fp->n_ref] = n;
+}
+
+/* ================================================================== */
+/* Multi-sample matrix path: MultiCount driven by   */
+/* VCFConvert.  Pinned against tools/ref_vcf_harness.cpp, which runs   */
+/* the reference's two classes unmodified (tests/golden/vcf/).         */
+
+/* MultiCount (src/MultiCount.hpp:36-289).  initCountsHash (:214-288) is FingerPrint's
+ * (src/FingerPrint.hpp:490-564) with `m_kmerToHash[hv] = kmerCount++` instead of a zero count:
+ * the dense index of a k-mer is its position in the site lists taken in file order.  The fp's
+ * map is reused with slot.cnt holding that index. */
+struct ntsm_oracle_mc {
+	ntsm_oracle_fp *fp;
+	uint32_t n_samples;
+	uint64_t listed;          /* kmerCount (:217) */
+	uint64_t stride;          /* m_kmerToHash.size() (:55,:108): the row stride */
+	uint8_t *mat;             /* m_matCounts (:266): listed * n_samples bytes */
+};
+
+ntsm_oracle_mc *ntsm_oracle_mc_create(const char *sites_path, unsigned k, int dupes, uint32_t n_samples, FILE *warn)
+{
+	ntsm_oracle_fp *fp = ntsm_oracle_fp_create(sites_path, k, dupes, 0, warn);
+	if (!fp) return NULL;
+	ntsm_oracle_mc *mc = (ntsm_oracle_mc *)calloc(1, sizeof *mc);
+	mc->fp = fp;
+	mc->n_samples = n_samples;
+	uint64_t n = 0;
+	for (uint32_t i = 0; i < fp->n_ref; ++i) {
+		const list_t *ls[2] = { &fp->ref[i], i < fp->n_var ? &fp->var[i] : NULL };
+		for (int a = 0; a < 2 && ls[a]; ++a)
+			for (uint32_t j = 0; j < ls[a]->n; ++j) map_find_any(&fp->counts, ls[a]->v[j])->cnt = n++;   /* :230,:250 */
+	}
+	mc->listed = n;
+	mc->stride = fp->table_size;
+	mc->mat = (uint8_t *)calloc(n * n_samples + 1, 1);
+	return mc;
+}
+
+void ntsm_oracle_mc_destroy(ntsm_oracle_mc *mc)
+{
+	if (!mc) return;
+	ntsm_oracle_fp_destroy(mc->fp);
+	free(mc->mat);
+	free(mc);
+}
+
+/* MultiCount::insertCount (:52-70), one thread: the first non-zero value written to a cell stays;
+ * a later insert of a different value only warns.  The stored value is `multi` truncated to a byte,
+ * the comparison is between the byte and the unsigned, and the byte goes to cerr as a CHARACTER. */
+void ntsm_oracle_mc_insert(ntsm_oracle_mc *mc, unsigned sample, uint64_t hash, unsigned multi, FILE *warn)
+{
+	const slot_t *e = map_find(&mc->fp->counts, hash);
+	if (!e) return;                                                /* :53 */
+	uint8_t *cell = &mc->mat[mc->stride * sample + e->cnt];        /* :56-57 */
+	if (*cell > 0) {                                               /* :58 */
+		if (*cell != multi && warn) {                              /* :59-62 */
+			fputs("Warning: Inconsistent k-mer counts, check for overlapping sites: ", warn);
+			fputc(*cell, warn);
+			fprintf(warn, " vs %u\n", multi);
+		}
+		return;
+	}
+	*cell = (uint8_t)multi;                                        /* :65-67 */
+}
+
+const uint8_t *ntsm_oracle_mc_matrix(const ntsm_oracle_mc *mc, uint64_t *bytes)
+{
+	if (bytes) *bytes = mc->listed * mc->n_samples;
+	return mc->mat;
+}
+ntsm_oracle_fp *ntsm_oracle_mc_fp(ntsm_oracle_mc *mc) { return mc->fp; }
+
+static int mc_list_max(const ntsm_oracle_mc *mc, const list_t *l, unsigned sample, uint32_t *mx, uint32_t *sum)
+{
+	uint32_t m = 0, s = 0;
+	for (uint32_t j = 0; j < l->n; ++j) {
+		const slot_t *e = map_find(&mc->fp->counts, l->v[j]);
+		if (!e) return -134;                                       /* m_kmerToHash.at() throws (:108,:117,:169,:176) */
+		const uint32_t c = mc->mat[mc->stride * sample + e->cnt];
+		if (m < c) m = c;
+		s += c;
+	}
+	*mx = m;
+	*sum = s;
+	return 0;
+}
+
+/* MultiCount::printCountsMax (:93-138): a counts file WITHOUT the #@TK / #@KS header lines */
+int ntsm_oracle_mc_print_counts_max(const ntsm_oracle_mc *mc, unsigned index, FILE *out)
+{
+	const ntsm_oracle_fp *fp = mc->fp;
+	fprintf(out, "\n#locusID\tcountAT\tcountCG\tsumAT\tsumCG\tdistinctAT\tdistinctCG\n");     /* :94 */
+	for (uint32_t i = 0; i < fp->n_ref; ++i) {
+		uint32_t mr, mv, sr, sv;
+		if (i >= fp->n_var) return -134;                           /* :99 */
+		if (mc_list_max(mc, &fp->ref[i], index, &mr, &sr)) return -134;
+		if (mc_list_max(mc, &fp->var[i], index, &mv, &sv)) return -134;
+		fprintf(out, "%s\t%u\t%u\t%u\t%u\t%u\t%u\n", fp->names[i], mr, mv, sr, sv, fp->ref[i].n, fp->var[i].n);
+	}
+	return 0;
+}
+
+/* MultiCount::printNormMatrix (:148-203).  value = maxREF / (maxREF + maxVAR) as doubles, missing
+ * (both zero) = the site's mean over the samples that have one -- the sum runs in sample order and
+ * is divided in long double by the number of ALL samples (:181,:185: `size` counts every sample).
+ * ostream state carried by `out`: doubles print as %.6g until the first missing value has been
+ * written with setprecision(19) (:190), from then on every value of that stream prints as %.19g. */
+int ntsm_oracle_mc_print_norm_matrix(const ntsm_oracle_mc *mc, const char *const *sample_ids, FILE *out, FILE *center_file)
+{
+	const ntsm_oracle_fp *fp = mc->fp;
+	const uint32_t S = mc->n_samples;
+	double *values = (double *)malloc((S + 1) * sizeof(double));
+	int precision = 6;
+	fputs("alleleID", out);                                        /* :149 */
+	for (uint32_t j = 0; j < S; ++j) fprintf(out, "\t%s", sample_ids[j]);
+	fputc('\n', out);
+	for (uint32_t i = 0; i < fp->n_ref; ++i) {
+		if (i >= fp->n_var) { free(values); return -134; }         /* :158 */
+		double sum = 0.0;
+		uint64_t size = 0;
+		for (uint32_t j = 0; j < S; ++j) {
+			uint32_t mr, mv, unused;
+			if (mc_list_max(mc, &fp->ref[i], j, &mr, &unused) || mc_list_max(mc, &fp->var[i], j, &mv, &unused)) { free(values); return -134; }
+			const unsigned denom = mr + mv;                        /* :179 */
+			if (denom == 0) values[j] = 1.7976931348623157e308;    /* UNDEF = numeric_limits<double>::max() (:41) */
+			else {
+				values[j] = (double)mr / (double)denom;            /* :183 */
+				sum += values[j];
+			}
+			++size;
+		}
+		fputs(fp->names[i], out);                                  /* :187 */
+		const long double size_f = (long double)size;
+		const long double center = (long double)sum / size_f;      /* :188-189 */
+		for (uint32_t j = 0; j < S; ++j) {
+			if (values[j] == 1.7976931348623157e308) {
+				precision = 19;                                    /* :192, and it sticks */
+				fprintf(out, "\t%.19Lg", center);
+			} else fprintf(out, "\t%.*g", precision, values[j]);   /* :194 */
+		}
+		fprintf(center_file, "%.19Lg\n", center);                  /* :198 */
+		fputc('\n', out);
+	}
+	free(values);
+	return 0;
+}
+
+/* VCFConvert (src/VCFConvert.hpp:40-218) with one thread.  Return codes: 0; -1 a file cannot be
+ * opened; -134 where the reference dies on an uncaught exception or a failed assert (empty line
+ * before the #CHROM line: string::at :74; unknown chromosome: robin_map::at :204; non-numeric POS:
+ * stoi :113; a data line whose sample columns are not as many as the header's: assert :146);
+ * -2 where the reference has undefined behaviour and no result to restate (a site closer than
+ * window/2 to the start of its chromosome, or beyond its end: getSeqFromSite reads outside the
+ * sequence, :207-209).
+ * n_samples_out / sample_ids_out (malloc'ed array of malloc'ed strings) describe the header. */
+struct chr_rec { char *name; char *seq; size_t len; };
+
+static char **split_tabs(char *line, size_t *n_out)
+{
+	size_t n = 1;
+	for (char *p = line; *p; ++p) n += *p == '\t';
+	char **f = (char **)malloc(n * sizeof(char *));
+	size_t i = 0;
+	f[i++] = line;
+	for (char *p = line; *p; ++p)
+		if (*p == '\t') { *p = 0; f[i++] = p + 1; }
+	*n_out = n;
+	return f;
+}
+
+static void mc_count_window(void *c, uint64_t hv, uint64_t pos, uint64_t fw, uint64_t rv);
+struct win_cb { ntsm_oracle_mc *mc; const uint8_t *geno; uint32_t S; unsigned multi; int var; FILE *warn; };
+static void mc_count_window(void *c, uint64_t hv, uint64_t pos, uint64_t fw, uint64_t rv)
+{   /* :148-169 */
+	struct win_cb *w = (struct win_cb *)c;
+	(void)pos; (void)fw; (void)rv;
+	for (uint32_t i = 0; i < w->S; ++i) {
+		const uint8_t g = w->geno[i];                              /* 0 hom1, 1 het, 2 hom2 */
+		if (g == (w->var ? 2 : 0)) ntsm_oracle_mc_insert(w->mc, i, hv, w->multi * 2, w->warn);
+		else if (g == 1) ntsm_oracle_mc_insert(w->mc, i, hv, w->multi, w->warn);
+	}
+}
+
+int ntsm_oracle_vcf_convert(const char *sites_path, const char *ref_path, const char *vcf_path, unsigned k, int dupes,
+                            unsigned multi, unsigned window, FILE *warn, ntsm_oracle_mc **mc_out, char ***sample_ids_out,
+                            uint32_t *n_samples_out)
+{
+	*mc_out = NULL;
+	/* the reference genome: every record kept whole, last record of a name wins (:47-58) */
+	ntsm_oracle_reader *r = ntsm_oracle_reader_open(ref_path);
+	if (!r) return -1;
+	struct chr_rec *chr = NULL;
+	size_t n_chr = 0;
+	const char *seq, *name;
+	long l;
+	while ((l = ntsm_oracle_reader_next(r, &seq, &name)) >= 0) {
+		chr = (struct chr_rec *)realloc(chr, (n_chr + 1) * sizeof *chr);
+		chr[n_chr].name = strdup(name);
+		chr[n_chr].seq = (char *)malloc((size_t)l + 1);
+		memcpy(chr[n_chr].seq, seq, (size_t)l);
+		chr[n_chr].seq[l] = 0;
+		chr[n_chr].len = (size_t)l;
+		++n_chr;
+	}
+	ntsm_oracle_reader_close(r);
+
+	FILE *fh = fopen(vcf_path, "rb");
+	int rc = fh ? 0 : -1;
+	char *line = NULL;
+	size_t cap = 0;
+	ssize_t got;
+	char **ids = NULL;
+	uint32_t S = 0;
+	/* header: lines are looked at until the one whose first field is "#CHROM" (:71-93) */
+	while (rc == 0 && (got = getline(&line, &cap, fh)) >= 0) {
+		if (got > 0 && line[got - 1] == '\n') line[--got] = 0;
+		if (got == 0) { rc = -134; break; }                        /* line.at(0) throws */
+		if (line[0] != '#') continue;
+		size_t nf;
+		char **f = split_tabs(line, &nf);
+		if (strcmp(f[0], "#CHROM") == 0) {
+			for (size_t i = 9; i < nf; ++i) {                      /* 8 more fields skipped, the rest are sample IDs */
+				ids = (char **)realloc(ids, (S + 1) * sizeof(char *));
+				ids[S++] = strdup(f[i]);
+			}
+			free(f);
+			break;
+		}
+		free(f);
+	}
+	ntsm_oracle_mc *mc = NULL;
+	if (rc == 0) {
+		mc = ntsm_oracle_mc_create(sites_path, k, dupes, S, warn);
+		if (!mc) rc = -1;
+	}
+	uint8_t *geno = (uint8_t *)malloc(S + 1);
+	char *wref = (char *)malloc(window + 1), *wvar = (char *)malloc(window + 1);
+	while (rc == 0 && fh && (got = getline(&line, &cap, fh)) >= 0) {
+		if (got == 0 || line[got - 1] != '\n') break;              /* :101-108: a last line without its newline leaves the stream at eof and is dropped */
+		line[--got] = 0;
+		size_t nf;
+		char **f = split_tabs(line, &nf);
+		do {
+			if (nf < 2) { rc = -134; break; }                      /* stoi of a missing / empty POS throws */
+			char *end;
+			const long loc = strtol(f[1], &end, 10);               /* stoi (:113): leading integer */
+			if (end == f[1]) { rc = -134; break; }
+			if (nf < 5) { rc = -134; break; }                      /* restated for well-formed lines only */
+			if (strcmp(f[3], ".") == 0) break;                     /* :121-123 */
+			if (strlen(f[4]) != 1) break;                          /* :125-127: ALT must be one character; REF is not looked at */
+			const char alt = f[4][0];
+			/* getSeqFromSite (:202-215) */
+			const struct chr_rec *c = NULL;
+			for (size_t i = 0; i < n_chr; ++i)
+				if (strcmp(chr[i].name, f[0]) == 0) c = &chr[i];   /* later record of the same name wins (:52) */
+			if (!c) { rc = -134; break; }
+			const unsigned half = window / 2;
+			if (loc < (long)half + 1 || (size_t)(loc - half - 1) > c->len) { rc = -2; break; }
+			const size_t offset = (size_t)loc - half - 1;
+			memset(wref, 0, window + 1);
+			memset(wvar, 0, window + 1);
+			const size_t avail = c->len - offset < window ? c->len - offset : window;   /* strncpy stops at the sequence's NUL and pads */
+			memcpy(wref, c->seq + offset, avail);
+			memcpy(wvar, c->seq + offset, avail);
+			wvar[half] = alt;                                      /* :211 */
+			/* sample columns (:136-146) */
+			if (nf != 9 + (size_t)S) { rc = -134; break; }
+			for (uint32_t i = 0; i < S; ++i) {
+				const char *g = f[9 + i];
+				geno[i] = !strcmp(g, "0|0") ? 0 : (!strcmp(g, "0|1") || !strcmp(g, "1|0")) ? 1 : !strcmp(g, "1|1") ? 2 : 0;   /* anything else keeps the vector's initial hom1 */
+			}
+			struct win_cb cb = { mc, geno, S, multi, 0, warn };
+			iterate(wref, strlen(wref), k, mc_count_window, &cb);  /* :148-158 */
+			cb.var = 1;
+			iterate(wvar, strlen(wvar), k, mc_count_window, &cb);  /* :159-169 */
+		} while (0);
+		free(f);
+	}
+	free(geno); free(wref); free(wvar); free(line);
+	if (fh) fclose(fh);
+	for (size_t i = 0; i < n_chr; ++i) { free(chr[i].name); free(chr[i].seq); }
+	free(chr);
+	if (rc != 0) {
+		ntsm_oracle_mc_destroy(mc);
+		for (uint32_t i = 0; i < S; ++i) free(ids[i]);
+		free(ids);
+		return rc;
+	}
+	*mc_out = mc;
+	*sample_ids_out = ids;
+	*n_samples_out = S;
+	return 0;
+}
+
+/* Whole run with the file layout of tools/ref_vcf_harness.cpp: <prefix>_matrix.tsv, <prefix>_center.txt,
+ * <prefix>_counts_<j>.txt per sample, <prefix>_mat.bin, and the warnings in <prefix>_stderr.txt. */
+int ntsm_oracle_vcf_run(const char *sites_path, const char *ref_path, const char *vcf_path, unsigned k, int dupes,
+                        unsigned multi, unsigned window, const char *prefix)
+{
+	char path[4096];
+	snprintf(path, sizeof path, "%s_stderr.txt", prefix);
+	FILE *warn = fopen(path, "wb");
+	if (!warn) return -1;
+	ntsm_oracle_mc *mc;
+	char **ids;
+	uint32_t S;
+	int rc = ntsm_oracle_vcf_convert(sites_path, ref_path, vcf_path, k, dupes, multi, window, warn, &mc, &ids, &S);
+	fclose(warn);
+	if (rc) return rc;
+	snprintf(path, sizeof path, "%s_mat.bin", prefix);
+	FILE *f = fopen(path, "wb");
+	uint64_t bytes;
+	const uint8_t *m = ntsm_oracle_mc_matrix(mc, &bytes);
+	fwrite(m, 1, bytes, f);
+	fclose(f);
+	for (uint32_t j = 0; j < S && rc == 0; ++j) {
+		snprintf(path, sizeof path, "%s_counts_%u.txt", prefix, j);
+		f = fopen(path, "wb");
+		rc = ntsm_oracle_mc_print_counts_max(mc, j, f);
+		fclose(f);
+	}
+	if (rc == 0) {
+		snprintf(path, sizeof path, "%s_matrix.tsv", prefix);
+		f = fopen(path, "wb");
+		snprintf(path, sizeof path, "%s_center.txt", prefix);
+		FILE *c = fopen(path, "wb");
+		rc = ntsm_oracle_mc_print_norm_matrix(mc, (const char *const *)ids, f, c);
+		fclose(f);
+		fclose(c);
+	}
+	for (uint32_t j = 0; j < S; ++j) free(ids[j]);
+	free(ids);
+	ntsm_oracle_mc_destroy(mc);
+	return rc;
 }
 
 /* ------------------------------------------------------------------ */
