@@ -296,6 +296,61 @@ const char *ntsm_scan_isa(const char *force);
 int ntsm_count_files(ntsm_ctx *const *ctxs, uint32_t n_ctx, const char *const *paths, uint32_t n_paths,
                      uint32_t threads, int verbose, int *early);
 
+/* ---------------- multi-sample matrix: MultiCount driven by VCFConvert ----------------
+ * src/MultiCount.hpp:36-289, src/VCFConvert.hpp:40-218, src/ntSeqMatchVCF.cpp.  The matrix
+ * m_matCounts[sample][dense k-mer index] (uint8) lives in device memory on top of a ctx whose site table is
+ * loaded (ntsm_load_siteset = MultiCount::initCountsHash, which is FingerPrint's).  Results equal the
+ * reference's classes run with one thread (tests/golden/vcf, made by tools/ref_vcf_harness.cpp).  Calls return
+ * NTSM_ERR_NOKEY where the reference process dies (uncaught exception / failed assert, exit 134). */
+typedef struct ntsm_multi ntsm_multi; /* MultiCount */
+typedef struct ntsm_vcf ntsm_vcf;     /* VCFConvert */
+int ntsm_multi_create(ntsm_multi **out, ntsm_ctx *ctx, uint32_t n_samples); /* MultiCount(sampleIDs) :43-49; the ctx must outlive it */
+void ntsm_multi_destroy(ntsm_multi *m);
+uint32_t ntsm_multi_n_samples(const ntsm_multi *m);
+/* insertCount(sampleIndex, hashVal, multi) :52-70, one call (a one-thread kernel: for drop-in completeness) */
+int ntsm_multi_insert_count(ntsm_multi *m, uint32_t sample, uint64_t hash, uint32_t multi);
+/* The inner loops of VCFConvert::count (:148-169) for n_lines SNP lines at once.  Line l has two windows of
+ * the reference genome, windows[(2l + a) * wstride .. + lens[2l + a]): a = 0 with the reference allele, a = 1
+ * with the alternative allele in the middle (ASCII, decoded with the reference's table); and one genotype code
+ * per sample, genotypes[l * n_samples + s]: 0 = "0|0" (and anything unrecognised), 1 = "0|1" / "1|0", 2 = "1|1".
+ * Every k-mer of window a that is a site k-mer is inserted for every sample: 2 * multi when the sample is
+ * homozygous for allele a, multi when heterozygous.  The first non-zero value written to a cell stays (the
+ * order is the reference's with one thread: line, a, offset in the window); later different values only warn. */
+int ntsm_multi_insert_windows(ntsm_multi *m, const char *windows, uint32_t wstride, const uint16_t *lens,
+                              const uint8_t *genotypes, uint32_t n_lines, uint32_t multi);
+/* "Warning: Inconsistent k-mer counts, ..." lines (:60-61) raised so far, in the reference's serial order */
+uint64_t ntsm_multi_n_warnings(const ntsm_multi *m);
+int64_t ntsm_multi_warnings_text(const ntsm_multi *m, char *buf, size_t cap); /* returns the full length */
+int ntsm_multi_get_matrix(ntsm_multi *m, uint8_t *out /* [n_samples][n_kmers] */);
+/* printCountsMax(index) :93-138 as arrays (n_sites each; any may be NULL) and as text ("\n#locusID..." + rows:
+ * no #@TK / #@KS lines); the text call returns the length, or NTSM_ERR_NOKEY */
+int ntsm_multi_counts_max(ntsm_multi *m, uint32_t sample, uint32_t *max_ref, uint32_t *max_var, uint32_t *sum_ref,
+                          uint32_t *sum_var);
+int64_t ntsm_multi_format_counts(ntsm_multi *m, const ntsm_sites *s, uint32_t sample, char *buf, size_t cap);
+/* printNormMatrix :148-203, the numbers: values[site * n_samples + sample] = maxREF / (maxREF + maxVAR), or
+ * DBL_MAX (MultiCount::UNDEF) where both are zero; sums[site] = the sum of the site's defined values taken in
+ * sample order (the reference divides it by n_samples in long double to get the centre).  Either may be NULL. */
+int ntsm_multi_norm_matrix(ntsm_multi *m, double *values, double *sums);
+/* printNormMatrix, the two files (matrix with missing values replaced by the centre; one centre per line),
+ * digit for digit including the stream precision that switches to 19 at the first missing value */
+int ntsm_multi_write_norm_matrix(ntsm_multi *m, const ntsm_sites *s, const char *const *sample_ids, const char *matrix_path,
+                                 const char *center_path);
+
+/* VCFConvert() + count(vcf) :42-174: reads the reference genome (plain or gz FASTA) and the multi-sample VCF
+ * (plain text), cuts the window around every SNP line (getSeqFromSite :202-215) and inserts batches of lines on
+ * the GPU.  NTSM_ERR_ARG for a site whose window would start before its chromosome (undefined upstream). */
+int ntsm_vcf_convert(ntsm_vcf **out, ntsm_ctx *ctx, const ntsm_sites *s, const char *ref_path, const char *vcf_path,
+                     uint32_t multi /* opt::multi, 20 */, uint32_t window /* opt::window, 31 */, int verbose);
+void ntsm_vcf_destroy(ntsm_vcf *v);
+ntsm_multi *ntsm_vcf_multi(ntsm_vcf *v);
+uint32_t ntsm_vcf_n_samples(const ntsm_vcf *v);
+const char *ntsm_vcf_sample_id(const ntsm_vcf *v, uint32_t i);
+uint64_t ntsm_vcf_lines_counted(const ntsm_vcf *v);
+int ntsm_vcf_output_matrix(ntsm_vcf *v, const char *prefix); /* outputMatrix :186-193: <prefix>_matrix.tsv, <prefix>_center.txt */
+int ntsm_vcf_output_counts(ntsm_vcf *v, const char *dir);    /* outputCounts :173-184: <dir>/<sampleID>.counts.txt (NULL = cwd) */
+/* the ntsmVCF command line (src/ntSeqMatchVCF.cpp:53-217); returns the process exit code */
+int ntsm_vcf_main(int argc, char **argv);
+
 /* the ntsmCount command line (src/ntSeqMatchCount.cpp:53-184); returns the process exit code */
 int ntsm_main(int argc, char **argv);
 

@@ -106,6 +106,28 @@ _SIGS = {
     "ntsm_crc32": (C.c_uint32, [C.c_uint32, C.c_void_p, C.c_uint64]),
     "ntsm_count_files": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_int)]),
     "ntsm_main": (C.c_int, [C.c_int, _P]),
+    # multi-sample matrix path (MultiCount / VCFConvert)
+    "ntsm_multi_create": (C.c_int, [C.POINTER(_P), _P, C.c_uint32]),
+    "ntsm_multi_destroy": (None, [_P]),
+    "ntsm_multi_n_samples": (C.c_uint32, [_P]),
+    "ntsm_multi_insert_count": (C.c_int, [_P, C.c_uint32, C.c_uint64, C.c_uint32]),
+    "ntsm_multi_insert_windows": (C.c_int, [_P, _P, C.c_uint32, _P, _P, C.c_uint32, C.c_uint32]),
+    "ntsm_multi_n_warnings": (C.c_uint64, [_P]),
+    "ntsm_multi_warnings_text": (C.c_int64, [_P, _P, C.c_size_t]),
+    "ntsm_multi_get_matrix": (C.c_int, [_P, _P]),
+    "ntsm_multi_counts_max": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
+    "ntsm_multi_format_counts": (C.c_int64, [_P, _P, C.c_uint32, _P, C.c_size_t]),
+    "ntsm_multi_norm_matrix": (C.c_int, [_P, _P, _P]),
+    "ntsm_multi_write_norm_matrix": (C.c_int, [_P, _P, _P, C.c_char_p, C.c_char_p]),
+    "ntsm_vcf_convert": (C.c_int, [C.POINTER(_P), _P, _P, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_int]),
+    "ntsm_vcf_destroy": (None, [_P]),
+    "ntsm_vcf_multi": (_P, [_P]),
+    "ntsm_vcf_n_samples": (C.c_uint32, [_P]),
+    "ntsm_vcf_sample_id": (C.c_char_p, [_P, C.c_uint32]),
+    "ntsm_vcf_lines_counted": (C.c_uint64, [_P]),
+    "ntsm_vcf_output_matrix": (C.c_int, [_P, C.c_char_p]),
+    "ntsm_vcf_output_counts": (C.c_int, [_P, C.c_char_p]),
+    "ntsm_vcf_main": (C.c_int, [C.c_int, _P]),
 }
 
 _lib = None

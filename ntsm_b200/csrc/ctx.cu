@@ -908,6 +908,24 @@ int ntsm_batch_copy_done(ntsm_batch *b)
 }
 int ntsm_ctx_parser_procs(const ntsm_ctx *c) { return c->opt_parser_procs; }
 uint32_t ntsm_ctx_k(const ntsm_ctx *c) { return c->cfg.k; }
+// what the multi-sample matrix path (multi.cu) needs of a ctx: the exact table, the site lists, the stream
+int ntsm_ctx_view_get(ntsm_ctx *c, ntsm_ctx_view *v)
+{
+	if (!c || !v) return NTSM_ERR_ARG;
+	if (!c->d_table) return fail(c, NTSM_ERR_ARG, "no site table loaded");
+	v->device = c->device;
+	v->k = c->cfg.k;
+	v->n_kmers = c->n_kmers;
+	v->n_sites = c->n_sites;
+	v->table_mask = c->table_cap - 1;
+	v->d_table = c->d_table;
+	v->d_allele_off = c->d_allele_off;
+	v->stream = c->compute_stream;
+	return NTSM_OK;
+}
+void ntsm_ctx_add_launches(ntsm_ctx *c, uint64_t n) { c->launches += n; }
+void ntsm_ctx_add_pcie(ntsm_ctx *c, uint64_t h2d, uint64_t d2h) { c->h2d_bytes += h2d; c->d2h_bytes += d2h; }
+void ntsm_ctx_set_error(ntsm_ctx *c, const char *text) { t_last_error = text; if (c) c->err = text; }
 
 extern "C" int ntsm_release_batch(ntsm_ctx *c, ntsm_batch *b)
 {

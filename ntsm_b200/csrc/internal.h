@@ -23,3 +23,15 @@ int ntsm_submit_foreign(ntsm_ctx *c, const void *bases, const void *mask, uint64
 int ntsm_batch_copy_done(ntsm_batch *b);
 int ntsm_ctx_parser_procs(const ntsm_ctx *c);
 uint32_t ntsm_ctx_k(const ntsm_ctx *c);
+// the multi-sample matrix path (multi.cu) works on a ctx's exact table and site lists
+struct ntsm_ctx_view {
+	int device;
+	uint32_t k, n_kmers, n_sites, table_mask;
+	const void *d_table;              // ntsm::TableSlot[table_mask + 1]
+	const uint32_t *d_allele_off;     // [2 * n_sites + 1]
+	void *stream;                     // the ctx's compute stream (cudaStream_t)
+};
+int ntsm_ctx_view_get(ntsm_ctx *c, ntsm_ctx_view *v);
+void ntsm_ctx_add_launches(ntsm_ctx *c, uint64_t n);
+void ntsm_ctx_add_pcie(ntsm_ctx *c, uint64_t h2d, uint64_t d2h);
+void ntsm_ctx_set_error(ntsm_ctx *c, const char *text);

@@ -25,15 +25,10 @@
 #include <stdint.h>
 
 #include "kmer_math.h"
+#include "table.cuh"
 
 namespace ntsm {
 
-struct __align__(16) TableSlot {
-	uint64_t key;    // reference hash64 value; kEmptyKey = unused
-	uint32_t idx;    // dense k-mer index into counts[]
-	uint32_t pad;
-};
-constexpr uint64_t kEmptyKey = ~0ULL;
 
 struct CountParams {
 	const uint2 *bases;        // 32 positions per element (two little-endian uint32 words)

@@ -1,0 +1,580 @@
+// vcf.cpp -- host side of the multi-sample matrix path: VCFConvert (src/VCFConvert.hpp:40-218) and the
+// ntsmVCF command line (src/ntSeqMatchVCF.cpp:53-217) over the device MultiCount of multi.cu.
+//
+// The host only reads text: the reference genome (kseq grammar, fastx.h), the VCF's header and data lines, the
+// window around each SNP (getSeqFromSite, :202-215) and one genotype code per sample.  Batches of lines go to
+// ntsm_multi_insert_windows, where every k-mer x sample insert of VCFConvert::count's inner loops (:148-169) runs on
+// the GPU.  The printers format what the device reduced (ntsm_multi_norm_matrix, ntsm_multi_counts_max) with the
+// ostream state the reference carries (printNormMatrix's sticky setprecision(19), src/MultiCount.hpp:148-203).
+//
+// Where the reference process dies (uncaught exception / failed assert, rc 134) the calls return NTSM_ERR_NOKEY;
+// where it has undefined behaviour (a site closer than window/2 to the start of its chromosome, or past its end:
+// getSeqFromSite reads outside the sequence) they return NTSM_ERR_ARG.
+#include <errno.h>
+#include <fcntl.h>
+#include <getopt.h>
+#include <limits.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ntsm_b200.h"
+#include "fastx.h"
+#include "internal.h"
+
+struct ntsm_vcf {
+	ntsm_ctx *ctx = nullptr;
+	const ntsm_sites *sites = nullptr;
+	ntsm_multi *multi = nullptr;
+	std::vector<std::string> sample_ids;        // m_sampleIDs (:192)
+	uint64_t lines_counted = 0;                 // SNP lines whose windows were inserted
+};
+
+namespace {
+
+int vfail(ntsm_ctx *ctx, int code, const std::string &text)
+{
+	ntsm_ctx_set_error(ctx, text.c_str());
+	return code;
+}
+
+// the whole input as one span: a mapping for regular files, a buffer for anything else (the reference reads
+// the VCF through an ifstream, :69: plain text only)
+struct Text {
+	const char *p = nullptr;
+	size_t n = 0;
+	void *map = nullptr;
+	std::string own;
+	bool open(const char *path)
+	{
+		const int fd = ::open(path, O_RDONLY);
+		if (fd < 0) return false;
+		struct stat st;
+		if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+			map = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+			if (map != MAP_FAILED) {
+				p = (const char *)map;
+				n = (size_t)st.st_size;
+				::close(fd);
+				return true;
+			}
+			map = nullptr;
+		}
+		char buf[1 << 16];
+		ssize_t got;
+		while ((got = read(fd, buf, sizeof buf)) > 0) own.append(buf, (size_t)got);
+		::close(fd);
+		p = own.data();
+		n = own.size();
+		return true;
+	}
+	~Text()
+	{
+		if (map) munmap(map, n);
+	}
+};
+
+struct Field { const char *p; size_t n; };
+
+// tab-separated fields of one line; getline(ss, item, '\t') semantics: a trailing tab yields a last empty field
+void split(const char *p, size_t n, std::vector<Field> &f)
+{
+	f.clear();
+	const char *end = p + n, *at = p;
+	for (;;) {
+		const char *t = (const char *)memchr(at, '\t', (size_t)(end - at));
+		if (!t) { f.push_back({ at, (size_t)(end - at) }); break; }
+		f.push_back({ at, (size_t)(t - at) });
+		at = t + 1;
+	}
+}
+
+struct Chrom { std::string seq; };
+
+inline uint8_t genotype_code(const char *g, size_t n)
+{   // :138-144; anything else keeps the vector's value-initialised hom1
+	if (n != 3 || g[1] != '|') return 0;
+	if (g[0] == '0') return g[2] == '1' ? 1 : 0;           // "0|0" hom1, "0|1" het ("0|x" otherwise: hom1)
+	if (g[0] == '1') return g[2] == '0' ? 1 : g[2] == '1' ? 2 : 0;
+	return 0;
+}
+
+}  // namespace
+
+extern "C" void ntsm_vcf_destroy(ntsm_vcf *v)
+{
+	if (!v) return;
+	ntsm_multi_destroy(v->multi);
+	delete v;
+}
+
+extern "C" ntsm_multi *ntsm_vcf_multi(ntsm_vcf *v) { return v ? v->multi : nullptr; }
+extern "C" uint32_t ntsm_vcf_n_samples(const ntsm_vcf *v) { return v ? (uint32_t)v->sample_ids.size() : 0; }
+extern "C" const char *ntsm_vcf_sample_id(const ntsm_vcf *v, uint32_t i) { return v && i < v->sample_ids.size() ? v->sample_ids[i].c_str() : nullptr; }
+extern "C" uint64_t ntsm_vcf_lines_counted(const ntsm_vcf *v) { return v ? v->lines_counted : 0; }
+
+// VCFConvert::VCFConvert (:42-59) + VCFConvert::count (:62-174)
+extern "C" int ntsm_vcf_convert(ntsm_vcf **out, ntsm_ctx *ctx, const ntsm_sites *sites, const char *ref_path, const char *vcf_path,
+                                uint32_t multi, uint32_t window, int verbose)
+{
+	if (!out || !ctx || !sites || !ref_path || !vcf_path) return vfail(ctx, NTSM_ERR_ARG, "ntsm_vcf_convert: null argument");
+	*out = nullptr;
+	if (window == 0 || window > 65535) return vfail(ctx, NTSM_ERR_ARG, "window must be in 1..65535");
+
+	// the reference genome: every record whole; a later record of the same name replaces the earlier one (:47-58)
+	if (verbose > 1) std::cerr << "Loading Reference " << ref_path << std::endl;
+	std::vector<Chrom> chroms;
+	std::unordered_map<std::string, uint32_t> chr_ids;
+	{
+		ntsm::FastxReader rd;
+		if (!rd.open(ref_path, 0, false)) return vfail(ctx, NTSM_ERR_IO, std::string("file ") + ref_path + " cannot be opened");
+		int64_t l;
+		while ((l = rd.next()) >= 0) {
+			chr_ids[rd.name()] = (uint32_t)chroms.size();
+			chroms.emplace_back();
+			chroms.back().seq.assign(rd.seq(), (size_t)l);
+		}
+	}
+
+	if (verbose > 1) std::cerr << "Reading VCF file: " << vcf_path << std::endl;
+	Text text;
+	if (!text.open(vcf_path)) return vfail(ctx, NTSM_ERR_IO, std::string("file ") + vcf_path + " cannot be opened");
+	const char *at = text.p, *const end = text.p + text.n;
+
+	ntsm_vcf *v = new ntsm_vcf();
+	v->ctx = ctx;
+	v->sites = sites;
+	std::vector<Field> f;
+	// header: lines are looked at until the one whose first field is "#CHROM"; 8 more fields are skipped, the rest
+	// are the sample IDs (:71-93).  A last line without '\n' is still a line here (the stream only goes bad after it).
+	while (at < end) {
+		const char *nl = (const char *)memchr(at, '\n', (size_t)(end - at));
+		const char *le = nl ? nl : end;
+		const size_t len = (size_t)(le - at);
+		if (len == 0) {                                            // line.at(0) throws
+			ntsm_vcf_destroy(v);
+			return vfail(ctx, NTSM_ERR_NOKEY, "empty line before the #CHROM line: the reference dies in string::at (src/VCFConvert.hpp:74)");
+		}
+		const bool is_header = at[0] == '#';
+		if (is_header) split(at, len, f);
+		at = nl ? nl + 1 : end;
+		if (is_header && f[0].n == 6 && memcmp(f[0].p, "#CHROM", 6) == 0) {
+			for (size_t i = 9; i < f.size(); ++i) v->sample_ids.emplace_back(f[i].p, f[i].n);
+			break;
+		}
+	}
+	const uint32_t S = (uint32_t)v->sample_ids.size();
+	if (verbose > 1) std::cerr << "Starting multicount of each rsID for " << S << " samples." << std::endl;
+	int rc = ntsm_multi_create(&v->multi, ctx, S);
+	if (rc) {
+		ntsm_vcf_destroy(v);
+		return rc;
+	}
+
+	const uint32_t half = window / 2;
+	const uint32_t wstride = (window + 15u) & ~15u;
+	const uint32_t batch_lines = 4096;
+	std::vector<char> windows((size_t)batch_lines * 2 * wstride);
+	std::vector<uint16_t> lens((size_t)batch_lines * 2);
+	std::vector<uint8_t> geno((size_t)batch_lines * (S ? S : 1));
+	uint32_t n = 0;
+	auto flush = [&]() -> int {
+		if (n == 0) return NTSM_OK;
+		const int r = ntsm_multi_insert_windows(v->multi, windows.data(), wstride, lens.data(), geno.data(), n, multi);
+		v->lines_counted += n;
+		n = 0;
+		return r;
+	};
+	auto die = [&](int code, const std::string &msg) {
+		ntsm_vcf_destroy(v);
+		return vfail(ctx, code, msg);
+	};
+
+	while (at < end) {
+		const char *nl = (const char *)memchr(at, '\n', (size_t)(end - at));
+		if (!nl) break;                                            // :101-108: the getline that hits end of file leaves the stream not good(): that line is dropped
+		split(at, (size_t)(nl - at), f);
+		at = nl + 1;
+		// getline on an exhausted stringstream leaves `item` as it was: a missing field reads as the last present one
+		auto field = [&](size_t i) -> const Field & { return f[i < f.size() ? i : f.size() - 1]; };
+		const std::string chr(field(0).p, field(0).n);
+		const std::string pos_text(field(1).p, field(1).n);
+		char *pe;
+		errno = 0;
+		const long loc_l = strtol(pos_text.c_str(), &pe, 10);       // stoi (:113)
+		if (pe == pos_text.c_str() || errno == ERANGE || loc_l > INT_MAX || loc_l < INT_MIN)
+			return die(NTSM_ERR_NOKEY, "POS '" + pos_text + "' is not an int: the reference dies in stoi (src/VCFConvert.hpp:113)");
+		if (verbose > 2) std::cerr << "Processing site: " << std::string(field(2).p, field(2).n) << std::endl;
+		if (field(3).n == 1 && field(3).p[0] == '.') continue;     // :121-123
+		if (field(4).n != 1) continue;                             // :125-127: ALT must be one character (REF's length is not looked at)
+		const char alt = field(4).p[0];
+		// getSeqFromSite (:202-215)
+		const auto it = chr_ids.find(chr);
+		if (it == chr_ids.end())
+			return die(NTSM_ERR_NOKEY, "chromosome '" + chr + "' is not in the reference: the reference dies in robin_map::at (src/VCFConvert.hpp:204)");
+		const std::string &seq = chroms[it->second].seq;
+		if (loc_l < (long)half + 1 || (size_t)(loc_l - half - 1) > seq.size())
+			return die(NTSM_ERR_ARG, "site " + chr + ":" + pos_text + " lies outside what getSeqFromSite can cut (src/VCFConvert.hpp:207-209 reads outside the sequence there)");
+		const size_t offset = (size_t)loc_l - half - 1;
+		size_t avail = std::min<size_t>(seq.size() - offset, window);            // strncpy stops at the sequence's NUL (or one inside it) and pads with NULs
+		avail = strnlen(seq.data() + offset, avail);
+		char *wr = windows.data() + (size_t)n * 2 * wstride, *wv = wr + wstride;
+		memset(wr, 0, 2 * (size_t)wstride);
+		memcpy(wr, seq.data() + offset, avail);
+		memcpy(wv, seq.data() + offset, avail);
+		if (half < wstride) wv[half] = alt;                        // :211
+		// std::string(refStr): up to the first NUL -- which may also be a NUL byte inside the genome or the ALT column
+		lens[2 * (size_t)n] = (uint16_t)strnlen(wr, window);
+		lens[2 * (size_t)n + 1] = (uint16_t)strnlen(wv, window);
+		// sample columns (:129-146)
+		const size_t n_cols = f.size() > 9 ? f.size() - 9 : 0;
+		if (n_cols != S)
+			return die(NTSM_ERR_NOKEY, "line for " + chr + ":" + pos_text + " has " + std::to_string(n_cols) + " sample columns, the header names " +
+			                               std::to_string(S) + ": the reference dies on its assert (src/VCFConvert.hpp:146)");
+		uint8_t *g = geno.data() + (size_t)n * S;
+		for (uint32_t s = 0; s < S; ++s) g[s] = genotype_code(f[9 + s].p, f[9 + s].n);
+		if (++n == batch_lines && (rc = flush())) {
+			ntsm_vcf_destroy(v);
+			return rc;
+		}
+	}
+	if ((rc = flush())) {
+		ntsm_vcf_destroy(v);
+		return rc;
+	}
+	*out = v;
+	return NTSM_OK;
+}
+
+// ---- printers ----
+namespace {
+
+// ostream << double at the stream's precision, with the few distinct values a matrix holds formatted once
+struct DoubleText {
+	struct Slot { uint64_t bits; int prec; uint8_t len; char text[32]; };
+	std::vector<Slot> slots = std::vector<Slot>(1024, Slot{ 0, 0, 0, { 0 } });
+	void put(std::string &o, double v, int prec)
+	{
+		uint64_t b;
+		memcpy(&b, &v, 8);
+		Slot &s = slots[((b * 0x9E3779B97F4A7C15ull) >> 54) ^ (prec == 6 ? 0 : 512)];
+		if (s.len == 0 || s.bits != b || s.prec != prec) {
+			s.bits = b;
+			s.prec = prec;
+			s.len = (uint8_t)snprintf(s.text, sizeof s.text, "%.*g", prec, v);
+		}
+		o.append(s.text, s.len);
+	}
+};
+
+}  // namespace
+
+// MultiCount::printNormMatrix (src/MultiCount.hpp:148-203) into two files
+extern "C" int ntsm_multi_write_norm_matrix(ntsm_multi *m, const ntsm_sites *sites, const char *const *sample_ids, const char *matrix_path,
+                                            const char *center_path)
+{
+	if (!m || !sites || !matrix_path || !center_path) return NTSM_ERR_ARG;
+	const uint32_t S = ntsm_sites_n_sites(sites), N = ntsm_multi_n_samples(m);
+	FILE *out = fopen(matrix_path, "wb");
+	FILE *cf = fopen(center_path, "wb");
+	if (!out || !cf) {
+		if (out) fclose(out);
+		if (cf) fclose(cf);
+		ntsm_set_thread_error("cannot open the matrix / center file for writing");
+		return NTSM_ERR_IO;
+	}
+	std::string o = "alleleID";                                    // :149-154
+	for (uint32_t j = 0; j < N; ++j) {
+		o += "\t";
+		o += sample_ids[j];
+	}
+	o += "\n";
+	fwrite(o.data(), 1, o.size(), out);
+	int rc = NTSM_OK;
+	if (ntsm_sites_printable(sites) != NTSM_OK) rc = NTSM_ERR_NOKEY;   // the first `at` on an erased k-mer / a missing var list throws (:158,:169)
+	std::vector<double> values, sums;
+	if (rc == NTSM_OK && S) {
+		values.resize((size_t)S * N + 1);
+		sums.resize(S);
+		rc = ntsm_multi_norm_matrix(m, values.data(), sums.data());
+	}
+	if (rc == NTSM_OK) {
+		int precision = 6;                                         // the stream's; setprecision(19) at the first missing value sticks (:192)
+		DoubleText cache;
+		char num[64];
+		std::string c;
+		for (uint32_t i = 0; i < S; ++i) {
+			o.assign(ntsm_sites_name(sites, i));                   // :187
+			const long double center = (long double)sums[i] / (long double)(uint64_t)N;   // :188-189: size counts every sample
+			const int cl = snprintf(num, sizeof num, "%.19Lg", center);
+			const double *row = values.data() + (size_t)i * N;
+			for (uint32_t j = 0; j < N; ++j) {
+				o.push_back('\t');
+				if (row[j] == 1.7976931348623157e308) {            // UNDEF (:41,190)
+					precision = 19;
+					o.append(num, (size_t)cl);
+				} else cache.put(o, row[j], precision);            // :194
+			}
+			o.push_back('\n');
+			fwrite(o.data(), 1, o.size(), out);
+			c.assign(num, (size_t)cl);                             // :198
+			c.push_back('\n');
+			fwrite(c.data(), 1, c.size(), cf);
+		}
+	}
+	fclose(out);
+	fclose(cf);
+	return rc;
+}
+
+// MultiCount::printCountsMax(index) (:93-138): the counts file of one sample, without the #@TK / #@KS lines
+extern "C" int64_t ntsm_multi_format_counts(ntsm_multi *m, const ntsm_sites *sites, uint32_t sample, char *buf, size_t cap)
+{
+	if (!m || !sites) return NTSM_ERR_ARG;
+	const uint32_t S = ntsm_sites_n_sites(sites);
+	std::vector<uint32_t> mr(S + 1), mv(S + 1), sr(S + 1), sv(S + 1);
+	const int rc = ntsm_multi_counts_max(m, sample, mr.data(), mv.data(), sr.data(), sv.data());
+	if (rc) return rc;
+	// same rows as FingerPrint::printCountsMax: ntsm_format_counts's text minus its two header lines
+	const int64_t need = ntsm_format_counts(sites, mr.data(), mv.data(), sr.data(), sv.data(), 0, nullptr, 0);
+	if (need < 0) return need;
+	std::string t((size_t)need, '\0');
+	ntsm_format_counts(sites, mr.data(), mv.data(), sr.data(), sv.data(), 0, &t[0], t.size());
+	const size_t cut = t.find("\n#locusID");                       // printCountsMax starts with that "\n" (:94)
+	const size_t len = t.size() - cut;
+	if (buf) memcpy(buf, t.data() + cut, std::min(cap, len));
+	return (int64_t)len;
+}
+
+// VCFConvert::outputMatrix (:186-193)
+extern "C" int ntsm_vcf_output_matrix(ntsm_vcf *v, const char *prefix)
+{
+	if (!v || !prefix) return NTSM_ERR_ARG;
+	std::vector<const char *> ids;
+	for (const std::string &s : v->sample_ids) ids.push_back(s.c_str());
+	ids.push_back(nullptr);
+	const std::string p(prefix);
+	return ntsm_multi_write_norm_matrix(v->multi, v->sites, ids.data(), (p + "_matrix.tsv").c_str(), (p + "_center.txt").c_str());
+}
+
+// VCFConvert::outputCounts (:173-184): <dir>/<sampleID>.counts.txt for every sample (the reference writes into the
+// working directory; dir == NULL or "" does the same)
+extern "C" int ntsm_vcf_output_counts(ntsm_vcf *v, const char *dir)
+{
+	if (!v) return NTSM_ERR_ARG;
+	const std::string d = dir && *dir ? std::string(dir) + "/" : std::string();
+	for (uint32_t i = 0; i < v->sample_ids.size(); ++i) {
+		const int64_t need = ntsm_multi_format_counts(v->multi, v->sites, i, nullptr, 0);
+		if (need < 0) return (int)need;
+		std::string t((size_t)need, '\0');
+		ntsm_multi_format_counts(v->multi, v->sites, i, &t[0], t.size());
+		FILE *fh = fopen((d + v->sample_ids[i] + ".counts.txt").c_str(), "wb");
+		if (!fh) {
+			ntsm_set_thread_error(("cannot write " + d + v->sample_ids[i] + ".counts.txt").c_str());
+			return NTSM_ERR_IO;
+		}
+		fwrite(t.data(), 1, t.size(), fh);
+		fclose(fh);
+	}
+	return NTSM_OK;
+}
+
+// ---- the ntsmVCF command line (src/ntSeqMatchVCF.cpp:53-217) ----
+#define PROGRAM "ntsmVCF"
+
+namespace {
+
+size_t vcf_rss_kb()
+{   // src/Util.h:31-50
+	std::ifstream f("/proc/self/status");
+	std::string line;
+	while (std::getline(f, line))
+		if (line.compare(0, 6, "VmRSS:") == 0) return (size_t)strtoull(line.c_str() + 6, nullptr, 10);
+	return 0;
+}
+
+bool vcf_fexists(const std::string &p) { return std::ifstream(p.c_str()).good(); }   // src/Util.h:22
+
+template <class T> bool vcf_parse(const char *arg, T &out)
+{
+	std::stringstream ss(arg ? arg : "");
+	return (bool)(ss >> out);
+}
+
+const char kVcfHelp[] =
+    "Usage: " PROGRAM " -s [FASTA] -r [FASTA] [VCF]\n"
+    "Converts a multi vcf file to a set of counts files.\n"
+    "Alternatively, you may also create a matrix to be used for PCA.\n"
+    "  -t, --threads = INT    Number of threads to run.[1]\n"
+    "  -d, --dupes            Allow shared k-mers between sites to\n"
+    "                         be counted.\n"
+    "  -s, --snp = STR        Interleaved fasta of SNP sites to\n"
+    "                         k-merize. [required]\n"
+    "  -p, --pca = STR        With multivcf generate rotation and\n"
+    "                         centering files with this prefix.\n"
+    "  -k, --kmer = INT       k-mer size used. [19]\n"
+    "  -m, --multi = INT      Value to multiply base counts [20]\n"
+    "  -w, --window = INT     Window size used. [31]\n"
+    "  -r, --ref = STR        Reference fasta. [required]\n"
+    "  -h, --help             Display this dialog.\n"
+    "  -v, --verbose          Display verbose output.\n"
+    "      --version          Print version information.\n";
+
+}  // namespace
+
+extern "C" int ntsm_vcf_main(int argc, char **argv)
+{
+	bool die = false;
+	int opt_version = 0, opt_counts = 0, verbose = 0, device = 0;
+	unsigned threads = 1, k = 19, multi = 20, window = 31;
+	bool dupes = false;
+	std::string snp, ref, pca;
+	static struct option long_options[] = { { "threads", required_argument, nullptr, 't' }, { "dupes", no_argument, nullptr, 'd' },
+		                                    { "snp", required_argument, nullptr, 's' },     { "pca", required_argument, nullptr, 'p' },
+		                                    { "kmer", required_argument, nullptr, 'k' },    { "multi", required_argument, nullptr, 'm' },
+		                                    { "window", required_argument, nullptr, 'w' },  { "ref", required_argument, nullptr, 'r' },
+		                                    { "help", no_argument, nullptr, 'h' },          { "version", no_argument, &opt_version, 1 },
+		                                    { "verbose", no_argument, nullptr, 'v' },
+		                                    // additions (long options only): per-sample counts files (VCFConvert::outputCounts, which the
+		                                    // reference's main never calls), and the GPU to use
+		                                    { "counts", no_argument, &opt_counts, 1 },      { "device", required_argument, nullptr, 1000 },
+		                                    { nullptr, 0, nullptr, 0 } };
+	optind = 1;
+	int c;
+	while ((c = getopt_long(argc, argv, "s:t:vhk:dr:w:m:p:", long_options, nullptr)) != -1) {
+		switch (c) {
+		case 'h': std::cerr << kVcfHelp << std::endl; return 0;
+		case 'd': dupes = true; break;
+		case 'v': verbose++; break;
+		case '?': die = true; break;
+		case 0: break;
+		default: {
+			bool ok = true;
+			if (c == 's') ok = vcf_parse(optarg, snp);
+			else if (c == 'p') ok = vcf_parse(optarg, pca);
+			else if (c == 'k') ok = vcf_parse(optarg, k);
+			else if (c == 'w') ok = vcf_parse(optarg, window);
+			else if (c == 'm') ok = vcf_parse(optarg, multi);
+			else if (c == 't') ok = vcf_parse(optarg, threads);
+			else if (c == 'r') ok = vcf_parse(optarg, ref);
+			else if (c == 1000) ok = vcf_parse(optarg, device);
+			if (!ok) {
+				std::cerr << "Error - Invalid parameter " << (char)(c == 1000 ? 'D' : c) << ": " << optarg << std::endl;
+				return 0;                                          // ntSeqMatchVCF.cpp:95,103,...: `return 0`
+			}
+		}
+		}
+	}
+	if (opt_version) {
+		std::cerr << PROGRAM " (ntsm) 663f9a5 -- ntsm_b200 matrix path\n"
+		             "Written by Justin Chu <cjustin@ds.dfci.harvard.edu>\n\nCopyright 2020 Dana-Farber Cancer Institute\n"
+		          << std::endl;
+		return 0;
+	}
+	if (k > 32) {
+		die = true;
+		std::cerr << "k cannot be greater than 32" << std::endl;
+	} else if (k == 32 || k == 0) {
+		die = true;
+		std::cerr << "k must be in 1..31 here (k = 32 is undefined behaviour upstream, vendor/KseqHashIterator.hpp:29)" << std::endl;
+	}
+	std::vector<std::string> inputs;
+	while (optind < argc) {
+		inputs.emplace_back(argv[optind++]);
+		if (!vcf_fexists(inputs.back())) {                         // assert(Util::fexists(...)) (:172)
+			std::cerr << PROGRAM ": " << inputs.back() << " does not exist" << std::endl;
+			return 134;
+		}
+	}
+	if (inputs.empty()) {
+		std::cerr << "Error: Need Input File" << std::endl;
+		die = true;
+	}
+	if (!vcf_fexists(ref)) {
+		std::cerr << "Error: Unable to load reference file" << std::endl;
+		die = true;
+	}
+	if (die) {
+		std::cerr << "Try '--help' for more information.\n";
+		return EXIT_FAILURE;
+	}
+	if (inputs.size() != 1) {                                       // assert(inputFiles.size() == 1) (:199)
+		std::cerr << PROGRAM ": exactly one VCF file is expected" << std::endl;
+		return 134;
+	}
+	const auto t0 = std::chrono::steady_clock::now();
+	if (ntsm_device_count() == 0) {
+		std::cerr << PROGRAM ": no CUDA device; this build has no CPU path" << std::endl;
+		return 1;
+	}
+	// the GPU's context comes up while the site file is read
+	std::thread warm([device] { ntsm_device_warmup(device); });
+	ntsm_sites *sites = nullptr;
+	int rc = ntsm_sites_load(&sites, snp.c_str(), k, dupes ? 1 : 0);
+	warm.join();
+	if (rc) {
+		std::cerr << "file " << snp << " cannot be opened" << std::endl;   // MultiCount.hpp:219-222
+		return 1;
+	}
+	for (uint32_t i = 0; i < ntsm_sites_n_warnings(sites); ++i) std::cerr << ntsm_sites_warning(sites, i) << std::endl;
+	ntsm_cfg cfg{};
+	cfg.k = k;
+	cfg.device = device;
+	cfg.n_buffers = 2;
+	cfg.batch_bases = 4096;
+	ntsm_ctx *ctx = nullptr;
+	if ((rc = ntsm_ctx_create(&ctx, &cfg)) || (rc = ntsm_load_siteset(ctx, sites))) {
+		std::cerr << PROGRAM ": " << ntsm_last_error(ctx) << std::endl;
+		return 1;
+	}
+	ntsm_vcf *v = nullptr;
+	rc = ntsm_vcf_convert(&v, ctx, sites, ref.c_str(), inputs[0].c_str(), multi, window, verbose);
+	const auto fail_exit = [&](int code) {
+		if (code == NTSM_ERR_NOKEY) {
+			std::cerr << "terminate called after throwing an instance of 'std::out_of_range'\n  what():  " << ntsm_last_error(ctx) << std::endl;
+			return 134;
+		}
+		std::cerr << PROGRAM ": " << ntsm_last_error(ctx) << std::endl;
+		return 1;
+	};
+	if (rc) return fail_exit(rc);
+	{
+		const int64_t wl = ntsm_multi_warnings_text(ntsm_vcf_multi(v), nullptr, 0);
+		if (wl > 0) {
+			std::string w((size_t)wl, '\0');
+			ntsm_multi_warnings_text(ntsm_vcf_multi(v), &w[0], w.size());
+			fwrite(w.data(), 1, w.size(), stderr);
+		}
+	}
+	if (pca.empty()) {
+		if (verbose > 1) std::cerr << "Outputting counts" << std::endl;   // :201-204 (and nothing else: the reference's main never calls outputCounts)
+	} else {
+		if (verbose > 1) std::cerr << "Outputting matrix and normalization values for PCA" << std::endl;
+		if ((rc = ntsm_vcf_output_matrix(v, pca.c_str()))) {
+			if (rc == NTSM_ERR_NOKEY) ntsm_ctx_set_error(ctx, "Couldn't find key.");
+			return fail_exit(rc);
+		}
+	}
+	if (opt_counts && (rc = ntsm_vcf_output_counts(v, nullptr))) {
+		if (rc == NTSM_ERR_NOKEY) ntsm_ctx_set_error(ctx, "Couldn't find key.");
+		return fail_exit(rc);
+	}
+	const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	std::cerr << "Time: " << secs << " s Memory: " << vcf_rss_kb() << " kbytes" << std::endl;   // :213-214
+	ntsm_vcf_destroy(v);
+	ntsm_ctx_destroy(ctx);
+	ntsm_sites_free(sites);
+	return 0;
+}

@@ -9,6 +9,7 @@
  */
 #include "ntsm_oracle.h"
 
+#include <errno.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/types.h>
@@ -780,14 +781,16 @@ int ntsm_oracle_vcf_convert(const char *sites_path, const char *ref_path, const 
 		size_t nf;
 		char **f = split_tabs(line, &nf);
 		do {
-			if (nf < 2) { rc = -134; break; }                      /* stoi of a missing / empty POS throws */
+			/* getline on an exhausted stringstream leaves `item` as it was (:110-125): a missing field
+			 * reads as the last one present */
+#define FIELD(i) (f[(size_t)(i) < nf ? (size_t)(i) : nf - 1])
 			char *end;
-			const long loc = strtol(f[1], &end, 10);               /* stoi (:113): leading integer */
-			if (end == f[1]) { rc = -134; break; }
-			if (nf < 5) { rc = -134; break; }                      /* restated for well-formed lines only */
-			if (strcmp(f[3], ".") == 0) break;                     /* :121-123 */
-			if (strlen(f[4]) != 1) break;                          /* :125-127: ALT must be one character; REF is not looked at */
-			const char alt = f[4][0];
+			errno = 0;
+			const long loc = strtol(FIELD(1), &end, 10);           /* stoi (:113): leading integer, or it throws */
+			if (end == FIELD(1) || errno == ERANGE || loc > 2147483647L || loc < -2147483647L - 1) { rc = -134; break; }
+			if (strcmp(FIELD(3), ".") == 0) break;                 /* :121-123 */
+			if (strlen(FIELD(4)) != 1) break;                      /* :125-127: ALT must be one character; REF is not looked at */
+			const char alt = FIELD(4)[0];
 			/* getSeqFromSite (:202-215) */
 			const struct chr_rec *c = NULL;
 			for (size_t i = 0; i < n_chr; ++i)
@@ -798,12 +801,13 @@ int ntsm_oracle_vcf_convert(const char *sites_path, const char *ref_path, const 
 			const size_t offset = (size_t)loc - half - 1;
 			memset(wref, 0, window + 1);
 			memset(wvar, 0, window + 1);
-			const size_t avail = c->len - offset < window ? c->len - offset : window;   /* strncpy stops at the sequence's NUL and pads */
+			size_t avail = c->len - offset < window ? c->len - offset : window;   /* strncpy stops at the sequence's NUL (or one inside it) and pads */
+			avail = strnlen(c->seq + offset, avail);
 			memcpy(wref, c->seq + offset, avail);
 			memcpy(wvar, c->seq + offset, avail);
 			wvar[half] = alt;                                      /* :211 */
 			/* sample columns (:136-146) */
-			if (nf != 9 + (size_t)S) { rc = -134; break; }
+			if ((nf > 9 ? nf - 9 : 0) != (size_t)S) { rc = -134; break; }   /* assert(sampleIndex == m_sampleIDs.size()) */
 			for (uint32_t i = 0; i < S; ++i) {
 				const char *g = f[9 + i];
 				geno[i] = !strcmp(g, "0|0") ? 0 : (!strcmp(g, "0|1") || !strcmp(g, "1|0")) ? 1 : !strcmp(g, "1|1") ? 2 : 0;   /* anything else keeps the vector's initial hom1 */

@@ -46,6 +46,15 @@ class Oracle:
         L.ntsm_oracle_reader_next.restype = C.c_long
         L.ntsm_oracle_reader_next.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
         L.ntsm_oracle_reader_close.argtypes = [C.c_void_p]
+        # multi-sample matrix path (MultiCount / VCFConvert)
+        L.ntsm_oracle_vcf_run.restype = C.c_int
+        L.ntsm_oracle_vcf_run.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint, C.c_int, C.c_uint, C.c_uint, C.c_char_p]
+        L.ntsm_oracle_mc_create.restype = C.c_void_p
+        L.ntsm_oracle_mc_create.argtypes = [C.c_char_p, C.c_uint, C.c_int, C.c_uint32, C.c_void_p]
+        L.ntsm_oracle_mc_destroy.argtypes = [C.c_void_p]
+        L.ntsm_oracle_mc_insert.argtypes = [C.c_void_p, C.c_uint, C.c_uint64, C.c_uint, C.c_void_p]
+        L.ntsm_oracle_mc_matrix.restype = C.POINTER(C.c_uint8)
+        L.ntsm_oracle_mc_matrix.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
 
     # -- primitives ---------------------------------------------------------------
     def nt4(self, b):
@@ -76,6 +85,16 @@ class Oracle:
             out.append((nm.value, C.string_at(s, l)))
         self.L.ntsm_oracle_reader_close(r)
         return out, l
+
+    def vcf_run(self, sites, ref, vcf, prefix, k=19, dupes=0, multi=20, window=31):
+        """VCFConvert + MultiCount restated, one thread; writes <prefix>_matrix.tsv, _center.txt, _counts_<j>.txt,
+        _mat.bin, _stderr.txt (the file layout of tools/ref_vcf_harness.cpp).  Returns 0, -134 (the reference
+        dies), -2 (undefined upstream), -1 (I/O)."""
+        return self.L.ntsm_oracle_vcf_run(os.fsencode(sites), os.fsencode(ref), os.fsencode(vcf), k, int(dupes), multi, window,
+                                          os.fsencode(prefix))
+
+    def multicount(self, sites_path, n_samples, k=19, dupes=False):
+        return OracleMC(self, sites_path, n_samples, k, dupes)
 
     def fingerprint(self, sites_path, k=19, dupes=False, cov=0.0):
         return OracleFP(self, sites_path, k, dupes, cov)
@@ -155,6 +174,32 @@ class OracleFP:
         b = C.create_string_buffer(2048)
         self.L.ntsm_oracle_fp_summary(self.h, b, 2048)
         return b.value.decode()
+
+
+class OracleMC:
+    """MultiCount restated (src/MultiCount.hpp:43-70); see oracle/ntsm_oracle.h."""
+
+    def __init__(self, o, sites_path, n_samples, k, dupes):
+        self.L, self.n_samples = o.L, n_samples
+        self.h = self.L.ntsm_oracle_mc_create(os.fsencode(sites_path), k, int(dupes), n_samples, None)
+        if not self.h:
+            raise FileNotFoundError(sites_path)
+
+    def close(self):
+        if self.h:
+            self.L.ntsm_oracle_mc_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def insert(self, sample, hash_value, multi):
+        self.L.ntsm_oracle_mc_insert(self.h, sample, hash_value, multi, None)
+
+    def matrix(self):
+        n = C.c_uint64()
+        p = self.L.ntsm_oracle_mc_matrix(self.h, C.byref(n))
+        a = np.ctypeslib.as_array(p, (n.value,)).copy() if n.value else np.zeros(0, np.uint8)
+        return a.reshape(self.n_samples, -1) if self.n_samples else a.reshape(0, 0)
 
 
 def load(path):
