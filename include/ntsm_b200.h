@@ -322,6 +322,9 @@ int ntsm_multi_insert_windows(ntsm_multi *m, const char *windows, uint32_t wstri
 uint64_t ntsm_multi_n_warnings(const ntsm_multi *m);
 int64_t ntsm_multi_warnings_text(const ntsm_multi *m, char *buf, size_t cap); /* returns the full length */
 int ntsm_multi_get_matrix(ntsm_multi *m, uint8_t *out /* [n_samples][n_kmers] */);
+/* introspection (bench): device time so far by CUDA events -- ms[0] k-merize + lookup + occurrence lists, ms[1] the
+ * fill kernel's passes, ms[2] the norm-matrix kernels; cells = (occurring k-mer, sample) pairs walked per fill pass */
+void ntsm_multi_kernel_ms(const ntsm_multi *m, double ms[3], uint64_t *cells);
 /* printCountsMax(index) :93-138 as arrays (n_sites each; any may be NULL) and as text ("\n#locusID..." + rows:
  * no #@TK / #@KS lines); the text call returns the length, or NTSM_ERR_NOKEY */
 int ntsm_multi_counts_max(ntsm_multi *m, uint32_t sample, uint32_t *max_ref, uint32_t *max_var, uint32_t *sum_ref,
@@ -334,13 +337,15 @@ int ntsm_multi_norm_matrix(ntsm_multi *m, double *values, double *sums);
 /* printNormMatrix, the two files (matrix with missing values replaced by the centre; one centre per line),
  * digit for digit including the stream precision that switches to 19 at the first missing value */
 int ntsm_multi_write_norm_matrix(ntsm_multi *m, const ntsm_sites *s, const char *const *sample_ids, const char *matrix_path,
-                                 const char *center_path);
+                                 const char *center_path, uint32_t threads /* host threads that format the text */);
 
 /* VCFConvert() + count(vcf) :42-174: reads the reference genome (plain or gz FASTA) and the multi-sample VCF
  * (plain text), cuts the window around every SNP line (getSeqFromSite :202-215) and inserts batches of lines on
  * the GPU.  NTSM_ERR_ARG for a site whose window would start before its chromosome (undefined upstream). */
 int ntsm_vcf_convert(ntsm_vcf **out, ntsm_ctx *ctx, const ntsm_sites *s, const char *ref_path, const char *vcf_path,
-                     uint32_t multi /* opt::multi, 20 */, uint32_t window /* opt::window, 31 */, int verbose);
+                     uint32_t multi /* opt::multi, 20 */, uint32_t window /* opt::window, 31 */,
+                     uint32_t threads /* opt::threads: host threads that parse the VCF (and later format the matrix);
+                                         the result does not depend on it */, int verbose);
 void ntsm_vcf_destroy(ntsm_vcf *v);
 ntsm_multi *ntsm_vcf_multi(ntsm_vcf *v);
 uint32_t ntsm_vcf_n_samples(const ntsm_vcf *v);

@@ -115,11 +115,12 @@ _SIGS = {
     "ntsm_multi_n_warnings": (C.c_uint64, [_P]),
     "ntsm_multi_warnings_text": (C.c_int64, [_P, _P, C.c_size_t]),
     "ntsm_multi_get_matrix": (C.c_int, [_P, _P]),
+    "ntsm_multi_kernel_ms": (None, [_P, _P, C.POINTER(C.c_uint64)]),
     "ntsm_multi_counts_max": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
     "ntsm_multi_format_counts": (C.c_int64, [_P, _P, C.c_uint32, _P, C.c_size_t]),
     "ntsm_multi_norm_matrix": (C.c_int, [_P, _P, _P]),
-    "ntsm_multi_write_norm_matrix": (C.c_int, [_P, _P, _P, C.c_char_p, C.c_char_p]),
-    "ntsm_vcf_convert": (C.c_int, [C.POINTER(_P), _P, _P, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_int]),
+    "ntsm_multi_write_norm_matrix": (C.c_int, [_P, _P, _P, C.c_char_p, C.c_char_p, C.c_uint32]),
+    "ntsm_vcf_convert": (C.c_int, [C.POINTER(_P), _P, _P, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
     "ntsm_vcf_destroy": (None, [_P]),
     "ntsm_vcf_multi": (_P, [_P]),
     "ntsm_vcf_n_samples": (C.c_uint32, [_P]),

@@ -35,3 +35,6 @@ int ntsm_ctx_view_get(ntsm_ctx *c, ntsm_ctx_view *v);
 void ntsm_ctx_add_launches(ntsm_ctx *c, uint64_t n);
 void ntsm_ctx_add_pcie(ntsm_ctx *c, uint64_t h2d, uint64_t d2h);
 void ntsm_ctx_set_error(ntsm_ctx *c, const char *text);
+// ntsm_multi_insert_windows with the genotypes already packed 2 bits per sample (16 per uint32, (n_samples + 15) / 16 words per line)
+int ntsm_multi_insert_windows_packed(ntsm_multi *m, const char *windows, uint32_t wstride, const uint16_t *lens, const uint32_t *geno2,
+                                     uint32_t n_lines, uint32_t multi);

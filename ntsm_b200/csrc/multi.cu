@@ -36,6 +36,10 @@ struct ntsm_multi {
 	std::vector<uint32_t> h_geno;
 	// the warnings of insertCount (:59-62) in the reference's serial order: (byte found, value wanted)
 	std::vector<std::pair<uint8_t, uint32_t>> warnings;
+	// device time of the kernels, by CUDA events on the stream (ntsm_multi_kernel_ms)
+	cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+	double ms_lists = 0, ms_fill = 0, ms_norm = 0;
+	uint64_t cells_touched = 0;             // (occurring k-mer, sample) pairs the fill kernel walked, per pass
 };
 
 static int mfail(ntsm_multi *m, int code, const char *fmt, ...)
@@ -75,6 +79,8 @@ extern "C" void ntsm_multi_destroy(ntsm_multi *m)
 	                 m->d_partial, m->d_scalars, m->d_cursor, m->d_rows, m->d_one };
 	for (void *p : ptrs)
 		if (p) cudaFree(p);
+	for (cudaEvent_t e : m->ev)
+		if (e) cudaEventDestroy(e);
 	delete m;
 }
 
@@ -102,6 +108,7 @@ extern "C" int ntsm_multi_create(ntsm_multi **out, ntsm_ctx *ctx, uint32_t n_sam
 		MCU(m, cudaMalloc(&m->d_cursor, nk * 4));
 		MCU(m, cudaMalloc(&m->d_rows, (size_t)4 * (m->v.n_sites + 1) * 4));
 		MCU(m, cudaMalloc(&m->d_one, 2 * 4));
+		for (cudaEvent_t &e : m->ev) MCU(m, cudaEventCreate(&e));
 		MCU(m, cudaStreamSynchronize(m->stream));
 		return NTSM_OK;
 	};
@@ -135,7 +142,7 @@ extern "C" int ntsm_multi_insert_count(ntsm_multi *m, uint32_t sample, uint64_t 
 // one batch of at most kMaxLines lines: the four kernels of multi.cuh
 static const uint32_t kMaxLines = 1u << 15;
 
-static int insert_batch(ntsm_multi *m, const char *windows, uint32_t wstride, const uint16_t *lens, const uint8_t *genotypes,
+static int insert_batch(ntsm_multi *m, const char *windows, uint32_t wstride, const uint16_t *lens, const uint32_t *geno2,
                         uint32_t n_lines, uint32_t multi)
 {
 	const uint32_t k = m->v.k, S = m->n_samples;
@@ -166,26 +173,17 @@ static int insert_batch(ntsm_multi *m, const char *windows, uint32_t wstride, co
 		MCU(m, cudaMalloc(&m->d_uniq, n * 4));
 		m->occ_cap = n;
 	}
-	// genotypes travel as 2 bits per sample
-	m->h_geno.assign((size_t)n_lines * gwords, 0u);
-	for (uint32_t l = 0; l < n_lines; ++l) {
-		const uint8_t *g = genotypes + (size_t)l * S;
-		uint32_t *w = m->h_geno.data() + (size_t)l * gwords;
-		for (uint32_t s = 0; s < S; ++s) {
-			if (g[s] > 2) return mfail(m, NTSM_ERR_ARG, "line %u sample %u: genotype code %u (0 hom1, 1 het, 2 hom2)", l, s, g[s]);
-			w[s >> 4] |= (uint32_t)g[s] << (2 * (s & 15));
-		}
-	}
 	cudaStream_t st = m->stream;
 	MCU(m, cudaMemcpyAsync(m->d_windows, windows, (size_t)n_lines * 2 * wstride, cudaMemcpyHostToDevice, st));
 	MCU(m, cudaMemcpyAsync(m->d_lens, lens, (size_t)n_lines * 2 * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
-	MCU(m, cudaMemcpyAsync(m->d_geno, m->h_geno.data(), m->h_geno.size() * 4, cudaMemcpyHostToDevice, st));
-	ntsm_ctx_add_pcie(m->ctx, (uint64_t)n_lines * 2 * wstride + (uint64_t)n_lines * 4 + m->h_geno.size() * 4, 0);
+	MCU(m, cudaMemcpyAsync(m->d_geno, geno2, (size_t)n_lines * gwords * 4, cudaMemcpyHostToDevice, st));
+	ntsm_ctx_add_pcie(m->ctx, (uint64_t)n_lines * 2 * wstride + (uint64_t)n_lines * 4 + (uint64_t)n_lines * gwords * 4, 0);
 	const uint32_t nk = m->v.n_kmers;
 	MCU(m, cudaMemsetAsync(m->d_cnt, 0, ((size_t)nk + 1) * 8, st));
 	MCU(m, cudaMemsetAsync(m->d_cursor, 0, ((size_t)nk + 1) * 4, st));
 	MCU(m, cudaMemsetAsync(m->d_scalars, 0, 16, st));
 
+	MCU(m, cudaEventRecord(m->ev[0], st));
 	VcfBatch B{ m->d_windows, m->d_lens, wstride, n_lines, J, m->d_geno, gwords };
 	const uint32_t occ_blocks = (uint32_t)((n_occ + 255) / 256);
 	vcf_kmerize_kernel<<<occ_blocks, 256, 0, st>>>(B, k, (const TableSlot *)m->v.d_table, m->v.table_mask, m->d_occ, m->d_cnt);
@@ -195,16 +193,21 @@ static int insert_batch(ntsm_multi *m, const char *windows, uint32_t wstride, co
 	occ_scan_add_kernel<<<nk / kScanThreads + 1, kScanThreads, 0, st>>>(m->d_off, m->d_partial, m->d_scalars, nk);
 	occ_scatter_kernel<<<occ_blocks, 256, 0, st>>>(m->d_occ, n_occ, m->d_off, m->d_cursor, m->d_list, m->d_uniq);
 	MCU(m, cudaGetLastError());
+	MCU(m, cudaEventRecord(m->ev[1], st));
 	unsigned long long grand = 0;
 	MCU(m, cudaMemcpyAsync(&grand, m->d_scalars, 8, cudaMemcpyDeviceToHost, st));
 	MCU(m, cudaStreamSynchronize(st));
 	ntsm_ctx_add_launches(m->ctx, 5);
+	float ms = 0;
+	if (cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]) == cudaSuccess) m->ms_lists += ms;
 	const uint32_t n_uniq = (uint32_t)(grand >> 32);
 	if (n_uniq == 0) return NTSM_OK;
 
 	FillParams P{ m->d_uniq, n_uniq, m->d_off, m->d_list, m->d_geno, gwords, J, S, multi, m->d_mat, m->stride, m->d_scalars + 1, nullptr };
-	const dim3 grid((n_uniq + 127) / 128, std::min<uint32_t>(S, 65535u));
+	const dim3 grid((n_uniq + 127) / 128, std::min<uint32_t>(gwords, 65535u));
+	MCU(m, cudaEventRecord(m->ev[2], st));
 	multi_fill_kernel<0><<<grid, 128, 0, st>>>(P);
+	MCU(m, cudaEventRecord(m->ev[3], st));
 	unsigned long long n_warn = 0;
 	MCU(m, cudaMemcpyAsync(&n_warn, m->d_scalars + 1, 8, cudaMemcpyDeviceToHost, st));
 	MCU(m, cudaStreamSynchronize(st));
@@ -225,10 +228,30 @@ static int insert_batch(ntsm_multi *m, const char *windows, uint32_t wstride, co
 		std::sort(w.begin(), w.end(), [](const MultiWarn &a, const MultiWarn &b) { return a.occ != b.occ ? a.occ < b.occ : a.sample < b.sample; });
 		for (const MultiWarn &x : w) m->warnings.emplace_back((uint8_t)x.old_value, x.wanted);
 	}
+	MCU(m, cudaEventRecord(m->ev[4], st));
 	multi_fill_kernel<2><<<grid, 128, 0, st>>>(P);
 	MCU(m, cudaGetLastError());
+	MCU(m, cudaEventRecord(m->ev[5], st));
 	MCU(m, cudaStreamSynchronize(st));                            // the host buffers of this batch are the caller's again
 	ntsm_ctx_add_launches(m->ctx, 1);
+	if (cudaEventElapsedTime(&ms, m->ev[2], m->ev[3]) == cudaSuccess) m->ms_fill += ms;
+	if (cudaEventElapsedTime(&ms, m->ev[4], m->ev[5]) == cudaSuccess) m->ms_fill += ms;
+	m->cells_touched += (uint64_t)n_uniq * S;
+	return NTSM_OK;
+}
+
+// genotypes as they travel: 2 bits per sample, 16 samples per little-endian uint32, (n_samples + 15) / 16 words per line
+int ntsm_multi_insert_windows_packed(ntsm_multi *m, const char *windows, uint32_t wstride, const uint16_t *lens, const uint32_t *geno2,
+                                     uint32_t n_lines, uint32_t multi)
+{
+	if (!m || (n_lines && (!windows || !lens || (!geno2 && m->n_samples)))) return mfail(m, NTSM_ERR_ARG, "ntsm_multi_insert_windows: null argument");
+	MCU(m, cudaSetDevice(m->v.device));
+	const uint32_t gwords = (m->n_samples + 15) / 16;
+	for (uint32_t at = 0; at < n_lines; at += kMaxLines) {
+		const uint32_t n = std::min(kMaxLines, n_lines - at);
+		const int rc = insert_batch(m, windows + (size_t)at * 2 * wstride, wstride, lens + (size_t)at * 2, geno2 + (size_t)at * gwords, n, multi);
+		if (rc) return rc;
+	}
 	return NTSM_OK;
 }
 
@@ -236,14 +259,17 @@ extern "C" int ntsm_multi_insert_windows(ntsm_multi *m, const char *windows, uin
                                          const uint8_t *genotypes, uint32_t n_lines, uint32_t multi)
 {
 	if (!m || (n_lines && (!windows || !lens || (!genotypes && m->n_samples)))) return mfail(m, NTSM_ERR_ARG, "ntsm_multi_insert_windows: null argument");
-	MCU(m, cudaSetDevice(m->v.device));
-	for (uint32_t at = 0; at < n_lines; at += kMaxLines) {
-		const uint32_t n = std::min(kMaxLines, n_lines - at);
-		const int rc = insert_batch(m, windows + (size_t)at * 2 * wstride, wstride, lens + (size_t)at * 2,
-		                            genotypes + (size_t)at * m->n_samples, n, multi);
-		if (rc) return rc;
+	const uint32_t S = m->n_samples, gwords = (S + 15) / 16;
+	m->h_geno.assign((size_t)n_lines * gwords, 0u);
+	for (uint32_t l = 0; l < n_lines; ++l) {
+		const uint8_t *g = genotypes + (size_t)l * S;
+		uint32_t *w = m->h_geno.data() + (size_t)l * gwords;
+		for (uint32_t s = 0; s < S; ++s) {
+			if (g[s] > 2) return mfail(m, NTSM_ERR_ARG, "line %u sample %u: genotype code %u (0 hom1, 1 het, 2 hom2)", l, s, g[s]);
+			w[s >> 4] |= (uint32_t)g[s] << (2 * (s & 15));
+		}
 	}
-	return NTSM_OK;
+	return ntsm_multi_insert_windows_packed(m, windows, wstride, lens, m->h_geno.data(), n_lines, multi);
 }
 
 extern "C" uint64_t ntsm_multi_n_warnings(const ntsm_multi *m) { return m ? m->warnings.size() : 0; }
@@ -304,6 +330,7 @@ extern "C" int ntsm_multi_norm_matrix(ntsm_multi *m, double *values, double *sum
 	cudaError_t e = cudaMalloc(&d_sums, (size_t)S * sizeof(double));
 	auto run = [&]() -> cudaError_t {
 		if (e != cudaSuccess) return e;
+		cudaEventRecord(m->ev[0], m->stream);
 		if (N) {
 			const dim3 grid((S + 31) / 32, (N + 31) / 32);
 			multi_norm_kernel<<<grid, dim3(32, 32), 0, m->stream>>>(m->d_mat, m->stride, m->v.d_allele_off, S, N, d_values);
@@ -311,6 +338,7 @@ extern "C" int ntsm_multi_norm_matrix(ntsm_multi *m, double *values, double *sum
 		multi_norm_sum_kernel<<<(S + 7) / 8, 256, 0, m->stream>>>(d_values, S, N, d_sums);
 		cudaError_t r = cudaGetLastError();
 		if (r != cudaSuccess) return r;
+		cudaEventRecord(m->ev[1], m->stream);
 		if (values && N && (r = cudaMemcpyAsync(values, d_values, (size_t)S * N * sizeof(double), cudaMemcpyDeviceToHost, m->stream)) != cudaSuccess) return r;
 		if (sums && (r = cudaMemcpyAsync(sums, d_sums, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, m->stream)) != cudaSuccess) return r;
 		return cudaStreamSynchronize(m->stream);
@@ -319,7 +347,18 @@ extern "C" int ntsm_multi_norm_matrix(ntsm_multi *m, double *values, double *sum
 	cudaFree(d_values);
 	if (d_sums) cudaFree(d_sums);
 	if (e != cudaSuccess) return mfail(m, NTSM_ERR_CUDA, "ntsm_multi_norm_matrix: %s", cudaGetErrorString(e));
+	float ms = 0;
+	if (cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]) == cudaSuccess) m->ms_norm += ms;
 	ntsm_ctx_add_launches(m->ctx, N ? 2 : 1);
 	ntsm_ctx_add_pcie(m->ctx, 0, (values ? (uint64_t)S * N * 8 : 0) + (sums ? (uint64_t)S * 8 : 0));
 	return NTSM_OK;
+}
+
+// device time so far, by CUDA events on the stream: ms[0] the k-merize + table lookup + occurrence lists of every batch,
+// ms[1] the fill kernel's passes, ms[2] the norm-matrix kernels; cells = (occurring k-mer, sample) pairs per fill pass
+extern "C" void ntsm_multi_kernel_ms(const ntsm_multi *m, double ms[3], uint64_t *cells)
+{
+	if (!m) return;
+	if (ms) { ms[0] = m->ms_lists; ms[1] = m->ms_fill; ms[2] = m->ms_norm; }
+	if (cells) *cells = m->cells_touched;
 }

@@ -16,7 +16,7 @@
 //                           table -> dense index of that occurrence (or none), and a per-k-mer occurrence count;
 //   2. an exclusive scan over the k-mer index space (occurrence offsets + rank among the k-mers that occur);
 //   3. occ_scatter_kernel   occurrence lists per k-mer (CSR) and the compact list of k-mers that occur;
-//   4. multi_fill_kernel    one thread per (occurring k-mer, sample) replays that cell's inserts IN THE
+//   4. multi_fill_kernel    one thread per (occurring k-mer, 16 samples) replays each cell's inserts IN THE
 //                           REFERENCE'S SERIAL ORDER (line, ref before alt, window offset) against the cell's
 //                           current byte: first non-zero writer wins, later different values are warnings.
 //                           Cells are independent, so the result is the one-thread reference's bit for bit
@@ -190,35 +190,40 @@ __global__ void multi_fill_kernel(const FillParams P)
 	if (u >= P.n_uniq) return;
 	const uint32_t idx = P.uniq[u];
 	const uint32_t beg = (uint32_t)P.off[idx], n = (uint32_t)P.off[idx + 1] - beg;
-	for (uint32_t s = blockIdx.y; s < P.n_samples; s += gridDim.y) {
-		uint8_t *cell = P.mat + P.stride * s + idx;               // :56-57
-		const uint32_t x0 = *cell;
-		uint32_t x = x0;
-		int64_t last = -1;
-		for (uint32_t t = 0; t < n; ++t) {
-			uint32_t o = 0xFFFFFFFFu;                             // next occurrence in the reference's order
-			for (uint32_t q = 0; q < n; ++q) {
-				const uint32_t c = P.list[beg + q];
-				if ((int64_t)c > last && c < o) o = c;
-			}
-			last = o;
-			const uint32_t w = o / P.J;                           // line * 2 + allele
-			const uint32_t g = (P.geno[(size_t)(w >> 1) * P.gwords + (s >> 4)] >> (2 * (s & 15))) & 3u;
-			uint32_t v;
-			if (g == 1) v = P.multi;                              // het: both alleles once (VCFConvert.hpp:153-155,164-166)
-			else if (g == ((w & 1) ? 2u : 0u)) v = P.multi * 2;   // homozygous for this window's allele (:151-152,162-163)
-			else continue;
-			if (x > 0) {                                          // :58
-				if (x != v) {                                     // :59
-					if (MODE == 0) atomicAdd(P.n_warn, 1ull);
-					if (MODE == 1) {
-						const unsigned long long at = atomicAdd(P.n_warn, 1ull);
-						P.warn[at] = MultiWarn{ o, s, x, v };
-					}
+	// a thread takes its k-mer through 16 samples at a time (one word of genotypes): the list offsets are read once
+	// per 16 cells, and a warp's 32 k-mers are 32 neighbouring bytes of each sample's row
+	for (uint32_t sg = blockIdx.y; sg < P.gwords; sg += gridDim.y) {
+		const uint32_t s_end = min(P.n_samples, sg * 16 + 16);
+		for (uint32_t s = sg * 16; s < s_end; ++s) {
+			uint8_t *cell = P.mat + P.stride * s + idx;           // :56-57
+			const uint32_t x0 = *cell;
+			uint32_t x = x0;
+			int64_t last = -1;
+			for (uint32_t t = 0; t < n; ++t) {
+				uint32_t o = 0xFFFFFFFFu;                         // next occurrence in the reference's order
+				for (uint32_t q = 0; q < n; ++q) {
+					const uint32_t c = P.list[beg + q];
+					if ((int64_t)c > last && c < o) o = c;
 				}
-			} else x = v & 0xFFu;                                 // :65-67, the byte takes the value's low 8 bits
+				last = o;
+				const uint32_t w = o / P.J;                       // line * 2 + allele
+				const uint32_t g = (P.geno[(size_t)(w >> 1) * P.gwords + sg] >> (2 * (s & 15))) & 3u;
+				uint32_t v;
+				if (g == 1) v = P.multi;                          // het: both alleles once (VCFConvert.hpp:153-155,164-166)
+				else if (g == ((w & 1) ? 2u : 0u)) v = P.multi * 2;   // homozygous for this window's allele (:151-152,162-163)
+				else continue;
+				if (x > 0) {                                      // :58
+					if (x != v) {                                 // :59
+						if (MODE == 0) atomicAdd(P.n_warn, 1ull);
+						if (MODE == 1) {
+							const unsigned long long at = atomicAdd(P.n_warn, 1ull);
+							P.warn[at] = MultiWarn{ o, s, x, v };
+						}
+					}
+				} else x = v & 0xFFu;                             // :65-67, the byte takes the value's low 8 bits
+			}
+			if (MODE == 2 && x != x0) *cell = (uint8_t)x;
 		}
-		if (MODE == 2 && x != x0) *cell = (uint8_t)x;
 	}
 }
 

@@ -21,9 +21,11 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <chrono>
 #include <fstream>
 #include <iostream>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -40,6 +42,7 @@ struct ntsm_vcf {
 	ntsm_multi *multi = nullptr;
 	std::vector<std::string> sample_ids;        // m_sampleIDs (:192)
 	uint64_t lines_counted = 0;                 // SNP lines whose windows were inserted
+	uint32_t threads = 1;                       // opt::threads: parser threads of count(), formatter threads of outputMatrix()
 };
 
 namespace {
@@ -88,16 +91,22 @@ struct Text {
 
 struct Field { const char *p; size_t n; };
 
-// tab-separated fields of one line; getline(ss, item, '\t') semantics: a trailing tab yields a last empty field
-void split(const char *p, size_t n, std::vector<Field> &f)
+// tab-separated fields of one line; getline(ss, item, '\t') semantics: a trailing tab yields a last empty field.
+// At most max_fields are split off; *rest (nullable) = where the next field starts, or nullptr if the line ended.
+void split(const char *p, size_t n, std::vector<Field> &f, size_t max_fields = (size_t)-1, const char **rest = nullptr)
 {
 	f.clear();
 	const char *end = p + n, *at = p;
+	if (rest) *rest = nullptr;
 	for (;;) {
 		const char *t = (const char *)memchr(at, '\t', (size_t)(end - at));
 		if (!t) { f.push_back({ at, (size_t)(end - at) }); break; }
 		f.push_back({ at, (size_t)(t - at) });
 		at = t + 1;
+		if (f.size() == max_fields) {
+			if (rest) *rest = at;
+			break;
+		}
 	}
 }
 
@@ -109,6 +118,117 @@ inline uint8_t genotype_code(const char *g, size_t n)
 	if (g[0] == '0') return g[2] == '1' ? 1 : 0;           // "0|0" hom1, "0|1" het ("0|x" otherwise: hom1)
 	if (g[0] == '1') return g[2] == '0' ? 1 : g[2] == '1' ? 2 : 0;
 	return 0;
+}
+
+// n items over `threads` workers (an atomic counter hands them out); threads <= 1 runs inline
+template <class F> void parallel_for(size_t n, uint32_t threads, F fn)
+{
+	if (threads <= 1 || n <= 1) {
+		for (size_t i = 0; i < n; ++i) fn(i);
+		return;
+	}
+	std::atomic<size_t> next{ 0 };
+	std::vector<std::thread> pool;
+	const size_t nt = std::min<size_t>(threads, n);
+	for (size_t t = 0; t < nt; ++t)
+		pool.emplace_back([&] {
+			for (size_t i; (i = next.fetch_add(1)) < n;) fn(i);
+		});
+	for (std::thread &t : pool) t.join();
+}
+
+struct ParseEnv {
+	const std::vector<Chrom> *chroms;
+	const std::unordered_map<std::string, uint32_t> *chr_ids;
+	uint32_t S, window, wstride;
+	int verbose;
+};
+
+// what one worker makes of a run of data lines: the windows and packed genotypes of the lines that are SNPs
+struct LineBatch {
+	std::vector<char> windows;
+	std::vector<uint16_t> lens;
+	std::vector<uint32_t> geno2;                // 2 bits per sample, (S + 15) / 16 words per line
+	uint32_t n = 0;
+	int err = 0;                                // first line that ends the run, as upstream: NTSM_ERR_NOKEY (dies) / NTSM_ERR_ARG (undefined)
+	std::string msg;
+};
+
+std::mutex g_verbose_mu;
+
+// VCFConvert::count's per-line work up to the inserts (:103-146) for the whole lines of [at, end)
+void parse_lines(const ParseEnv &E, const char *at, const char *end, LineBatch &B)
+{
+	const uint32_t S = E.S, window = E.window, wstride = E.wstride, half = window / 2, gwords = (S + 15) / 16;
+	size_t n_lines = 0;
+	for (const char *p = at; p < end; ++n_lines) p = (const char *)memchr(p, '\n', (size_t)(end - p)) + 1;
+	B.windows.assign(n_lines * 2 * wstride, 0);
+	B.lens.assign(n_lines * 2, 0);
+	B.geno2.assign(n_lines * gwords + 1, 0u);
+	B.n = 0;
+	B.err = 0;
+	B.msg.clear();
+	std::vector<Field> f;
+	auto die = [&](int code, const std::string &msg) {
+		B.err = code;
+		B.msg = msg;
+	};
+	while (at < end) {
+		const char *nl = (const char *)memchr(at, '\n', (size_t)(end - at));
+		const char *cols;                                          // the sample columns, if the line has any
+		split(at, (size_t)(nl - at), f, 9, &cols);
+		at = nl + 1;
+		// getline on an exhausted stringstream leaves `item` as it was: a missing field reads as the last present one
+		auto field = [&](size_t i) -> const Field & { return f[i < f.size() ? i : f.size() - 1]; };
+		const std::string chr(field(0).p, field(0).n);
+		const std::string pos_text(field(1).p, field(1).n);
+		char *pe;
+		errno = 0;
+		const long loc_l = strtol(pos_text.c_str(), &pe, 10);       // stoi (:113)
+		if (pe == pos_text.c_str() || errno == ERANGE || loc_l > INT_MAX || loc_l < INT_MIN)
+			return die(NTSM_ERR_NOKEY, "POS '" + pos_text + "' is not an int: the reference dies in stoi (src/VCFConvert.hpp:113)");
+		if (E.verbose > 2) {
+			std::lock_guard<std::mutex> lk(g_verbose_mu);          // `omp critical` (:117-118)
+			std::cerr << "Processing site: " << std::string(field(2).p, field(2).n) << std::endl;
+		}
+		if (field(3).n == 1 && field(3).p[0] == '.') continue;     // :121-123
+		if (field(4).n != 1) continue;                             // :125-127: ALT must be one character (REF's length is not looked at)
+		const char alt = field(4).p[0];
+		// getSeqFromSite (:202-215)
+		const auto it = E.chr_ids->find(chr);
+		if (it == E.chr_ids->end())
+			return die(NTSM_ERR_NOKEY, "chromosome '" + chr + "' is not in the reference: the reference dies in robin_map::at (src/VCFConvert.hpp:204)");
+		const std::string &seq = (*E.chroms)[it->second].seq;
+		if (loc_l < (long)half + 1 || (size_t)(loc_l - half - 1) > seq.size())
+			return die(NTSM_ERR_ARG, "site " + chr + ":" + pos_text + " lies outside what getSeqFromSite can cut (src/VCFConvert.hpp:207-209 reads outside the sequence there)");
+		const size_t offset = (size_t)loc_l - half - 1;
+		size_t avail = std::min<size_t>(seq.size() - offset, window);            // strncpy stops at the sequence's NUL (or one inside it) and pads with NULs
+		avail = strnlen(seq.data() + offset, avail);
+		char *wr = B.windows.data() + (size_t)B.n * 2 * wstride, *wv = wr + wstride;
+		memset(wr, 0, 2 * (size_t)wstride);                        // a line given up below leaves its slot to the next one
+		memcpy(wr, seq.data() + offset, avail);
+		memcpy(wv, seq.data() + offset, avail);
+		if (half < wstride) wv[half] = alt;                        // :211
+		// std::string(refStr): up to the first NUL -- which may also be a NUL byte inside the genome or the ALT column
+		B.lens[2 * (size_t)B.n] = (uint16_t)strnlen(wr, window);
+		B.lens[2 * (size_t)B.n + 1] = (uint16_t)strnlen(wv, window);
+		// sample columns (:129-146): "0|0" hom1, "0|1" / "1|0" het, "1|1" hom2, anything else stays hom1
+		uint32_t *g = B.geno2.data() + (size_t)B.n * gwords;
+		for (uint32_t w = 0; w < gwords; ++w) g[w] = 0;
+		size_t n_cols = 0;
+		for (const char *q = cols; q;) {
+			// almost every column is three characters and a tab
+			const char *t = q + 3 < nl && q[3] == '\t' && q[0] != '\t' && q[1] != '\t' && q[2] != '\t' ? q + 3 : (const char *)memchr(q, '\t', (size_t)(nl - q));
+			const char *fe = t ? t : nl;
+			if (n_cols < S) g[n_cols >> 4] |= (uint32_t)genotype_code(q, (size_t)(fe - q)) << (2 * (n_cols & 15));
+			++n_cols;
+			q = t ? t + 1 : nullptr;
+		}
+		if (n_cols != S)
+			return die(NTSM_ERR_NOKEY, "line for " + chr + ":" + pos_text + " has " + std::to_string(n_cols) + " sample columns, the header names " +
+			                               std::to_string(S) + ": the reference dies on its assert (src/VCFConvert.hpp:146)");
+		++B.n;
+	}
 }
 
 }  // namespace
@@ -127,7 +247,7 @@ extern "C" uint64_t ntsm_vcf_lines_counted(const ntsm_vcf *v) { return v ? v->li
 
 // VCFConvert::VCFConvert (:42-59) + VCFConvert::count (:62-174)
 extern "C" int ntsm_vcf_convert(ntsm_vcf **out, ntsm_ctx *ctx, const ntsm_sites *sites, const char *ref_path, const char *vcf_path,
-                                uint32_t multi, uint32_t window, int verbose)
+                                uint32_t multi, uint32_t window, uint32_t threads, int verbose)
 {
 	if (!out || !ctx || !sites || !ref_path || !vcf_path) return vfail(ctx, NTSM_ERR_ARG, "ntsm_vcf_convert: null argument");
 	*out = nullptr;
@@ -183,77 +303,52 @@ extern "C" int ntsm_vcf_convert(ntsm_vcf **out, ntsm_ctx *ctx, const ntsm_sites 
 		return rc;
 	}
 
-	const uint32_t half = window / 2;
+	// The data lines.  Parsing is per line and independent, so `threads` workers (opt::threads: the reference runs this
+	// loop under `omp parallel`, :99) parse batches of lines side by side; the batches then go to the GPU in file
+	// order, which -- unlike upstream with more than one thread -- keeps "the first writer of a cell wins" the
+	// one-thread result whatever `threads` is.
 	const uint32_t wstride = (window + 15u) & ~15u;
-	const uint32_t batch_lines = 4096;
-	std::vector<char> windows((size_t)batch_lines * 2 * wstride);
-	std::vector<uint16_t> lens((size_t)batch_lines * 2);
-	std::vector<uint8_t> geno((size_t)batch_lines * (S ? S : 1));
-	uint32_t n = 0;
-	auto flush = [&]() -> int {
-		if (n == 0) return NTSM_OK;
-		const int r = ntsm_multi_insert_windows(v->multi, windows.data(), wstride, lens.data(), geno.data(), n, multi);
-		v->lines_counted += n;
-		n = 0;
-		return r;
-	};
-	auto die = [&](int code, const std::string &msg) {
-		ntsm_vcf_destroy(v);
-		return vfail(ctx, code, msg);
-	};
-
-	while (at < end) {
-		const char *nl = (const char *)memchr(at, '\n', (size_t)(end - at));
-		if (!nl) break;                                            // :101-108: the getline that hits end of file leaves the stream not good(): that line is dropped
-		split(at, (size_t)(nl - at), f);
-		at = nl + 1;
-		// getline on an exhausted stringstream leaves `item` as it was: a missing field reads as the last present one
-		auto field = [&](size_t i) -> const Field & { return f[i < f.size() ? i : f.size() - 1]; };
-		const std::string chr(field(0).p, field(0).n);
-		const std::string pos_text(field(1).p, field(1).n);
-		char *pe;
-		errno = 0;
-		const long loc_l = strtol(pos_text.c_str(), &pe, 10);       // stoi (:113)
-		if (pe == pos_text.c_str() || errno == ERANGE || loc_l > INT_MAX || loc_l < INT_MIN)
-			return die(NTSM_ERR_NOKEY, "POS '" + pos_text + "' is not an int: the reference dies in stoi (src/VCFConvert.hpp:113)");
-		if (verbose > 2) std::cerr << "Processing site: " << std::string(field(2).p, field(2).n) << std::endl;
-		if (field(3).n == 1 && field(3).p[0] == '.') continue;     // :121-123
-		if (field(4).n != 1) continue;                             // :125-127: ALT must be one character (REF's length is not looked at)
-		const char alt = field(4).p[0];
-		// getSeqFromSite (:202-215)
-		const auto it = chr_ids.find(chr);
-		if (it == chr_ids.end())
-			return die(NTSM_ERR_NOKEY, "chromosome '" + chr + "' is not in the reference: the reference dies in robin_map::at (src/VCFConvert.hpp:204)");
-		const std::string &seq = chroms[it->second].seq;
-		if (loc_l < (long)half + 1 || (size_t)(loc_l - half - 1) > seq.size())
-			return die(NTSM_ERR_ARG, "site " + chr + ":" + pos_text + " lies outside what getSeqFromSite can cut (src/VCFConvert.hpp:207-209 reads outside the sequence there)");
-		const size_t offset = (size_t)loc_l - half - 1;
-		size_t avail = std::min<size_t>(seq.size() - offset, window);            // strncpy stops at the sequence's NUL (or one inside it) and pads with NULs
-		avail = strnlen(seq.data() + offset, avail);
-		char *wr = windows.data() + (size_t)n * 2 * wstride, *wv = wr + wstride;
-		memset(wr, 0, 2 * (size_t)wstride);
-		memcpy(wr, seq.data() + offset, avail);
-		memcpy(wv, seq.data() + offset, avail);
-		if (half < wstride) wv[half] = alt;                        // :211
-		// std::string(refStr): up to the first NUL -- which may also be a NUL byte inside the genome or the ALT column
-		lens[2 * (size_t)n] = (uint16_t)strnlen(wr, window);
-		lens[2 * (size_t)n + 1] = (uint16_t)strnlen(wv, window);
-		// sample columns (:129-146)
-		const size_t n_cols = f.size() > 9 ? f.size() - 9 : 0;
-		if (n_cols != S)
-			return die(NTSM_ERR_NOKEY, "line for " + chr + ":" + pos_text + " has " + std::to_string(n_cols) + " sample columns, the header names " +
-			                               std::to_string(S) + ": the reference dies on its assert (src/VCFConvert.hpp:146)");
-		uint8_t *g = geno.data() + (size_t)n * S;
-		for (uint32_t s = 0; s < S; ++s) g[s] = genotype_code(f[9 + s].p, f[9 + s].n);
-		if (++n == batch_lines && (rc = flush())) {
-			ntsm_vcf_destroy(v);
-			return rc;
+	const uint32_t batch_lines = 2048;
+	std::vector<std::pair<const char *, const char *>> spans;       // [begin, end) of each batch: whole lines, '\n' included
+	{
+		const char *b = at;
+		uint32_t in_batch = 0;
+		while (at < end) {
+			const char *nl = (const char *)memchr(at, '\n', (size_t)(end - at));
+			if (!nl) break;                                        // :101-108: the getline that hits end of file leaves the stream not good(): that line is dropped
+			at = nl + 1;
+			if (++in_batch == batch_lines) {
+				spans.emplace_back(b, at);
+				b = at;
+				in_batch = 0;
+			}
+		}
+		if (in_batch) spans.emplace_back(b, at);
+	}
+	const ParseEnv env{ &chroms, &chr_ids, S, window, wstride, verbose };
+	const uint32_t T = std::max(1u, threads);
+	const size_t round = std::max<size_t>(4 * (size_t)T, 16);
+	std::vector<LineBatch> batches(std::min(round, spans.size()));
+	for (size_t r0 = 0; r0 < spans.size(); r0 += round) {
+		const size_t nb = std::min(round, spans.size() - r0);
+		parallel_for(nb, T, [&](size_t i) { parse_lines(env, spans[r0 + i].first, spans[r0 + i].second, batches[i]); });
+		for (size_t i = 0; i < nb; ++i) {
+			LineBatch &b = batches[i];
+			if (b.n) {
+				rc = ntsm_multi_insert_windows_packed(v->multi, b.windows.data(), wstride, b.lens.data(), b.geno2.data(), b.n, multi);
+				if (rc) {
+					ntsm_vcf_destroy(v);
+					return rc;
+				}
+				v->lines_counted += b.n;
+			}
+			if (b.err) {                                           // the lines before it in the file have been inserted, as upstream before it dies
+				ntsm_vcf_destroy(v);
+				return vfail(ctx, b.err, b.msg);
+			}
 		}
 	}
-	if ((rc = flush())) {
-		ntsm_vcf_destroy(v);
-		return rc;
-	}
+	v->threads = T;
 	*out = v;
 	return NTSM_OK;
 }
@@ -281,9 +376,12 @@ struct DoubleText {
 
 }  // namespace
 
-// MultiCount::printNormMatrix (src/MultiCount.hpp:148-203) into two files
+// MultiCount::printNormMatrix (src/MultiCount.hpp:148-203) into two files.  The numbers come from the device
+// (ntsm_multi_norm_matrix); the text is made by `threads` workers, a block of rows each, and written in row order.
+// The one piece of state the reference's stream carries from row to row -- setprecision(19) from the first missing
+// value on (:192) -- is known up front: it is the position of the first UNDEF in the matrix.
 extern "C" int ntsm_multi_write_norm_matrix(ntsm_multi *m, const ntsm_sites *sites, const char *const *sample_ids, const char *matrix_path,
-                                            const char *center_path)
+                                            const char *center_path, uint32_t threads)
 {
 	if (!m || !sites || !matrix_path || !center_path) return NTSM_ERR_ARG;
 	const uint32_t S = ntsm_sites_n_sites(sites), N = ntsm_multi_n_samples(m);
@@ -310,28 +408,48 @@ extern "C" int ntsm_multi_write_norm_matrix(ntsm_multi *m, const ntsm_sites *sit
 		sums.resize(S);
 		rc = ntsm_multi_norm_matrix(m, values.data(), sums.data());
 	}
-	if (rc == NTSM_OK) {
-		int precision = 6;                                         // the stream's; setprecision(19) at the first missing value sticks (:192)
-		DoubleText cache;
-		char num[64];
-		std::string c;
-		for (uint32_t i = 0; i < S; ++i) {
-			o.assign(ntsm_sites_name(sites, i));                   // :187
-			const long double center = (long double)sums[i] / (long double)(uint64_t)N;   // :188-189: size counts every sample
-			const int cl = snprintf(num, sizeof num, "%.19Lg", center);
-			const double *row = values.data() + (size_t)i * N;
-			for (uint32_t j = 0; j < N; ++j) {
-				o.push_back('\t');
-				if (row[j] == 1.7976931348623157e308) {            // UNDEF (:41,190)
-					precision = 19;
-					o.append(num, (size_t)cl);
-				} else cache.put(o, row[j], precision);            // :194
+	if (rc == NTSM_OK && S) {
+		const uint32_t T = std::max(1u, threads), rows_per_block = 64;
+		const size_t n_blocks = ((size_t)S + rows_per_block - 1) / rows_per_block;
+		// where the stream's precision switches: the first missing value in row-major order
+		std::vector<uint64_t> first(n_blocks, UINT64_MAX);
+		parallel_for(n_blocks, T, [&](size_t b) {
+			const size_t lo = b * rows_per_block * (size_t)N, hi = std::min<size_t>((size_t)S, (b + 1) * rows_per_block) * (size_t)N;
+			for (size_t x = lo; x < hi; ++x)
+				if (values[x] == 1.7976931348623157e308) { first[b] = x; break; }
+		});
+		uint64_t sw = UINT64_MAX;
+		for (uint64_t x : first) sw = std::min(sw, x);
+		const size_t round = std::max<size_t>(4 * (size_t)T, 16);
+		std::vector<std::string> mtext(round), ctext(round);
+		for (size_t b0 = 0; b0 < n_blocks; b0 += round) {
+			const size_t nb = std::min(round, n_blocks - b0);
+			parallel_for(nb, T, [&](size_t bi) {
+				std::string &mo = mtext[bi], &co = ctext[bi];
+				mo.clear();
+				co.clear();
+				DoubleText cache;
+				char num[64];
+				const uint32_t i0 = (uint32_t)((b0 + bi) * rows_per_block), i1 = std::min<uint32_t>(S, i0 + rows_per_block);
+				for (uint32_t i = i0; i < i1; ++i) {
+					mo += ntsm_sites_name(sites, i);               // :187
+					const long double center = (long double)sums[i] / (long double)(uint64_t)N;   // :188-189: size counts every sample
+					const int cl = snprintf(num, sizeof num, "%.19Lg", center);
+					const double *row = values.data() + (size_t)i * N;
+					for (uint32_t j = 0; j < N; ++j) {
+						mo.push_back('\t');
+						if (row[j] == 1.7976931348623157e308) mo.append(num, (size_t)cl);        // UNDEF (:41,190): the centre, 19 digits
+						else cache.put(mo, row[j], (uint64_t)i * N + j > sw ? 19 : 6);          // :194 at the stream's precision
+					}
+					mo.push_back('\n');
+					co.append(num, (size_t)cl);                    // :198
+					co.push_back('\n');
+				}
+			});
+			for (size_t bi = 0; bi < nb; ++bi) {
+				fwrite(mtext[bi].data(), 1, mtext[bi].size(), out);
+				fwrite(ctext[bi].data(), 1, ctext[bi].size(), cf);
 			}
-			o.push_back('\n');
-			fwrite(o.data(), 1, o.size(), out);
-			c.assign(num, (size_t)cl);                             // :198
-			c.push_back('\n');
-			fwrite(c.data(), 1, c.size(), cf);
 		}
 	}
 	fclose(out);
@@ -366,7 +484,7 @@ extern "C" int ntsm_vcf_output_matrix(ntsm_vcf *v, const char *prefix)
 	for (const std::string &s : v->sample_ids) ids.push_back(s.c_str());
 	ids.push_back(nullptr);
 	const std::string p(prefix);
-	return ntsm_multi_write_norm_matrix(v->multi, v->sites, ids.data(), (p + "_matrix.tsv").c_str(), (p + "_center.txt").c_str());
+	return ntsm_multi_write_norm_matrix(v->multi, v->sites, ids.data(), (p + "_matrix.tsv").c_str(), (p + "_center.txt").c_str(), v->threads);
 }
 
 // VCFConvert::outputCounts (:173-184): <dir>/<sampleID>.counts.txt for every sample (the reference writes into the
@@ -540,7 +658,7 @@ extern "C" int ntsm_vcf_main(int argc, char **argv)
 		return 1;
 	}
 	ntsm_vcf *v = nullptr;
-	rc = ntsm_vcf_convert(&v, ctx, sites, ref.c_str(), inputs[0].c_str(), multi, window, verbose);
+	rc = ntsm_vcf_convert(&v, ctx, sites, ref.c_str(), inputs[0].c_str(), multi, window, threads, verbose);
 	const auto fail_exit = [&](int code) {
 		if (code == NTSM_ERR_NOKEY) {
 			std::cerr << "terminate called after throwing an instance of 'std::out_of_range'\n  what():  " << ntsm_last_error(ctx) << std::endl;

@@ -111,15 +111,15 @@ class MultiCount:
         check(_lib.lib().ntsm_multi_norm_matrix(self._h, v.ctypes.data if v.size else None, s.ctypes.data if S else None), self._fp._ctx)
         return v, s
 
-    def printNormMatrix(self, matrix_path, center_path):
+    def printNormMatrix(self, matrix_path, center_path, threads=1):
         ids = (C.c_char_p * (len(self.sample_ids) + 1))(*[s.encode() if isinstance(s, str) else s for s in self.sample_ids], None)
-        _raise(_lib.lib().ntsm_multi_write_norm_matrix(self._h, self.sites._h, ids, os.fsencode(matrix_path), os.fsencode(center_path)), self._fp._ctx)
+        _raise(_lib.lib().ntsm_multi_write_norm_matrix(self._h, self.sites._h, ids, os.fsencode(matrix_path), os.fsencode(center_path), threads), self._fp._ctx)
 
 
 class VCFConvert:
-    def __init__(self, sites, ref, k=19, dupes=False, multi=20, window=31, device=0, verbose=0):
+    def __init__(self, sites, ref, k=19, dupes=False, multi=20, window=31, threads=1, device=0, verbose=0):
         self._fp = FingerPrint(sites if isinstance(sites, SiteSet) else SiteSet(sites, k, dupes), k=k, device=device, batch_bases=4096, n_buffers=2)
-        self.ref, self.multi, self.window, self.verbose = ref, multi, window, verbose
+        self.ref, self.multi, self.window, self.threads, self.verbose = ref, multi, window, threads, verbose
         self._h = None
         self.counts = None          # m_counts, after count()
 
@@ -135,7 +135,7 @@ class VCFConvert:
         self.close()
         h = C.c_void_p()
         rc = L.ntsm_vcf_convert(C.byref(h), self._fp._ctx, self._fp.sites._h, os.fsencode(self.ref), os.fsencode(filename), self.multi,
-                                self.window, self.verbose)
+                                self.window, self.threads, self.verbose)
         if rc == -5:
             raise FileNotFoundError((L.ntsm_last_error(self._fp._ctx) or b"").decode())
         _raise(rc, self._fp._ctx)

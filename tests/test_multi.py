@@ -153,7 +153,7 @@ def test_abi_matches_reference_classes_fixture(name, tmp_path):
     import ntsm_b200
     d, a, want_rc = _case(name)
     vc = ntsm_b200.VCFConvert(os.path.join(d, "sites.fa"), os.path.join(d, a["ref"]), k=a["k"], dupes=bool(a["dupes"]), multi=a["multi"],
-                              window=a["window"])
+                              window=a["window"], threads=1 + len(name) % 3)
     if want_rc:
         with pytest.raises(KeyError):                       # the reference dies (uncaught exception / assert): rc 134
             vc.count(os.path.join(d, "in.vcf"))
@@ -179,7 +179,7 @@ def test_abi_matches_reference_classes_fixture(name, tmp_path):
 def test_ntsmvcf_binary_matches_reference_classes_fixture(name, tmp_path):
     d, a, want_rc = _case(name)
     argv = [NTSMVCF, "-s", os.path.join(d, "sites.fa"), "-r", os.path.join(d, a["ref"]), "-k", str(a["k"]), "-m", str(a["multi"]),
-            "-w", str(a["window"]), "-p", "out", "--counts"] + (["-d"] if a["dupes"] else []) + [os.path.join(d, "in.vcf")]
+            "-w", str(a["window"]), "-p", "out", "--counts", "-t", str(1 + len(name) % 5)] + (["-d"] if a["dupes"] else []) + [os.path.join(d, "in.vcf")]
     p = subprocess.run(argv, cwd=str(tmp_path), capture_output=True)
     if want_rc:
         assert p.returncode == 134 and b"terminate called" in p.stderr
@@ -206,7 +206,7 @@ def test_abi_matches_oracle_on_fuzzed_vcfs(oracle, seed, n_sites, n_samples, ove
     _fuzz_inputs(rng, d, n_sites, n_samples, repeats=seed % 2, overlap=overlap)
     dupes = 1 if overlap else 0
     assert oracle.vcf_run(d + "/sites.fa", d + "/ref.fa", d + "/in.vcf", d + "/orc", dupes=dupes, multi=multi) == 0
-    vc = ntsm_b200.VCFConvert(d + "/sites.fa", d + "/ref.fa", dupes=bool(dupes), multi=multi)
+    vc = ntsm_b200.VCFConvert(d + "/sites.fa", d + "/ref.fa", dupes=bool(dupes), multi=multi, threads=seed)
     vc.count(d + "/in.vcf")
     vc.outputMatrix(d + "/gpu")
     assert filecmp.cmp(d + "/orc_matrix.tsv", d + "/gpu_matrix.tsv", shallow=False)
@@ -227,12 +227,14 @@ def test_abi_matches_oracle_on_fuzzed_vcfs(oracle, seed, n_sites, n_samples, ove
 
 
 def _panel_windows():
-    recs = [l.rstrip("\n") for l in open(SITES300)]
-    wins = []
-    for i in range(0, len(recs), 4):
-        refk, vark = recs[i + 1].split("N"), recs[i + 3].split("N")
-        wins.append(((refk[0] + "".join(x[-1] for x in refk[1:])).encode(), (vark[0] + "".join(x[-1] for x in vark[1:])).encode()))
-    return wins
+    """[(ref window, alt window)] of the 300-site slice of the real panel (3-13 of a window's 13 k-mers are listed)."""
+    import panel_util
+    rng = random.Random(300)
+    out = []
+    for name, w, alt in panel_util.panel_windows(open(SITES300).read().splitlines(), rng):
+        assert w is not None
+        out.append((w.encode(), (w[:15] + alt + w[16:]).encode()))
+    return out
 
 
 @pytest.mark.gpu
@@ -289,8 +291,6 @@ def test_norm_matrix_many_samples_vs_oracle(oracle, tmp_path):
     pieces, at, lines = [], 0, []
     samples = ["HG%05d" % i for i in range(2504)]
     for i, (w, v) in enumerate(wins):
-        if len(w) != 31:
-            continue
         pad = "".join(rng.choice("ACGT") for _ in range(rng.randrange(20, 50)))
         pieces.append(pad + w.decode())
         at += len(pad)
@@ -304,7 +304,7 @@ def test_norm_matrix_many_samples_vs_oracle(oracle, tmp_path):
         fh.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(samples) + "\n")
         fh.writelines(lines)
     assert oracle.vcf_run(SITES300, d + "/ref.fa", d + "/in.vcf", d + "/orc") == 0
-    vc = ntsm_b200.VCFConvert(SITES300, d + "/ref.fa")
+    vc = ntsm_b200.VCFConvert(SITES300, d + "/ref.fa", threads=8)
     vc.count(d + "/in.vcf")
     assert vc.lines_counted == len(lines) and len(vc.sample_ids) == 2504
     vc.outputMatrix(d + "/gpu")

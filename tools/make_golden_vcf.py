@@ -238,27 +238,23 @@ def main():
     write_case("abort_unpaired_site", odd, fasta("chr1", g), vcf_header(["S1"]) + vcf_line("chr1", pos[0], "rs1", "A", "C", ["0|1"]))
 
     # 13. a slice of the real panel (tests/golden/shared/sites300.fa): genome with the 300 windows planted, 24 samples
-    recs = [l.rstrip("\n") for l in open(SITES300)]
-    wins = []
-    for i in range(0, len(recs), 4):
-        name = recs[i][1:].split()[0]
-        refk, vark = recs[i + 1].split("N"), recs[i + 3].split("N")
-        w = refk[0] + "".join(x[-1] for x in refk[1:])
-        v = vark[0] + "".join(x[-1] for x in vark[1:])
-        wins.append((name, w, v))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import panel_util
+    wins = panel_util.panel_windows(open(SITES300).read().splitlines(), rng)      # the panel lists 3-13 of a window's 13 k-mers
     pieces, positions, at = [], [], 0
-    for name, w, v in wins:
+    for name, w, alt in wins:
+        if w is None:
+            continue
         pad = rand_seq(rng, rng.randrange(5, 60))
         pieces.append(pad + w)
         at += len(pad)
-        half = len(w) // 2
-        positions.append((name, at + half + 1, w[half], v[half], len(w)))
+        positions.append((name, at + 16, w[15], alt))
         at += len(w)
     g = "".join(pieces) + rand_seq(rng, 100)
     samples = ["NA%05d" % (18500 + i) for i in range(24)]
     vcf = vcf_header(samples)
-    for name, p, r, a, wl in positions:
-        if wl != 31 or rng.random() < 0.03:
+    for name, p, r, a in positions:
+        if rng.random() < 0.03:
             continue
         vcf += vcf_line("chr1", p, name, r, a, [rng.choice(GT) if rng.random() > 0.02 else "./." for _ in samples])
     write_case("panel300_24samples", open(SITES300).read(), fasta("chr1", g, 80), vcf)

@@ -14,7 +14,7 @@
 // VCFConvert::count, MultiCount::insertCount, printCountsMax, printNormMatrix -- is the
 // reference's own code running on its own data structures.
 //
-//   usage: ref_vcf_harness <sites.fa> <ref.fa> <in.vcf> <out_prefix> [k] [multi] [window] [dupes 0|1]
+//   usage: ref_vcf_harness <sites.fa> <ref.fa> <in.vcf> <out_prefix> [k] [multi] [window] [dupes 0|1] [threads] [matrix_only 0|1]
 //   writes <out_prefix>_matrix.tsv, <out_prefix>_center.txt (VCFConvert::outputMatrix),
 //          <out_prefix>_counts_<j>.txt for every sample j (MultiCount::printCountsMax(j)),
 //          <out_prefix>_mat.bin (raw m_matCounts) ; stderr = the reference's warnings
@@ -73,8 +73,9 @@ int main(int argc, char **argv)
 	if (argc > 6) opt::multi = atoi(argv[6]);
 	if (argc > 7) opt::window = atoi(argv[7]);
 	if (argc > 8) opt::dupes = atoi(argv[8]) != 0;
-	opt::threads = 1;
-	omp_set_num_threads(1);      // the reference's only deterministic mode (first writer of a cell wins, MultiCount.hpp:52-69)
+	opt::threads = argc > 9 ? atoi(argv[9]) : 1;   // 1 = the reference's only deterministic mode (first writer of a cell wins, MultiCount.hpp:52-69)
+	omp_set_num_threads(opt::threads);             // ntSeqMatchVCF.cpp:158-161; more threads only for timing (tools/bench_matrix.py)
+	const bool matrix_only = argc > 10 && atoi(argv[10]) != 0;
 
 	VCFConvert convert;          // ntSeqMatchVCF.cpp:198
 	size_t listed = 0;           // kmerCount of MultiCount.hpp:217: every k-mer that entered a site list
@@ -82,7 +83,14 @@ int main(int argc, char **argv)
 	for (size_t i = 0; i < convert.m_counts.m_alleleIDToKmerVar.size(); ++i) listed += convert.m_counts.m_alleleIDToKmerVar[i]->size();
 	convert.m_counts.m_matCounts = std::vector<uint8_t>(listed * samples_on_header(vcf.c_str()), 0);   // MultiCount.hpp:266 with the IDs known
 
+	double t0 = omp_get_wtime();
 	convert.count(vcf);          // ntSeqMatchVCF.cpp:200
+	double t1 = omp_get_wtime();
+	if (matrix_only) {           // what ntsmVCF -p does and nothing else, timed (ntSeqMatchVCF.cpp:200-211)
+		convert.outputMatrix(prefix);
+		fprintf(stderr, "harness_seconds count %.3f outputMatrix %.3f\n", t1 - t0, omp_get_wtime() - t1);
+		return 0;
+	}
 	{
 		std::ofstream mat((prefix + "_mat.bin").c_str(), std::ios::binary);
 		mat.write((const char *)convert.m_counts.m_matCounts.data(), convert.m_counts.m_matCounts.size());
