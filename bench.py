@@ -570,6 +570,18 @@ def ours(args):
         cpu = {"value": cb / secs / 1e9, "unit": "Gbases/s", "cores": cores, "kind": kind,
                "sample": "%d x %dbp reads (%.2f Gbases) of the same generator in %d plain FASTQ files, ntsmCount -t %d; %.1f s" % (
                    n_s, READ_LEN, cb / 1e9, cores, cores, secs)}
+    # the multi-sample matrix path (`ntsmVCF -p`): its own workload and clock, measured by
+    # tools/bench_matrix.py in a process of its own on this rank's GPU, next to the reference's classes on the host cores
+    matrix_path = None
+    if rank == 0 and not args.no_cpu:
+        try:
+            visible = [x for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x]
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES=visible[local] if local < len(visible) else str(local))
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_matrix.py"), "--threads", str(cores)],
+                               capture_output=True, text=True, timeout=600, env=env)
+            matrix_path = json.loads(p.stdout.strip().splitlines()[-1]) if p.returncode == 0 else {"error": p.stderr[-400:]}
+        except Exception as e:      # the bench line must not depend on it
+            matrix_path = {"error": repr(e)}
     if world > 1:
         dist.barrier()
 
@@ -620,6 +632,7 @@ def ours(args):
             "check": dict(check, e2e_TK=int(f_rows[4][0]), e2e_ascii_TK=int(a_rows[4][0]), e2e_packed_TK=e2e_check,
                           ascii_equals_packed=ascii_check, n_gpu_equals_1_gpu=n_equals_1),
             "parity_vs_reference_on_cpu_sample": parity,
+            "matrix_path": matrix_path,
         }
         emit(out)
     if world > 1:

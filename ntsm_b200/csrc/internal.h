@@ -38,3 +38,7 @@ void ntsm_ctx_set_error(ntsm_ctx *c, const char *text);
 // ntsm_multi_insert_windows with the genotypes already packed 2 bits per sample (16 per uint32, (n_samples + 15) / 16 words per line)
 int ntsm_multi_insert_windows_packed(ntsm_multi *m, const char *windows, uint32_t wstride, const uint16_t *lens, const uint32_t *geno2,
                                      uint32_t n_lines, uint32_t multi);
+// printNormMatrix's numbers in blocks of rows (multi.cu): kernels once, rows fetched as the caller formats
+int ntsm_multi_norm_begin(ntsm_multi *m, uint64_t *first_undef);
+int ntsm_multi_norm_fetch(ntsm_multi *m, uint32_t row0, uint32_t n_rows, double *values, double *sums);
+void ntsm_multi_norm_end(ntsm_multi *m);

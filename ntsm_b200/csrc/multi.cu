@@ -33,6 +33,7 @@ struct ntsm_multi {
 	uint32_t *d_cursor = nullptr;
 	uint32_t *d_rows = nullptr;             // 4 * n_sites (printCountsMax)
 	uint32_t *d_one = nullptr;              // result of a single insertCount
+	double *d_values = nullptr, *d_sums = nullptr;   // printNormMatrix's numbers between ntsm_multi_norm_begin and _end
 	std::vector<uint32_t> h_geno;
 	// the warnings of insertCount (:59-62) in the reference's serial order: (byte found, value wanted)
 	std::vector<std::pair<uint8_t, uint32_t>> warnings;
@@ -76,7 +77,7 @@ extern "C" void ntsm_multi_destroy(ntsm_multi *m)
 	if (!m) return;
 	cudaSetDevice(m->v.device);
 	void *ptrs[] = { m->d_mat, m->d_windows, m->d_lens, m->d_geno, m->d_occ, m->d_list, m->d_uniq, m->d_cnt, m->d_off,
-	                 m->d_partial, m->d_scalars, m->d_cursor, m->d_rows, m->d_one };
+	                 m->d_partial, m->d_scalars, m->d_cursor, m->d_rows, m->d_one, m->d_values, m->d_sums };
 	for (void *p : ptrs)
 		if (p) cudaFree(p);
 	for (cudaEvent_t e : m->ev)
@@ -319,39 +320,68 @@ extern "C" int ntsm_multi_counts_max(ntsm_multi *m, uint32_t sample, uint32_t *m
 	return NTSM_OK;
 }
 
-extern "C" int ntsm_multi_norm_matrix(ntsm_multi *m, double *values, double *sums)
+// printNormMatrix in three steps, so that a caller can take the rows in blocks while it formats the previous ones:
+// begin runs the kernels and leaves values[site][sample] and sums[site] on the device (first_undef, nullable: the
+// row-major index of the first missing value, UINT64_MAX if there is none -- where the reference's stream switches to
+// 19 digits, :192), fetch copies rows [row0, row0 + n_rows) into caller memory, end frees the device copies.
+int ntsm_multi_norm_begin(ntsm_multi *m, uint64_t *first_undef)
 {
 	if (!m) return NTSM_ERR_ARG;
 	MCU(m, cudaSetDevice(m->v.device));
+	ntsm_multi_norm_end(m);
 	const uint32_t S = m->v.n_sites, N = m->n_samples;
+	if (first_undef) *first_undef = UINT64_MAX;
 	if (S == 0) return NTSM_OK;
-	double *d_values = nullptr, *d_sums = nullptr;
-	MCU(m, cudaMalloc(&d_values, ((size_t)S * N + 1) * sizeof(double)));
-	cudaError_t e = cudaMalloc(&d_sums, (size_t)S * sizeof(double));
-	auto run = [&]() -> cudaError_t {
-		if (e != cudaSuccess) return e;
-		cudaEventRecord(m->ev[0], m->stream);
-		if (N) {
-			const dim3 grid((S + 31) / 32, (N + 31) / 32);
-			multi_norm_kernel<<<grid, dim3(32, 32), 0, m->stream>>>(m->d_mat, m->stride, m->v.d_allele_off, S, N, d_values);
-		}
-		multi_norm_sum_kernel<<<(S + 7) / 8, 256, 0, m->stream>>>(d_values, S, N, d_sums);
-		cudaError_t r = cudaGetLastError();
-		if (r != cudaSuccess) return r;
-		cudaEventRecord(m->ev[1], m->stream);
-		if (values && N && (r = cudaMemcpyAsync(values, d_values, (size_t)S * N * sizeof(double), cudaMemcpyDeviceToHost, m->stream)) != cudaSuccess) return r;
-		if (sums && (r = cudaMemcpyAsync(sums, d_sums, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, m->stream)) != cudaSuccess) return r;
-		return cudaStreamSynchronize(m->stream);
-	};
-	e = run();
-	cudaFree(d_values);
-	if (d_sums) cudaFree(d_sums);
-	if (e != cudaSuccess) return mfail(m, NTSM_ERR_CUDA, "ntsm_multi_norm_matrix: %s", cudaGetErrorString(e));
+	MCU(m, cudaMalloc(&m->d_values, ((size_t)S * N + 1) * sizeof(double)));
+	MCU(m, cudaMalloc(&m->d_sums, (size_t)S * sizeof(double)));
+	MCU(m, cudaMemsetAsync(m->d_scalars, 0xFF, 8, m->stream));
+	MCU(m, cudaEventRecord(m->ev[0], m->stream));
+	if (N) {
+		const dim3 grid((S + 31) / 32, (N + 31) / 32);
+		multi_norm_kernel<<<grid, dim3(32, 32), 0, m->stream>>>(m->d_mat, m->stride, m->v.d_allele_off, S, N, m->d_values, m->d_scalars);
+	}
+	multi_norm_sum_kernel<<<(S + 7) / 8, 256, 0, m->stream>>>(m->d_values, S, N, m->d_sums);
+	MCU(m, cudaGetLastError());
+	MCU(m, cudaEventRecord(m->ev[1], m->stream));
+	unsigned long long first = 0;
+	MCU(m, cudaMemcpyAsync(&first, m->d_scalars, 8, cudaMemcpyDeviceToHost, m->stream));
+	MCU(m, cudaStreamSynchronize(m->stream));
+	if (first_undef) *first_undef = first;
 	float ms = 0;
 	if (cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]) == cudaSuccess) m->ms_norm += ms;
 	ntsm_ctx_add_launches(m->ctx, N ? 2 : 1);
-	ntsm_ctx_add_pcie(m->ctx, 0, (values ? (uint64_t)S * N * 8 : 0) + (sums ? (uint64_t)S * 8 : 0));
 	return NTSM_OK;
+}
+
+int ntsm_multi_norm_fetch(ntsm_multi *m, uint32_t row0, uint32_t n_rows, double *values, double *sums)
+{
+	if (!m) return NTSM_ERR_ARG;
+	const uint32_t S = m->v.n_sites, N = m->n_samples;
+	if (n_rows == 0) return NTSM_OK;
+	if (!m->d_values || row0 > S || n_rows > S - row0) return mfail(m, NTSM_ERR_ARG, "ntsm_multi_norm_fetch: rows %u..%u of %u (begin first)", row0, row0 + n_rows, S);
+	MCU(m, cudaSetDevice(m->v.device));
+	if (values && N) MCU(m, cudaMemcpyAsync(values, m->d_values + (size_t)row0 * N, (size_t)n_rows * N * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+	if (sums) MCU(m, cudaMemcpyAsync(sums, m->d_sums + row0, (size_t)n_rows * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+	MCU(m, cudaStreamSynchronize(m->stream));
+	ntsm_ctx_add_pcie(m->ctx, 0, (values ? (uint64_t)n_rows * N * 8 : 0) + (sums ? (uint64_t)n_rows * 8 : 0));
+	return NTSM_OK;
+}
+
+void ntsm_multi_norm_end(ntsm_multi *m)
+{
+	if (!m) return;
+	if (m->d_values) cudaFree(m->d_values);
+	if (m->d_sums) cudaFree(m->d_sums);
+	m->d_values = m->d_sums = nullptr;
+}
+
+extern "C" int ntsm_multi_norm_matrix(ntsm_multi *m, double *values, double *sums)
+{
+	if (!m) return NTSM_ERR_ARG;
+	int rc = ntsm_multi_norm_begin(m, nullptr);
+	if (rc == NTSM_OK) rc = ntsm_multi_norm_fetch(m, 0, m->v.n_sites, values, sums);
+	ntsm_multi_norm_end(m);
+	return rc;
 }
 
 // device time so far, by CUDA events on the stream: ms[0] the k-merize + table lookup + occurrence lists of every batch,

@@ -261,7 +261,8 @@ __global__ void multi_counts_max_kernel(const uint8_t *__restrict__ row, const u
 // as doubles, kUndef where both are zero.  A 32 x 32 tile: threads read the matrix with the SITE index fastest (adjacent
 // sites are adjacent bytes of a sample's row) and write the values with the SAMPLE index fastest (rows of the output).
 __global__ void __launch_bounds__(1024) multi_norm_kernel(const uint8_t *__restrict__ mat, uint64_t stride, const uint32_t *__restrict__ allele_off,
-                                                           uint32_t n_sites, uint32_t n_samples, double *__restrict__ values)
+                                                           uint32_t n_sites, uint32_t n_samples, double *__restrict__ values,
+                                                           unsigned long long *__restrict__ first_undef)
 {
 	__shared__ double tile[32][33];
 	const uint32_t i = blockIdx.x * 32 + threadIdx.x, s = blockIdx.y * 32 + threadIdx.y;
@@ -276,6 +277,15 @@ __global__ void __launch_bounds__(1024) multi_norm_kernel(const uint8_t *__restr
 		if (denom) v = (double)mr / (double)denom;                // :183 (IEEE division, as the host's)
 	}
 	tile[threadIdx.y][threadIdx.x] = v;
+	// row-major position of the first missing value of the whole matrix: where the reference's output stream starts printing 19
+	// digits (MultiCount.hpp:192).  One atomic per warp that holds one.
+	unsigned long long at = i < n_sites && s < n_samples && v == kUndef ? (unsigned long long)i * n_samples + s : ~0ull;
+#pragma unroll
+	for (int d = 16; d; d >>= 1) {
+		const unsigned long long o = __shfl_xor_sync(0xffffffffu, at, d);
+		at = o < at ? o : at;
+	}
+	if ((threadIdx.x & 31) == 0 && at != ~0ull) atomicMin(first_undef, at);
 	__syncthreads();
 	const uint32_t oi = blockIdx.x * 32 + threadIdx.y, os = blockIdx.y * 32 + threadIdx.x;
 	if (oi < n_sites && os < n_samples) values[(size_t)oi * n_samples + os] = tile[threadIdx.x][threadIdx.y];

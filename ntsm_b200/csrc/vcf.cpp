@@ -23,6 +23,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <fstream>
 #include <iostream>
 #include <mutex>
@@ -402,40 +403,84 @@ extern "C" int ntsm_multi_write_norm_matrix(ntsm_multi *m, const ntsm_sites *sit
 	fwrite(o.data(), 1, o.size(), out);
 	int rc = NTSM_OK;
 	if (ntsm_sites_printable(sites) != NTSM_OK) rc = NTSM_ERR_NOKEY;   // the first `at` on an erased k-mer / a missing var list throws (:158,:169)
-	std::vector<double> values, sums;
+	uint64_t sw = UINT64_MAX;                                      // row-major position of the first missing value: the precision switch
+	if (rc == NTSM_OK && S) rc = ntsm_multi_norm_begin(m, &sw);
 	if (rc == NTSM_OK && S) {
-		values.resize((size_t)S * N + 1);
-		sums.resize(S);
-		rc = ntsm_multi_norm_matrix(m, values.data(), sums.data());
-	}
-	if (rc == NTSM_OK && S) {
-		const uint32_t T = std::max(1u, threads), rows_per_block = 64;
-		const size_t n_blocks = ((size_t)S + rows_per_block - 1) / rows_per_block;
-		// where the stream's precision switches: the first missing value in row-major order
-		std::vector<uint64_t> first(n_blocks, UINT64_MAX);
-		parallel_for(n_blocks, T, [&](size_t b) {
-			const size_t lo = b * rows_per_block * (size_t)N, hi = std::min<size_t>((size_t)S, (b + 1) * rows_per_block) * (size_t)N;
-			for (size_t x = lo; x < hi; ++x)
-				if (values[x] == 1.7976931348623157e308) { first[b] = x; break; }
+		// Three stages side by side: a fetcher copies the next block of rows off the device, `threads` workers turn the
+		// current block into text (64 rows each), a writer puts the finished text into the two files in row order.
+		const uint32_t T = std::max(1u, threads), rows_per_item = 64;
+		const uint32_t block_rows = std::max<uint32_t>(rows_per_item, std::min<uint32_t>(S, (uint32_t)std::max<size_t>(rows_per_item * 2 * (size_t)T, (32u << 20) / ((size_t)N * 8 + 8))));
+		const uint32_t n_blocks = (S + block_rows - 1) / block_rows;
+		struct Block {
+			std::vector<double> values, sums;
+			std::vector<std::string> mtext, ctext;
+			int state = 0;                                         // 0 free, 1 fetched, 2 formatted
+		} blk[2];
+		for (Block &b : blk) {
+			b.values.resize((size_t)block_rows * N + 1);
+			b.sums.resize(block_rows);
+			ntsm_host_register(b.values.data(), b.values.size() * sizeof(double));   // page-locked: the copies run at the link's rate; best effort
+		}
+		std::mutex mu;
+		std::condition_variable cv;
+		int failed = NTSM_OK;
+		std::thread fetcher([&] {
+			for (uint32_t b = 0; b < n_blocks; ++b) {
+				Block &B = blk[b & 1];
+				{
+					std::unique_lock<std::mutex> lk(mu);
+					cv.wait(lk, [&] { return B.state == 0 || failed; });
+					if (failed) return;
+				}
+				const uint32_t r0 = b * block_rows, nr = std::min(block_rows, S - r0);
+				const int r = ntsm_multi_norm_fetch(m, r0, nr, B.values.data(), B.sums.data());
+				std::lock_guard<std::mutex> lk(mu);
+				if (r) failed = r;
+				B.state = 1;
+				cv.notify_all();
+			}
 		});
-		uint64_t sw = UINT64_MAX;
-		for (uint64_t x : first) sw = std::min(sw, x);
-		const size_t round = std::max<size_t>(4 * (size_t)T, 16);
-		std::vector<std::string> mtext(round), ctext(round);
-		for (size_t b0 = 0; b0 < n_blocks; b0 += round) {
-			const size_t nb = std::min(round, n_blocks - b0);
-			parallel_for(nb, T, [&](size_t bi) {
-				std::string &mo = mtext[bi], &co = ctext[bi];
+		std::thread writer([&] {
+			for (uint32_t b = 0; b < n_blocks; ++b) {
+				Block &B = blk[b & 1];
+				{
+					std::unique_lock<std::mutex> lk(mu);
+					cv.wait(lk, [&] { return B.state == 2 || failed; });
+					if (failed) return;
+				}
+				for (size_t i = 0; i < B.mtext.size(); ++i) {
+					fwrite(B.mtext[i].data(), 1, B.mtext[i].size(), out);
+					fwrite(B.ctext[i].data(), 1, B.ctext[i].size(), cf);
+				}
+				std::lock_guard<std::mutex> lk(mu);
+				B.state = 0;
+				cv.notify_all();
+			}
+		});
+		for (uint32_t b = 0; b < n_blocks; ++b) {
+			Block &B = blk[b & 1];
+			{
+				std::unique_lock<std::mutex> lk(mu);
+				cv.wait(lk, [&] { return B.state == 1 || failed; });
+				if (failed) break;
+			}
+			const uint32_t r0 = b * block_rows, nr = std::min(block_rows, S - r0);
+			const size_t items = (nr + rows_per_item - 1) / rows_per_item;
+			B.mtext.resize(items);
+			B.ctext.resize(items);
+			parallel_for(items, T, [&](size_t it) {
+				std::string &mo = B.mtext[it], &co = B.ctext[it];
 				mo.clear();
 				co.clear();
 				DoubleText cache;
 				char num[64];
-				const uint32_t i0 = (uint32_t)((b0 + bi) * rows_per_block), i1 = std::min<uint32_t>(S, i0 + rows_per_block);
-				for (uint32_t i = i0; i < i1; ++i) {
+				const uint32_t l0 = (uint32_t)it * rows_per_item, l1 = std::min(nr, l0 + rows_per_item);
+				for (uint32_t l = l0; l < l1; ++l) {
+					const uint32_t i = r0 + l;
 					mo += ntsm_sites_name(sites, i);               // :187
-					const long double center = (long double)sums[i] / (long double)(uint64_t)N;   // :188-189: size counts every sample
+					const long double center = (long double)B.sums[l] / (long double)(uint64_t)N;   // :188-189: size counts every sample
 					const int cl = snprintf(num, sizeof num, "%.19Lg", center);
-					const double *row = values.data() + (size_t)i * N;
+					const double *row = B.values.data() + (size_t)l * N;
 					for (uint32_t j = 0; j < N; ++j) {
 						mo.push_back('\t');
 						if (row[j] == 1.7976931348623157e308) mo.append(num, (size_t)cl);        // UNDEF (:41,190): the centre, 19 digits
@@ -446,12 +491,16 @@ extern "C" int ntsm_multi_write_norm_matrix(ntsm_multi *m, const ntsm_sites *sit
 					co.push_back('\n');
 				}
 			});
-			for (size_t bi = 0; bi < nb; ++bi) {
-				fwrite(mtext[bi].data(), 1, mtext[bi].size(), out);
-				fwrite(ctext[bi].data(), 1, ctext[bi].size(), cf);
-			}
+			std::lock_guard<std::mutex> lk(mu);
+			B.state = 2;
+			cv.notify_all();
 		}
+		fetcher.join();
+		writer.join();
+		for (Block &b : blk) ntsm_host_unregister(b.values.data());
+		if (failed) rc = failed;
 	}
+	ntsm_multi_norm_end(m);
 	fclose(out);
 	fclose(cf);
 	return rc;
