@@ -347,6 +347,19 @@ int ntsm_vcf_convert(ntsm_vcf **out, ntsm_ctx *ctx, const ntsm_sites *s, const c
                      uint32_t threads /* opt::threads: host threads that parse the VCF (and later format the matrix);
                                          the result does not depend on it */, int verbose);
 void ntsm_vcf_destroy(ntsm_vcf *v);
+/* The host half of the above on its own, no device needed: the SNP lines of the VCF as ntsm_multi_insert_windows takes
+ * them (windows [2 * count][wstride] + lens [2 * count], genotypes [count][n_samples]).  Returns the code
+ * ntsm_vcf_convert would; *out is set even then and holds the lines in front of the fatal one. */
+typedef struct ntsm_vcf_lines ntsm_vcf_lines;
+int ntsm_vcf_parse(ntsm_vcf_lines **out, const char *ref_path, const char *vcf_path, uint32_t window, uint32_t threads, int verbose);
+void ntsm_vcf_lines_free(ntsm_vcf_lines *l);
+uint32_t ntsm_vcf_lines_n_samples(const ntsm_vcf_lines *l);
+const char *ntsm_vcf_lines_sample_id(const ntsm_vcf_lines *l, uint32_t i);
+uint64_t ntsm_vcf_lines_count(const ntsm_vcf_lines *l);
+uint32_t ntsm_vcf_lines_wstride(const ntsm_vcf_lines *l);
+const char *ntsm_vcf_lines_windows(const ntsm_vcf_lines *l);
+const uint16_t *ntsm_vcf_lines_lens(const ntsm_vcf_lines *l);
+const uint8_t *ntsm_vcf_lines_genotypes(const ntsm_vcf_lines *l);
 ntsm_multi *ntsm_vcf_multi(ntsm_vcf *v);
 uint32_t ntsm_vcf_n_samples(const ntsm_vcf *v);
 const char *ntsm_vcf_sample_id(const ntsm_vcf *v, uint32_t i);

@@ -122,6 +122,15 @@ _SIGS = {
     "ntsm_multi_write_norm_matrix": (C.c_int, [_P, _P, _P, C.c_char_p, C.c_char_p, C.c_uint32]),
     "ntsm_vcf_convert": (C.c_int, [C.POINTER(_P), _P, _P, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
     "ntsm_vcf_destroy": (None, [_P]),
+    "ntsm_vcf_parse": (C.c_int, [C.POINTER(_P), C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_int]),
+    "ntsm_vcf_lines_free": (None, [_P]),
+    "ntsm_vcf_lines_n_samples": (C.c_uint32, [_P]),
+    "ntsm_vcf_lines_sample_id": (C.c_char_p, [_P, C.c_uint32]),
+    "ntsm_vcf_lines_count": (C.c_uint64, [_P]),
+    "ntsm_vcf_lines_wstride": (C.c_uint32, [_P]),
+    "ntsm_vcf_lines_windows": (_P, [_P]),
+    "ntsm_vcf_lines_lens": (_P, [_P]),
+    "ntsm_vcf_lines_genotypes": (_P, [_P]),
     "ntsm_vcf_multi": (_P, [_P]),
     "ntsm_vcf_n_samples": (C.c_uint32, [_P]),
     "ntsm_vcf_sample_id": (C.c_char_p, [_P, C.c_uint32]),

@@ -40,7 +40,7 @@ struct ntsm_multi {
 	// device time of the kernels, by CUDA events on the stream (ntsm_multi_kernel_ms)
 	cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 	double ms_lists = 0, ms_fill = 0, ms_norm = 0;
-	uint64_t cells_touched = 0;             // (occurring k-mer, sample) pairs the fill kernel walked, per pass
+	uint64_t cells_touched = 0;             // (occurring k-mer, sample) pairs the fill kernel walked (once with multi <= 127, else twice)
 };
 
 static int mfail(ntsm_multi *m, int code, const char *fmt, ...)
@@ -206,13 +206,17 @@ static int insert_batch(ntsm_multi *m, const char *windows, uint32_t wstride, co
 
 	FillParams P{ m->d_uniq, n_uniq, m->d_off, m->d_list, m->d_geno, gwords, J, S, multi, m->d_mat, m->stride, m->d_scalars + 1, nullptr };
 	const dim3 grid((n_uniq + 127) / 128, std::min<uint32_t>(gwords, 65535u));
+	const bool one_pass = multi <= 127;                           // every value fits the byte: write and count together (multi.cuh)
 	MCU(m, cudaEventRecord(m->ev[2], st));
-	multi_fill_kernel<0><<<grid, 128, 0, st>>>(P);
+	if (one_pass) multi_fill_kernel<3><<<grid, 128, 0, st>>>(P);
+	else multi_fill_kernel<0><<<grid, 128, 0, st>>>(P);
+	MCU(m, cudaGetLastError());
 	MCU(m, cudaEventRecord(m->ev[3], st));
 	unsigned long long n_warn = 0;
 	MCU(m, cudaMemcpyAsync(&n_warn, m->d_scalars + 1, 8, cudaMemcpyDeviceToHost, st));
 	MCU(m, cudaStreamSynchronize(st));
 	ntsm_ctx_add_launches(m->ctx, 1);
+	if (cudaEventElapsedTime(&ms, m->ev[2], m->ev[3]) == cudaSuccess) m->ms_fill += ms;
 	if (n_warn) {
 		MultiWarn *d_warn = nullptr;
 		MCU(m, cudaMalloc(&d_warn, n_warn * sizeof(MultiWarn)));
@@ -229,14 +233,16 @@ static int insert_batch(ntsm_multi *m, const char *windows, uint32_t wstride, co
 		std::sort(w.begin(), w.end(), [](const MultiWarn &a, const MultiWarn &b) { return a.occ != b.occ ? a.occ < b.occ : a.sample < b.sample; });
 		for (const MultiWarn &x : w) m->warnings.emplace_back((uint8_t)x.old_value, x.wanted);
 	}
-	MCU(m, cudaEventRecord(m->ev[4], st));
-	multi_fill_kernel<2><<<grid, 128, 0, st>>>(P);
-	MCU(m, cudaGetLastError());
-	MCU(m, cudaEventRecord(m->ev[5], st));
-	MCU(m, cudaStreamSynchronize(st));                            // the host buffers of this batch are the caller's again
-	ntsm_ctx_add_launches(m->ctx, 1);
-	if (cudaEventElapsedTime(&ms, m->ev[2], m->ev[3]) == cudaSuccess) m->ms_fill += ms;
-	if (cudaEventElapsedTime(&ms, m->ev[4], m->ev[5]) == cudaSuccess) m->ms_fill += ms;
+	if (!one_pass) {
+		MCU(m, cudaEventRecord(m->ev[4], st));
+		multi_fill_kernel<2><<<grid, 128, 0, st>>>(P);
+		MCU(m, cudaGetLastError());
+		MCU(m, cudaEventRecord(m->ev[5], st));
+		MCU(m, cudaStreamSynchronize(st));
+		ntsm_ctx_add_launches(m->ctx, 1);
+		if (cudaEventElapsedTime(&ms, m->ev[4], m->ev[5]) == cudaSuccess) m->ms_fill += ms;
+	}
+	// (every path above ends on a stream synchronize: the host buffers of this batch are the caller's again)
 	m->cells_touched += (uint64_t)n_uniq * S;
 	return NTSM_OK;
 }

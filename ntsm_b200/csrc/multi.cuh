@@ -181,8 +181,27 @@ struct FillParams {
 	MultiWarn *warn;
 };
 
-// MODE 0: dry run, only count the warnings this batch will raise; MODE 1: dry run, record them; MODE 2: write the cells.
-// (Almost every batch raises none: 0 then 2.  The cells are written last so that 0 and 1 see the same bytes.)
+// MODE 0: dry run, only count the warnings this batch will raise; MODE 1: dry run, record them; MODE 2: write the cells;
+// MODE 3: write the cells and count the warnings in one pass.
+// With multi <= 127 every inserted value fits the byte, and a replay that starts from the bytes AFTER the batch raises
+// exactly the warnings of the replay from the bytes before it (a cell that was empty now holds its first writer's value,
+// which that writer's own insert equals): one pass of MODE 3, and MODE 1 afterwards only if it counted any.  With larger
+// multi the byte wraps (400 is stored as 144 and a later 400 "differs"), so 0, (1), then 2: the cells are written last.
+// MultiCount::insertCount's decision for one insert of value v into a cell that holds x (:58-67)
+template <int MODE>
+__device__ __forceinline__ void fill_insert(const FillParams &P, uint32_t &x, uint32_t v, uint32_t o, uint32_t s)
+{
+	if (x > 0) {                                                  // :58
+		if (x != v) {                                             // :59
+			if (MODE == 0 || MODE == 3) atomicAdd(P.n_warn, 1ull);
+			if (MODE == 1) {
+				const unsigned long long at = atomicAdd(P.n_warn, 1ull);
+				P.warn[at] = MultiWarn{ o, s, x, v };
+			}
+		}
+	} else x = v & 0xFFu;                                         // :65-67, the byte takes the value's low 8 bits
+}
+
 template <int MODE>
 __global__ void multi_fill_kernel(const FillParams P)
 {
@@ -190,12 +209,29 @@ __global__ void multi_fill_kernel(const FillParams P)
 	if (u >= P.n_uniq) return;
 	const uint32_t idx = P.uniq[u];
 	const uint32_t beg = (uint32_t)P.off[idx], n = (uint32_t)P.off[idx + 1] - beg;
+	const uint32_t first = P.list[beg];
 	// a thread takes its k-mer through 16 samples at a time (one word of genotypes): the list offsets are read once
 	// per 16 cells, and a warp's 32 k-mers are 32 neighbouring bytes of each sample's row
 	for (uint32_t sg = blockIdx.y; sg < P.gwords; sg += gridDim.y) {
 		const uint32_t s_end = min(P.n_samples, sg * 16 + 16);
+		if (n == 1) {
+			// the k-mer occurs once in the batch (nearly always): one genotype word decides all 16 cells
+			const uint32_t w = first / P.J;                       // line * 2 + allele
+			const uint32_t gw = P.geno[(size_t)(w >> 1) * P.gwords + sg];
+			const uint32_t hom = (w & 1) ? 2u : 0u;
+			uint8_t *cell = P.mat + P.stride * (sg * 16) + idx;   // :56-57
+			for (uint32_t s = sg * 16; s < s_end; ++s, cell += P.stride) {
+				const uint32_t g = (gw >> (2 * (s & 15))) & 3u;
+				if (g != 1 && g != hom) continue;                 // this sample does not carry this window's allele
+				const uint32_t x0 = *cell;
+				uint32_t x = x0;
+				fill_insert<MODE>(P, x, g == 1 ? P.multi : P.multi * 2, first, s);   // VCFConvert.hpp:151-155,162-166
+				if ((MODE == 2 || MODE == 3) && x != x0) *cell = (uint8_t)x;
+			}
+			continue;
+		}
 		for (uint32_t s = sg * 16; s < s_end; ++s) {
-			uint8_t *cell = P.mat + P.stride * s + idx;           // :56-57
+			uint8_t *cell = P.mat + P.stride * s + idx;
 			const uint32_t x0 = *cell;
 			uint32_t x = x0;
 			int64_t last = -1;
@@ -206,23 +242,12 @@ __global__ void multi_fill_kernel(const FillParams P)
 					if ((int64_t)c > last && c < o) o = c;
 				}
 				last = o;
-				const uint32_t w = o / P.J;                       // line * 2 + allele
+				const uint32_t w = o / P.J;
 				const uint32_t g = (P.geno[(size_t)(w >> 1) * P.gwords + sg] >> (2 * (s & 15))) & 3u;
-				uint32_t v;
-				if (g == 1) v = P.multi;                          // het: both alleles once (VCFConvert.hpp:153-155,164-166)
-				else if (g == ((w & 1) ? 2u : 0u)) v = P.multi * 2;   // homozygous for this window's allele (:151-152,162-163)
-				else continue;
-				if (x > 0) {                                      // :58
-					if (x != v) {                                 // :59
-						if (MODE == 0) atomicAdd(P.n_warn, 1ull);
-						if (MODE == 1) {
-							const unsigned long long at = atomicAdd(P.n_warn, 1ull);
-							P.warn[at] = MultiWarn{ o, s, x, v };
-						}
-					}
-				} else x = v & 0xFFu;                             // :65-67, the byte takes the value's low 8 bits
+				if (g == 1) fill_insert<MODE>(P, x, P.multi, o, s);                       // het: both alleles once
+				else if (g == ((w & 1) ? 2u : 0u)) fill_insert<MODE>(P, x, P.multi * 2, o, s);   // homozygous for this window's allele
 			}
-			if (MODE == 2 && x != x0) *cell = (uint8_t)x;
+			if ((MODE == 2 || MODE == 3) && x != x0) *cell = (uint8_t)x;
 		}
 	}
 }

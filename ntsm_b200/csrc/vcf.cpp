@@ -246,21 +246,22 @@ extern "C" uint32_t ntsm_vcf_n_samples(const ntsm_vcf *v) { return v ? (uint32_t
 extern "C" const char *ntsm_vcf_sample_id(const ntsm_vcf *v, uint32_t i) { return v && i < v->sample_ids.size() ? v->sample_ids[i].c_str() : nullptr; }
 extern "C" uint64_t ntsm_vcf_lines_counted(const ntsm_vcf *v) { return v ? v->lines_counted : 0; }
 
-// VCFConvert::VCFConvert (:42-59) + VCFConvert::count (:62-174)
-extern "C" int ntsm_vcf_convert(ntsm_vcf **out, ntsm_ctx *ctx, const ntsm_sites *sites, const char *ref_path, const char *vcf_path,
-                                uint32_t multi, uint32_t window, uint32_t threads, int verbose)
-{
-	if (!out || !ctx || !sites || !ref_path || !vcf_path) return vfail(ctx, NTSM_ERR_ARG, "ntsm_vcf_convert: null argument");
-	*out = nullptr;
-	if (window == 0 || window > 65535) return vfail(ctx, NTSM_ERR_ARG, "window must be in 1..65535");
+namespace {
 
+// The host half of VCFConvert::VCFConvert (:42-59) + VCFConvert::count (:62-146): genome, header, and every SNP line
+// turned into two windows + packed genotypes, handed on in file order.  on_header(sample IDs) is called once, then
+// on_batch(batch, wstride) for every run of lines; either may return non-zero to stop.  No device is touched here.
+template <class H, class B>
+int vcf_stream(const char *ref_path, const char *vcf_path, uint32_t window, uint32_t threads, int verbose, std::string &err, H on_header, B on_batch)
+{
+	if (window == 0 || window > 65535) { err = "window must be in 1..65535"; return NTSM_ERR_ARG; }
 	// the reference genome: every record whole; a later record of the same name replaces the earlier one (:47-58)
 	if (verbose > 1) std::cerr << "Loading Reference " << ref_path << std::endl;
 	std::vector<Chrom> chroms;
 	std::unordered_map<std::string, uint32_t> chr_ids;
 	{
 		ntsm::FastxReader rd;
-		if (!rd.open(ref_path, 0, false)) return vfail(ctx, NTSM_ERR_IO, std::string("file ") + ref_path + " cannot be opened");
+		if (!rd.open(ref_path, 0, false)) { err = std::string("file ") + ref_path + " cannot be opened"; return NTSM_ERR_IO; }
 		int64_t l;
 		while ((l = rd.next()) >= 0) {
 			chr_ids[rd.name()] = (uint32_t)chroms.size();
@@ -271,12 +272,10 @@ extern "C" int ntsm_vcf_convert(ntsm_vcf **out, ntsm_ctx *ctx, const ntsm_sites 
 
 	if (verbose > 1) std::cerr << "Reading VCF file: " << vcf_path << std::endl;
 	Text text;
-	if (!text.open(vcf_path)) return vfail(ctx, NTSM_ERR_IO, std::string("file ") + vcf_path + " cannot be opened");
+	if (!text.open(vcf_path)) { err = std::string("file ") + vcf_path + " cannot be opened"; return NTSM_ERR_IO; }
 	const char *at = text.p, *const end = text.p + text.n;
 
-	ntsm_vcf *v = new ntsm_vcf();
-	v->ctx = ctx;
-	v->sites = sites;
+	std::vector<std::string> sample_ids;
 	std::vector<Field> f;
 	// header: lines are looked at until the one whose first field is "#CHROM"; 8 more fields are skipped, the rest
 	// are the sample IDs (:71-93).  A last line without '\n' is still a line here (the stream only goes bad after it).
@@ -285,27 +284,24 @@ extern "C" int ntsm_vcf_convert(ntsm_vcf **out, ntsm_ctx *ctx, const ntsm_sites 
 		const char *le = nl ? nl : end;
 		const size_t len = (size_t)(le - at);
 		if (len == 0) {                                            // line.at(0) throws
-			ntsm_vcf_destroy(v);
-			return vfail(ctx, NTSM_ERR_NOKEY, "empty line before the #CHROM line: the reference dies in string::at (src/VCFConvert.hpp:74)");
+			err = "empty line before the #CHROM line: the reference dies in string::at (src/VCFConvert.hpp:74)";
+			return NTSM_ERR_NOKEY;
 		}
 		const bool is_header = at[0] == '#';
 		if (is_header) split(at, len, f);
 		at = nl ? nl + 1 : end;
 		if (is_header && f[0].n == 6 && memcmp(f[0].p, "#CHROM", 6) == 0) {
-			for (size_t i = 9; i < f.size(); ++i) v->sample_ids.emplace_back(f[i].p, f[i].n);
+			for (size_t i = 9; i < f.size(); ++i) sample_ids.emplace_back(f[i].p, f[i].n);
 			break;
 		}
 	}
-	const uint32_t S = (uint32_t)v->sample_ids.size();
+	const uint32_t S = (uint32_t)sample_ids.size();
 	if (verbose > 1) std::cerr << "Starting multicount of each rsID for " << S << " samples." << std::endl;
-	int rc = ntsm_multi_create(&v->multi, ctx, S);
-	if (rc) {
-		ntsm_vcf_destroy(v);
-		return rc;
-	}
+	int rc = on_header(sample_ids);
+	if (rc) return rc;
 
 	// The data lines.  Parsing is per line and independent, so `threads` workers (opt::threads: the reference runs this
-	// loop under `omp parallel`, :99) parse batches of lines side by side; the batches then go to the GPU in file
+	// loop under `omp parallel`, :99) parse batches of lines side by side; the batches are then handed on in file
 	// order, which -- unlike upstream with more than one thread -- keeps "the first writer of a cell wins" the
 	// one-thread result whatever `threads` is.
 	const uint32_t wstride = (window + 15u) & ~15u;
@@ -335,24 +331,99 @@ extern "C" int ntsm_vcf_convert(ntsm_vcf **out, ntsm_ctx *ctx, const ntsm_sites 
 		parallel_for(nb, T, [&](size_t i) { parse_lines(env, spans[r0 + i].first, spans[r0 + i].second, batches[i]); });
 		for (size_t i = 0; i < nb; ++i) {
 			LineBatch &b = batches[i];
-			if (b.n) {
-				rc = ntsm_multi_insert_windows_packed(v->multi, b.windows.data(), wstride, b.lens.data(), b.geno2.data(), b.n, multi);
-				if (rc) {
-					ntsm_vcf_destroy(v);
-					return rc;
-				}
-				v->lines_counted += b.n;
-			}
-			if (b.err) {                                           // the lines before it in the file have been inserted, as upstream before it dies
-				ntsm_vcf_destroy(v);
-				return vfail(ctx, b.err, b.msg);
+			if (b.n && (rc = on_batch(b, wstride))) return rc;     // the lines before a fatal one are handed on, as upstream inserts them before it dies
+			if (b.err) {
+				err = b.msg;
+				return b.err;
 			}
 		}
 	}
-	v->threads = T;
+	return NTSM_OK;
+}
+
+}  // namespace
+
+// VCFConvert::VCFConvert (:42-59) + VCFConvert::count (:62-174)
+extern "C" int ntsm_vcf_convert(ntsm_vcf **out, ntsm_ctx *ctx, const ntsm_sites *sites, const char *ref_path, const char *vcf_path,
+                                uint32_t multi, uint32_t window, uint32_t threads, int verbose)
+{
+	if (!out || !ctx || !sites || !ref_path || !vcf_path) return vfail(ctx, NTSM_ERR_ARG, "ntsm_vcf_convert: null argument");
+	*out = nullptr;
+	ntsm_vcf *v = new ntsm_vcf();
+	v->ctx = ctx;
+	v->sites = sites;
+	v->threads = std::max(1u, threads);
+	std::string err;
+	bool own_error = false;                                        // the failing call has already left its text on the ctx
+	const int rc = vcf_stream(
+	    ref_path, vcf_path, window, threads, verbose, err,
+	    [&](const std::vector<std::string> &ids) {
+		    v->sample_ids = ids;
+		    const int r = ntsm_multi_create(&v->multi, ctx, (uint32_t)ids.size());
+		    own_error = r != 0;
+		    return r;
+	    },
+	    [&](const LineBatch &b, uint32_t wstride) {
+		    const int r = ntsm_multi_insert_windows_packed(v->multi, b.windows.data(), wstride, b.lens.data(), b.geno2.data(), b.n, multi);
+		    own_error = r != 0;
+		    v->lines_counted += b.n;
+		    return r;
+	    });
+	if (rc) {
+		ntsm_vcf_destroy(v);
+		return own_error ? rc : vfail(ctx, rc, err);
+	}
 	*out = v;
 	return NTSM_OK;
 }
+
+// The host half alone, kept whole in memory: what ntsm_vcf_convert would insert.  No device needed (tests of the parser;
+// callers that feed ntsm_multi_insert_windows themselves).
+struct ntsm_vcf_lines {
+	std::vector<std::string> sample_ids;
+	uint32_t wstride = 0;
+	uint64_t n = 0;
+	std::vector<char> windows;
+	std::vector<uint16_t> lens;
+	std::vector<uint8_t> genotypes;             // [n][n_samples] 0 hom1, 1 het, 2 hom2
+};
+
+extern "C" int ntsm_vcf_parse(ntsm_vcf_lines **out, const char *ref_path, const char *vcf_path, uint32_t window, uint32_t threads, int verbose)
+{
+	if (!out || !ref_path || !vcf_path) return vfail(nullptr, NTSM_ERR_ARG, "ntsm_vcf_parse: null argument");
+	*out = nullptr;
+	ntsm_vcf_lines *L = new ntsm_vcf_lines();
+	std::string err;
+	const int rc = vcf_stream(
+	    ref_path, vcf_path, window, threads, verbose, err,
+	    [&](const std::vector<std::string> &ids) {
+		    L->sample_ids = ids;
+		    return 0;
+	    },
+	    [&](const LineBatch &b, uint32_t wstride) {
+		    const size_t S = L->sample_ids.size(), gwords = (S + 15) / 16;
+		    L->wstride = wstride;
+		    L->windows.insert(L->windows.end(), b.windows.begin(), b.windows.begin() + (size_t)b.n * 2 * wstride);
+		    L->lens.insert(L->lens.end(), b.lens.begin(), b.lens.begin() + (size_t)b.n * 2);
+		    for (uint32_t l = 0; l < b.n; ++l)
+			    for (size_t s = 0; s < S; ++s) L->genotypes.push_back((uint8_t)((b.geno2[l * gwords + (s >> 4)] >> (2 * (s & 15))) & 3u));
+		    L->n += b.n;
+		    return 0;
+	    });
+	// the lines in front of a fatal one stay available (upstream has inserted them by then); the code says how it ended
+	*out = L;
+	if (rc) vfail(nullptr, rc, err);
+	return rc;
+}
+
+extern "C" void ntsm_vcf_lines_free(ntsm_vcf_lines *L) { delete L; }
+extern "C" uint32_t ntsm_vcf_lines_n_samples(const ntsm_vcf_lines *L) { return L ? (uint32_t)L->sample_ids.size() : 0; }
+extern "C" const char *ntsm_vcf_lines_sample_id(const ntsm_vcf_lines *L, uint32_t i) { return L && i < L->sample_ids.size() ? L->sample_ids[i].c_str() : nullptr; }
+extern "C" uint64_t ntsm_vcf_lines_count(const ntsm_vcf_lines *L) { return L ? L->n : 0; }
+extern "C" uint32_t ntsm_vcf_lines_wstride(const ntsm_vcf_lines *L) { return L ? L->wstride : 0; }
+extern "C" const char *ntsm_vcf_lines_windows(const ntsm_vcf_lines *L) { return L ? L->windows.data() : nullptr; }
+extern "C" const uint16_t *ntsm_vcf_lines_lens(const ntsm_vcf_lines *L) { return L ? L->lens.data() : nullptr; }
+extern "C" const uint8_t *ntsm_vcf_lines_genotypes(const ntsm_vcf_lines *L) { return L ? L->genotypes.data() : nullptr; }
 
 // ---- printers ----
 namespace {

@@ -149,3 +149,28 @@ class VCFConvert:
 
     def outputCounts(self, directory=None):
         _raise(_lib.lib().ntsm_vcf_output_counts(self._h, os.fsencode(directory) if directory else None), self._fp._ctx)
+
+
+def parse_vcf(ref, vcf, window=31, threads=1, verbose=0):
+    """The host half of VCFConvert::count on its own (ntsm_vcf_parse; no GPU needed): returns
+    (rc, sample_ids, [(ref_window, alt_window), ...], genotypes[n_lines][n_samples]).  rc is 0, or the code
+    ntsm_vcf_convert would return (-134 where the reference dies); the lines in front of a fatal one are still returned."""
+    L = _lib.lib()
+    h = C.c_void_p()
+    rc = L.ntsm_vcf_parse(C.byref(h), os.fsencode(ref), os.fsencode(vcf), window, threads, verbose)
+    if not h:
+        return rc, [], [], np.zeros((0, 0), np.uint8)
+    try:
+        S, n, ws = L.ntsm_vcf_lines_n_samples(h), L.ntsm_vcf_lines_count(h), L.ntsm_vcf_lines_wstride(h)
+        ids = [L.ntsm_vcf_lines_sample_id(h, i).decode() for i in range(S)]
+        wins = []
+        if n:
+            raw = np.ctypeslib.as_array(C.cast(L.ntsm_vcf_lines_windows(h), C.POINTER(C.c_uint8)), (2 * n, ws))
+            lens = np.ctypeslib.as_array(C.cast(L.ntsm_vcf_lines_lens(h), C.POINTER(C.c_uint16)), (2 * n,))
+            wins = [(raw[2 * i, :lens[2 * i]].tobytes(), raw[2 * i + 1, :lens[2 * i + 1]].tobytes()) for i in range(n)]
+        g = np.zeros((n, S), np.uint8)
+        if n and S:
+            g = np.ctypeslib.as_array(C.cast(L.ntsm_vcf_lines_genotypes(h), C.POINTER(C.c_uint8)), (n, S)).copy()
+        return rc, ids, wins, g
+    finally:
+        L.ntsm_vcf_lines_free(h)

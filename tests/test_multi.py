@@ -117,6 +117,58 @@ def test_oracle_matches_live_reference_classes_on_fuzzed_vcfs(oracle, seed, tmp_
     assert open(d + "/orc_stderr.txt", "rb").read() == p.stderr
 
 
+def _oracle_matrix_from_parsed(oracle, sites, k, dupes, multi, n_samples, wins, geno):
+    """MultiCount::insertCount (the oracle's) driven by the LIBRARY's parsed lines in VCFConvert::count's loop order."""
+    omc = oracle.multicount(sites, n_samples, k=k, dupes=bool(dupes))
+    for l, pair in enumerate(wins):
+        for a in range(2):
+            for (_, h, _, _) in oracle.iter(pair[a], k):
+                for s in range(n_samples):
+                    g = geno[l, s]
+                    if g == (2 if a else 0):
+                        omc.insert(s, h, multi * 2)
+                    elif g == 1:
+                        omc.insert(s, h, multi)
+    return omc.matrix()
+
+
+@pytest.mark.parametrize("name", vcf_cases())
+def test_host_vcf_parser_feeds_the_reference_matrix(oracle, name):
+    """The library's host half (genome, header, getSeqFromSite windows, genotype codes; ntsm_vcf_parse, no GPU) against the
+    reference-made fixtures: the windows and genotypes it produces, pushed through the oracle's insertCount, give the
+    reference's byte matrix; where the reference dies while reading the VCF, so does the parser; -t changes nothing."""
+    from ntsm_b200.multicount import parse_vcf
+    d, a, want_rc = _case(name)
+    ref, vcf = os.path.join(d, a["ref"]), os.path.join(d, "in.vcf")
+    rc, ids, wins, geno = parse_vcf(ref, vcf, window=a["window"], threads=1)
+    rc7, ids7, wins7, geno7 = parse_vcf(ref, vcf, window=a["window"], threads=7)
+    assert (rc, ids, wins) == (rc7, ids7, wins7) and np.array_equal(geno, geno7)
+    dies_while_reading = name in ("abort_unknown_chrom", "abort_few_columns", "abort_empty_header_line", "abort_bad_pos")
+    assert rc == (-134 if dies_while_reading else 0)
+    if want_rc:
+        return
+    header = [l for l in open(vcf, errors="replace") if l.startswith("#CHROM")]
+    assert ids == (header[0].rstrip("\n").split("\t")[9:] if header else [])
+    want = np.fromfile(os.path.join(d, "out_mat.bin"), np.uint8)
+    got = _oracle_matrix_from_parsed(oracle, os.path.join(d, "sites.fa"), a["k"], a["dupes"], a["multi"], len(ids), wins, geno)
+    assert got.size == want.size and np.array_equal(got.ravel(), want)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_host_vcf_parser_vs_oracle_on_fuzzed_vcfs(oracle, seed, tmp_path):
+    from ntsm_b200.multicount import parse_vcf
+    rng = random.Random(500 + seed)
+    d = str(tmp_path)
+    k, window = rng.choice([(19, 31), (21, 31), (17, 33)])
+    _fuzz_inputs(rng, d, rng.randrange(5, 60), rng.randrange(1, 40), k=k, window=window, repeats=seed % 2, overlap=seed % 3 == 0)
+    dupes = 1 if seed % 3 == 0 else 0
+    assert oracle.vcf_run(d + "/sites.fa", d + "/ref.fa", d + "/in.vcf", d + "/orc", k=k, dupes=dupes, multi=20, window=window) == 0
+    rc, ids, wins, geno = parse_vcf(d + "/ref.fa", d + "/in.vcf", window=window, threads=1 + seed)
+    assert rc == 0
+    got = _oracle_matrix_from_parsed(oracle, d + "/sites.fa", k, dupes, 20, len(ids), wins, geno)
+    assert got.tobytes() == open(d + "/orc_mat.bin", "rb").read()
+
+
 def test_ntsmvcf_binary_has_no_cpu_path():
     assert os.path.exists(NTSMVCF), "make -C ntsm_b200/csrc"
     try:
