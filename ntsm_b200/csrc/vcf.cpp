@@ -221,6 +221,7 @@ void parse_lines(const ParseEnv &E, const char *at, const char *end, LineBatch &
 			// almost every column is three characters and a tab
 			const char *t = q + 3 < nl && q[3] == '\t' && q[0] != '\t' && q[1] != '\t' && q[2] != '\t' ? q + 3 : (const char *)memchr(q, '\t', (size_t)(nl - q));
 			const char *fe = t ? t : nl;
+			if (!t && fe == q) break;                              // the same `while (getline(...))` (:136): nothing after the line's last tab, no column
 			if (n_cols < S) g[n_cols >> 4] |= (uint32_t)genotype_code(q, (size_t)(fe - q)) << (2 * (n_cols & 15));
 			++n_cols;
 			q = t ? t + 1 : nullptr;
@@ -291,6 +292,9 @@ int vcf_stream(const char *ref_path, const char *vcf_path, uint32_t window, uint
 		if (is_header) split(at, len, f);
 		at = nl ? nl + 1 : end;
 		if (is_header && f[0].n == 6 && memcmp(f[0].p, "#CHROM", 6) == 0) {
+			// `while (getline(ss, item, '\t'))` (:88): a tab at the very end of the line leaves nothing to extract and ends
+			// the loop -- no empty last ID (an empty field between two tabs does count)
+			if (f.size() > 9 && f.back().n == 0) f.pop_back();
 			for (size_t i = 9; i < f.size(); ++i) sample_ids.emplace_back(f[i].p, f[i].n);
 			break;
 		}

@@ -695,17 +695,29 @@ int ntsm_oracle_mc_print_norm_matrix(const ntsm_oracle_mc *mc, const char *const
  * n_samples_out / sample_ids_out (malloc'ed array of malloc'ed strings) describe the header. */
 struct chr_rec { char *name; char *seq; size_t len; };
 
-static char **split_tabs(char *line, size_t *n_out)
+/* Tab-separated fields of a line of `len` bytes (which may hold NUL bytes: std::string items do): pointers + lengths;
+ * every field is also NUL-terminated in place for the calls that take C strings as the reference's do (stoi). */
+static char **split_tabs(char *line, size_t len, size_t *n_out, size_t **len_out)
 {
 	size_t n = 1;
-	for (char *p = line; *p; ++p) n += *p == '\t';
+	for (size_t p = 0; p < len; ++p) n += line[p] == '\t';
 	char **f = (char **)malloc(n * sizeof(char *));
-	size_t i = 0;
-	f[i++] = line;
-	for (char *p = line; *p; ++p)
-		if (*p == '\t') { *p = 0; f[i++] = p + 1; }
+	size_t *fl = (size_t *)malloc(n * sizeof(size_t));
+	size_t i = 0, start = 0;
+	for (size_t p = 0; p <= len; ++p)
+		if (p == len || line[p] == '\t') {
+			f[i] = line + start;
+			fl[i++] = p - start;
+			line[p] = 0;                                           /* line has len + 1 bytes */
+			start = p + 1;
+		}
 	*n_out = n;
+	*len_out = fl;
 	return f;
+}
+static int field_is(char *const *f, const size_t *fl, size_t i, const char *lit)
+{
+	return fl[i] == strlen(lit) && memcmp(f[i], lit, fl[i]) == 0;
 }
 
 static void mc_count_window(void *c, uint64_t hv, uint64_t pos, uint64_t fw, uint64_t rv);
@@ -756,17 +768,20 @@ int ntsm_oracle_vcf_convert(const char *sites_path, const char *ref_path, const 
 		if (got > 0 && line[got - 1] == '\n') line[--got] = 0;
 		if (got == 0) { rc = -134; break; }                        /* line.at(0) throws */
 		if (line[0] != '#') continue;
-		size_t nf;
-		char **f = split_tabs(line, &nf);
-		if (strcmp(f[0], "#CHROM") == 0) {
+		size_t nf, *fl;
+		char **f = split_tabs(line, (size_t)got, &nf, &fl);
+		if (field_is(f, fl, 0, "#CHROM")) {
+			/* `while (getline(ss, item, '\t'))` (:88): a tab at the very end of the line leaves nothing to extract and
+			 * ends the loop -- no empty last ID (an empty field between two tabs does count) */
+			if (nf > 9 && fl[nf - 1] == 0) --nf;
 			for (size_t i = 9; i < nf; ++i) {                      /* 8 more fields skipped, the rest are sample IDs */
 				ids = (char **)realloc(ids, (S + 1) * sizeof(char *));
 				ids[S++] = strdup(f[i]);
 			}
-			free(f);
+			free(f); free(fl);
 			break;
 		}
-		free(f);
+		free(f); free(fl);
 	}
 	ntsm_oracle_mc *mc = NULL;
 	if (rc == 0) {
@@ -778,23 +793,24 @@ int ntsm_oracle_vcf_convert(const char *sites_path, const char *ref_path, const 
 	while (rc == 0 && fh && (got = getline(&line, &cap, fh)) >= 0) {
 		if (got == 0 || line[got - 1] != '\n') break;              /* :101-108: a last line without its newline leaves the stream at eof and is dropped */
 		line[--got] = 0;
-		size_t nf;
-		char **f = split_tabs(line, &nf);
+		size_t nf, *fl;
+		char **f = split_tabs(line, (size_t)got, &nf, &fl);
 		do {
 			/* getline on an exhausted stringstream leaves `item` as it was (:110-125): a missing field
 			 * reads as the last one present */
-#define FIELD(i) (f[(size_t)(i) < nf ? (size_t)(i) : nf - 1])
+#define FIDX(i) ((size_t)(i) < nf ? (size_t)(i) : nf - 1)
+#define FIELD(i) (f[FIDX(i)])
 			char *end;
 			errno = 0;
 			const long loc = strtol(FIELD(1), &end, 10);           /* stoi (:113): leading integer, or it throws */
 			if (end == FIELD(1) || errno == ERANGE || loc > 2147483647L || loc < -2147483647L - 1) { rc = -134; break; }
-			if (strcmp(FIELD(3), ".") == 0) break;                 /* :121-123 */
-			if (strlen(FIELD(4)) != 1) break;                      /* :125-127: ALT must be one character; REF is not looked at */
+			if (field_is(f, fl, FIDX(3), ".")) break;              /* :121-123 */
+			if (fl[FIDX(4)] != 1) break;                           /* :125-127: ALT must be one character; REF is not looked at */
 			const char alt = FIELD(4)[0];
 			/* getSeqFromSite (:202-215) */
 			const struct chr_rec *c = NULL;
 			for (size_t i = 0; i < n_chr; ++i)
-				if (strcmp(chr[i].name, f[0]) == 0) c = &chr[i];   /* later record of the same name wins (:52) */
+				if (field_is(f, fl, 0, chr[i].name)) c = &chr[i];  /* later record of the same name wins (:52) */
 			if (!c) { rc = -134; break; }
 			const unsigned half = window / 2;
 			if (loc < (long)half + 1 || (size_t)(loc - half - 1) > c->len) { rc = -2; break; }
@@ -807,17 +823,19 @@ int ntsm_oracle_vcf_convert(const char *sites_path, const char *ref_path, const 
 			memcpy(wvar, c->seq + offset, avail);
 			wvar[half] = alt;                                      /* :211 */
 			/* sample columns (:136-146) */
-			if ((nf > 9 ? nf - 9 : 0) != (size_t)S) { rc = -134; break; }   /* assert(sampleIndex == m_sampleIDs.size()) */
+			size_t n_cols = nf > 9 ? nf - 9 : 0;
+			if (n_cols && fl[nf - 1] == 0) --n_cols;               /* the same `while (getline(...))` (:136): a trailing tab adds no column */
+			if (n_cols != (size_t)S) { rc = -134; break; }         /* assert(sampleIndex == m_sampleIDs.size()) (:146) */
 			for (uint32_t i = 0; i < S; ++i) {
-				const char *g = f[9 + i];
-				geno[i] = !strcmp(g, "0|0") ? 0 : (!strcmp(g, "0|1") || !strcmp(g, "1|0")) ? 1 : !strcmp(g, "1|1") ? 2 : 0;   /* anything else keeps the vector's initial hom1 */
+				geno[i] = field_is(f, fl, 9 + i, "0|0") ? 0 : (field_is(f, fl, 9 + i, "0|1") || field_is(f, fl, 9 + i, "1|0")) ? 1
+				          : field_is(f, fl, 9 + i, "1|1") ? 2 : 0;   /* anything else keeps the vector's initial hom1 */
 			}
 			struct win_cb cb = { mc, geno, S, multi, 0, warn };
 			iterate(wref, strlen(wref), k, mc_count_window, &cb);  /* :148-158 */
 			cb.var = 1;
 			iterate(wvar, strlen(wvar), k, mc_count_window, &cb);  /* :159-169 */
 		} while (0);
-		free(f);
+		free(f); free(fl);
 	}
 	free(geno); free(wref); free(wvar); free(line);
 	if (fh) fclose(fh);

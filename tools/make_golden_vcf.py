@@ -259,6 +259,21 @@ def main():
         vcf += vcf_line("chr1", p, name, r, a, [rng.choice(GT) if rng.random() > 0.02 else "./." for _ in samples])
     write_case("panel300_24samples", open(SITES300).read(), fasta("chr1", g, 80), vcf)
 
+    # 14. tabs at the end of lines: `while (getline(ss, item, '\t'))` stops on the nothing after a last tab (no empty last
+    #     sample ID / column), while an empty field BETWEEN two tabs is a column (an unknown genotype: hom1)
+    g, pos, sites = basic_inputs(rng, 5)
+    vcf = "##x\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1\tS2\tS3\t\n"
+    vcf += vcf_line("chr1", pos[0], "rs1", "A", "C", ["0|1", "1|1", "0|0"]).replace("\n", "\t\n")
+    vcf += vcf_line("chr1", pos[1], "rs2", "A", "C", ["1|1", "", "0|1"])
+    vcf += vcf_line("chr1", pos[2], "rs3", "A", "C", ["1|1", "0|1", ""]).replace("\n", "\t\n")      # "...0|1\t\t": third column empty
+    vcf += vcf_line("chr1", pos[3], "rs4", "A", "C", ["0|1", "1|0", "1|1"])
+    write_case("trailing_tabs", sites, fasta("chr1", g), vcf)
+    vcf2 = vcf_header(["S1", "S2"]) + vcf_line("chr1", pos[0], "rs1", "A", "C", ["0|1", "1|1"]).replace("\n", "\t\t\n")
+    write_case("abort_two_trailing_tabs", sites, fasta("chr1", g), vcf2)
+    write_case("zero_samples_trailing_tab", sites, fasta("chr1", g),
+               "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t\n" + "chr1\t%d\trs1\tA\tC\t.\tPASS\t.\tGT\n" % pos[0] +
+               "chr1\t%d\trs2\tA\tC\t.\tPASS\t.\tGT\t\n" % pos[1])
+
 
 if __name__ == "__main__":
     main()
