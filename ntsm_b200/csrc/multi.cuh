@@ -220,13 +220,22 @@ __global__ void multi_fill_kernel(const FillParams P)
 			const uint32_t gw = P.geno[(size_t)(w >> 1) * P.gwords + sg];
 			const uint32_t hom = (w & 1) ? 2u : 0u;
 			uint8_t *cell = P.mat + P.stride * (sg * 16) + idx;   // :56-57
-			for (uint32_t s = sg * 16; s < s_end; ++s, cell += P.stride) {
-				const uint32_t g = (gw >> (2 * (s & 15))) & 3u;
-				if (g != 1 && g != hom) continue;                 // this sample does not carry this window's allele
-				const uint32_t x0 = *cell;
-				uint32_t x = x0;
+			// all the bytes this thread needs are requested before the first one is looked at (ncu on the load-per-cell-in-turn
+			// form: 26 of 30 stall cycles on the long scoreboard, profiles/r02z_matrix_ncu_summary.txt; this form: 6.3 -> 6.1 ms
+			// for the whole job -- what is left is the index chain in front of the cells and 32-byte partial-sector writes)
+			uint32_t xs[16];
+#pragma unroll
+			for (uint32_t t = 0; t < 16; ++t) {
+				const uint32_t g = (gw >> (2 * t)) & 3u;
+				xs[t] = sg * 16 + t < s_end && (g == 1 || g == hom) ? cell[(size_t)t * P.stride] : 0u;
+			}
+#pragma unroll
+			for (uint32_t t = 0; t < 16; ++t) {
+				const uint32_t g = (gw >> (2 * t)) & 3u, s = sg * 16 + t;
+				if (s >= s_end || (g != 1 && g != hom)) continue; // out of range / this sample does not carry this window's allele
+				uint32_t x = xs[t];
 				fill_insert<MODE>(P, x, g == 1 ? P.multi : P.multi * 2, first, s);   // VCFConvert.hpp:151-155,162-166
-				if ((MODE == 2 || MODE == 3) && x != x0) *cell = (uint8_t)x;
+				if ((MODE == 2 || MODE == 3) && x != xs[t]) cell[(size_t)t * P.stride] = (uint8_t)x;
 			}
 			continue;
 		}

@@ -110,6 +110,7 @@ def main():
     ap.add_argument("--samples", type=int, default=2504)
     ap.add_argument("--ref-sites", type=int, default=6000, help="sites of the bounded reference sample")
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
+    ap.add_argument("--profile", action="store_true", help="one run of ours only (under ncu): no warm-up, no one-thread run, no reference")
     args = ap.parse_args()
     peaks = {}
     try:
@@ -122,6 +123,10 @@ def main():
         t = time.perf_counter()
         sites_path, ref, vcf, lines, vcf_bytes = write_inputs(d, panel, args.samples, 1, "full")
         log("inputs: %d sites, %d SNP lines, %d samples, VCF %.2f GB (%.1f s to write)" % (len(panel), lines, args.samples, vcf_bytes / 1e9, time.perf_counter() - t))
+        if args.profile:
+            vc, ours = run_ours(sites_path, ref, vcf, os.path.join(d, "full"), args.threads)
+            print(json.dumps({"profile_run": ours}))
+            return
         run_ours(sites_path, ref, vcf, os.path.join(d, "warm"), args.threads)                 # warm-up: CUDA context, page cache
         vc, ours = run_ours(sites_path, ref, vcf, os.path.join(d, "full"), args.threads)
         _, ours_1t = run_ours(sites_path, ref, vcf, os.path.join(d, "full1"), 1)
