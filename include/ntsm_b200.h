@@ -340,8 +340,8 @@ int ntsm_multi_write_norm_matrix(ntsm_multi *m, const ntsm_sites *s, const char 
                                  const char *center_path, uint32_t threads /* host threads that format the text */);
 
 /* VCFConvert() + count(vcf) :42-174: reads the reference genome (plain or gz FASTA) and the multi-sample VCF
- * (plain text), cuts the window around every SNP line (getSeqFromSite :202-215) and inserts batches of lines on
- * the GPU.  NTSM_ERR_ARG for a site whose window would start before its chromosome (undefined upstream). */
+ * (plain text as upstream; gzip / bgzip'ed files are inflated on the way, an extension), cuts the window around
+ * every SNP line (getSeqFromSite :202-215) and inserts batches of lines on the GPU.  NTSM_ERR_ARG for a site whose window would start before its chromosome (undefined upstream). */
 int ntsm_vcf_convert(ntsm_vcf **out, ntsm_ctx *ctx, const ntsm_sites *s, const char *ref_path, const char *vcf_path,
                      uint32_t multi /* opt::multi, 20 */, uint32_t window /* opt::window, 31 */,
                      uint32_t threads /* opt::threads: host threads that parse the VCF (and later format the matrix);

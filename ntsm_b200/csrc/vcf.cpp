@@ -11,14 +11,11 @@
 // where it has undefined behaviour (a site closer than window/2 to the start of its chromosome, or past its end:
 // getSeqFromSite reads outside the sequence) they return NTSM_ERR_ARG.
 #include <errno.h>
-#include <fcntl.h>
 #include <getopt.h>
 #include <limits.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
-#include <sys/mman.h>
-#include <sys/stat.h>
 #include <unistd.h>
 
 #include <atomic>
@@ -54,39 +51,29 @@ int vfail(ntsm_ctx *ctx, int code, const std::string &text)
 	return code;
 }
 
-// the whole input as one span: a mapping for regular files, a buffer for anything else (the reference reads
-// the VCF through an ifstream, :69: plain text only)
+// The whole input as one span.  The reference reads the VCF through an ifstream (:69): plain text.  A plain regular file
+// is scanned in place through GzSource's mapping; anything else is read into memory -- and a gzip / bgzip'ed VCF (what
+// cohort VCFs are shipped as; upstream would read the compressed bytes as text and find no header) is inflated on the
+// way by the library's own decoder, BGZF blocks on `helpers` threads (gzsource.h).
 struct Text {
 	const char *p = nullptr;
 	size_t n = 0;
-	void *map = nullptr;
+	ntsm::GzSource src;
 	std::string own;
-	bool open(const char *path)
+	bool open(const char *path, int helpers)
 	{
-		const int fd = ::open(path, O_RDONLY);
-		if (fd < 0) return false;
-		struct stat st;
-		if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
-			map = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
-			if (map != MAP_FAILED) {
-				p = (const char *)map;
-				n = (size_t)st.st_size;
-				::close(fd);
-				return true;
-			}
-			map = nullptr;
+		if (!src.open(path, helpers, true)) return false;
+		const uint8_t *base;
+		if (src.mapped(&base, &n)) {
+			p = (const char *)base;
+			return true;
 		}
-		char buf[1 << 16];
-		ssize_t got;
-		while ((got = read(fd, buf, sizeof buf)) > 0) own.append(buf, (size_t)got);
-		::close(fd);
+		std::vector<char> buf(1 << 20);
+		int got;
+		while ((got = src.read(buf.data(), (unsigned)buf.size())) > 0) own.append(buf.data(), (size_t)got);
 		p = own.data();
 		n = own.size();
 		return true;
-	}
-	~Text()
-	{
-		if (map) munmap(map, n);
 	}
 };
 
@@ -273,7 +260,7 @@ int vcf_stream(const char *ref_path, const char *vcf_path, uint32_t window, uint
 
 	if (verbose > 1) std::cerr << "Reading VCF file: " << vcf_path << std::endl;
 	Text text;
-	if (!text.open(vcf_path)) { err = std::string("file ") + vcf_path + " cannot be opened"; return NTSM_ERR_IO; }
+	if (!text.open(vcf_path, (int)std::max(1u, threads) - 1)) { err = std::string("file ") + vcf_path + " cannot be opened"; return NTSM_ERR_IO; }
 	const char *at = text.p, *const end = text.p + text.n;
 
 	std::vector<std::string> sample_ids;

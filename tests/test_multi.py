@@ -235,6 +235,24 @@ def test_malformed_vcfs_three_ways(oracle, name, tmp_path):
         assert got.tobytes() == open(t + "/ref_mat.bin", "rb").read()
 
 
+def test_gzipped_vcf_parses_like_plain(tmp_path):
+    """An extension: a gzip / multi-member (bgzip-style) VCF is inflated by the library's own decoder and parsed like the plain
+    file (upstream's ifstream would take the compressed bytes for text)."""
+    import gzip
+    from ntsm_b200.multicount import parse_vcf
+    d, a, _ = _case("panel300_24samples")
+    ref, raw = os.path.join(d, a["ref"]), open(os.path.join(d, "in.vcf"), "rb").read()
+    want = parse_vcf(ref, os.path.join(d, "in.vcf"), threads=2)
+    open(tmp_path / "one.vcf.gz", "wb").write(gzip.compress(raw))
+    with open(tmp_path / "members.vcf.gz", "wb") as fh:
+        for i in range(0, len(raw), 40000):
+            fh.write(gzip.compress(raw[i:i + 40000]))
+    for f, threads in (("one.vcf.gz", 1), ("members.vcf.gz", 4)):
+        got = parse_vcf(ref, str(tmp_path / f), threads=threads)
+        assert got[:3] == want[:3] and np.array_equal(got[3], want[3])
+    assert parse_vcf(ref, str(tmp_path / "missing.vcf"))[0] == -5
+
+
 def test_ntsmvcf_binary_has_no_cpu_path():
     assert os.path.exists(NTSMVCF), "make -C ntsm_b200/csrc"
     try:
