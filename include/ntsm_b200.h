@@ -360,6 +360,8 @@ uint32_t ntsm_vcf_lines_wstride(const ntsm_vcf_lines *l);
 const char *ntsm_vcf_lines_windows(const ntsm_vcf_lines *l);
 const uint16_t *ntsm_vcf_lines_lens(const ntsm_vcf_lines *l);
 const uint8_t *ntsm_vcf_lines_genotypes(const ntsm_vcf_lines *l);
+/* test knob: bytes per region in which a VCF that is not a plain regular file (gzip, pipe) is read; 0 = just ask */
+uint64_t ntsm_vcf_stream_chunk(uint64_t bytes);
 ntsm_multi *ntsm_vcf_multi(ntsm_vcf *v);
 uint32_t ntsm_vcf_n_samples(const ntsm_vcf *v);
 const char *ntsm_vcf_sample_id(const ntsm_vcf *v, uint32_t i);

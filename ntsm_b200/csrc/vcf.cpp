@@ -51,30 +51,74 @@ int vfail(ntsm_ctx *ctx, int code, const std::string &text)
 	return code;
 }
 
-// The whole input as one span.  The reference reads the VCF through an ifstream (:69): plain text.  A plain regular file
-// is scanned in place through GzSource's mapping; anything else is read into memory -- and a gzip / bgzip'ed VCF (what
-// cohort VCFs are shipped as; upstream would read the compressed bytes as text and find no header) is inflated on the
+// The input as a sequence of regions of whole lines.  The reference reads the VCF through an ifstream (:69): plain text.
+// A plain regular file is ONE region, scanned in place through GzSource's mapping; anything else arrives in regions of
+// g_stream_chunk bytes cut at line ends -- and a gzip / bgzip'ed VCF (what cohort VCFs are shipped as: tens of GB of text
+// that could not be held whole; upstream would read the compressed bytes as text and find no header) is inflated on the
 // way by the library's own decoder, BGZF blocks on `helpers` threads (gzsource.h).
-struct Text {
-	const char *p = nullptr;
-	size_t n = 0;
+size_t g_stream_chunk = 64u << 20;
+
+struct Regions {
 	ntsm::GzSource src;
-	std::string own;
+	bool mapped = false, done = false;
+	const uint8_t *base = nullptr;
+	size_t size = 0;
+	std::vector<char> buf;
+	size_t carry = 0;                                              // bytes of an unfinished line at the front of buf
 	bool open(const char *path, int helpers)
 	{
 		if (!src.open(path, helpers, true)) return false;
-		const uint8_t *base;
-		if (src.mapped(&base, &n)) {
-			p = (const char *)base;
-			return true;
-		}
-		std::vector<char> buf(1 << 20);
-		int got;
-		while ((got = src.read(buf.data(), (unsigned)buf.size())) > 0) own.append(buf.data(), (size_t)got);
-		p = own.data();
-		n = own.size();
+		mapped = src.mapped(&base, &size);
 		return true;
 	}
+	// the next region [*p, *p + *n): whole lines, except that the LAST region ends where the input ends; false when there is none
+	bool next(const char **p, size_t *n, bool *last)
+	{
+		if (done) return false;
+		if (mapped) {
+			done = true;
+			*p = (const char *)base;
+			*n = size;
+			*last = true;
+			return size > 0;
+		}
+		if (buf.size() < g_stream_chunk) buf.resize(g_stream_chunk);
+		size_t have = carry;
+		for (;;) {
+			while (have < buf.size()) {
+				const int got = src.read(buf.data() + have, (unsigned)std::min<size_t>(buf.size() - have, 1u << 30));
+				if (got <= 0) { done = true; break; }
+				have += (size_t)got;
+			}
+			if (done) {
+				*p = buf.data();
+				*n = have;
+				*last = true;
+				carry = 0;
+				return have > 0;
+			}
+			// cut at the last line end; a line longer than the buffer makes the buffer grow
+			size_t cut = have;
+			while (cut > 0 && buf[cut - 1] != '\n') --cut;
+			if (cut == 0) {
+				buf.resize(buf.size() * 2);
+				continue;
+			}
+			region_end = cut;
+			*p = buf.data();
+			*n = cut;
+			*last = false;
+			carry = have - cut;
+			return true;
+		}
+	}
+	// called before the following next(): moves the unfinished line to the front
+	void recycle()
+	{
+		if (!mapped && carry && region_end) memmove(buf.data(), buf.data() + region_end, carry);
+		region_end = 0;
+	}
+	size_t region_end = 0;
 };
 
 struct Field { const char *p; size_t n; };
@@ -259,76 +303,95 @@ int vcf_stream(const char *ref_path, const char *vcf_path, uint32_t window, uint
 	}
 
 	if (verbose > 1) std::cerr << "Reading VCF file: " << vcf_path << std::endl;
-	Text text;
-	if (!text.open(vcf_path, (int)std::max(1u, threads) - 1)) { err = std::string("file ") + vcf_path + " cannot be opened"; return NTSM_ERR_IO; }
-	const char *at = text.p, *const end = text.p + text.n;
+	Regions regions;
+	if (!regions.open(vcf_path, (int)std::max(1u, threads) - 1)) { err = std::string("file ") + vcf_path + " cannot be opened"; return NTSM_ERR_IO; }
 
 	std::vector<std::string> sample_ids;
 	std::vector<Field> f;
-	// header: lines are looked at until the one whose first field is "#CHROM"; 8 more fields are skipped, the rest
-	// are the sample IDs (:71-93).  A last line without '\n' is still a line here (the stream only goes bad after it).
-	while (at < end) {
-		const char *nl = (const char *)memchr(at, '\n', (size_t)(end - at));
-		const char *le = nl ? nl : end;
-		const size_t len = (size_t)(le - at);
-		if (len == 0) {                                            // line.at(0) throws
-			err = "empty line before the #CHROM line: the reference dies in string::at (src/VCFConvert.hpp:74)";
-			return NTSM_ERR_NOKEY;
-		}
-		const bool is_header = at[0] == '#';
-		if (is_header) split(at, len, f);
-		at = nl ? nl + 1 : end;
-		if (is_header && f[0].n == 6 && memcmp(f[0].p, "#CHROM", 6) == 0) {
-			// `while (getline(ss, item, '\t'))` (:88): a tab at the very end of the line leaves nothing to extract and ends
-			// the loop -- no empty last ID (an empty field between two tabs does count)
-			if (f.size() > 9 && f.back().n == 0) f.pop_back();
-			for (size_t i = 9; i < f.size(); ++i) sample_ids.emplace_back(f[i].p, f[i].n);
-			break;
-		}
-	}
-	const uint32_t S = (uint32_t)sample_ids.size();
-	if (verbose > 1) std::cerr << "Starting multicount of each rsID for " << S << " samples." << std::endl;
-	int rc = on_header(sample_ids);
-	if (rc) return rc;
-
-	// The data lines.  Parsing is per line and independent, so `threads` workers (opt::threads: the reference runs this
-	// loop under `omp parallel`, :99) parse batches of lines side by side; the batches are then handed on in file
-	// order, which -- unlike upstream with more than one thread -- keeps "the first writer of a cell wins" the
-	// one-thread result whatever `threads` is.
+	bool in_header = true;
+	uint32_t S = 0;
+	int rc = NTSM_OK;
 	const uint32_t wstride = (window + 15u) & ~15u;
 	const uint32_t batch_lines = 2048;
-	std::vector<std::pair<const char *, const char *>> spans;       // [begin, end) of each batch: whole lines, '\n' included
-	{
-		const char *b = at;
-		uint32_t in_batch = 0;
-		while (at < end) {
-			const char *nl = (const char *)memchr(at, '\n', (size_t)(end - at));
-			if (!nl) break;                                        // :101-108: the getline that hits end of file leaves the stream not good(): that line is dropped
-			at = nl + 1;
-			if (++in_batch == batch_lines) {
-				spans.emplace_back(b, at);
-				b = at;
-				in_batch = 0;
-			}
-		}
-		if (in_batch) spans.emplace_back(b, at);
-	}
-	const ParseEnv env{ &chroms, &chr_ids, S, window, wstride, verbose };
 	const uint32_t T = std::max(1u, threads);
 	const size_t round = std::max<size_t>(4 * (size_t)T, 16);
-	std::vector<LineBatch> batches(std::min(round, spans.size()));
-	for (size_t r0 = 0; r0 < spans.size(); r0 += round) {
-		const size_t nb = std::min(round, spans.size() - r0);
-		parallel_for(nb, T, [&](size_t i) { parse_lines(env, spans[r0 + i].first, spans[r0 + i].second, batches[i]); });
-		for (size_t i = 0; i < nb; ++i) {
-			LineBatch &b = batches[i];
-			if (b.n && (rc = on_batch(b, wstride))) return rc;     // the lines before a fatal one are handed on, as upstream inserts them before it dies
-			if (b.err) {
-				err = b.msg;
-				return b.err;
+	std::vector<std::pair<const char *, const char *>> spans;       // [begin, end) of each batch: whole lines, '\n' included
+	std::vector<LineBatch> batches;
+	auto header_done = [&]() -> int {
+		in_header = false;
+		S = (uint32_t)sample_ids.size();
+		if (verbose > 1) std::cerr << "Starting multicount of each rsID for " << S << " samples." << std::endl;
+		return on_header(sample_ids);
+	};
+
+	const char *rp;
+	size_t rn;
+	bool last;
+	while (regions.next(&rp, &rn, &last)) {
+		const char *at = rp, *const end = rp + rn;
+		// header: lines are looked at until the one whose first field is "#CHROM"; 8 more fields are skipped, the rest
+		// are the sample IDs (:71-93).  A last line without '\n' is still a line here (the stream only goes bad after it).
+		while (in_header && at < end) {
+			const char *nl = (const char *)memchr(at, '\n', (size_t)(end - at));
+			const char *le = nl ? nl : end;
+			const size_t len = (size_t)(le - at);
+			if (len == 0) {                                        // line.at(0) throws
+				err = "empty line before the #CHROM line: the reference dies in string::at (src/VCFConvert.hpp:74)";
+				return NTSM_ERR_NOKEY;
+			}
+			const bool is_header = at[0] == '#';
+			if (is_header) split(at, len, f);
+			at = nl ? nl + 1 : end;
+			if (is_header && f[0].n == 6 && memcmp(f[0].p, "#CHROM", 6) == 0) {
+				// `while (getline(ss, item, '\t'))` (:88): a tab at the very end of the line leaves nothing to extract and ends
+				// the loop -- no empty last ID (an empty field between two tabs does count)
+				if (f.size() > 9 && f.back().n == 0) f.pop_back();
+				for (size_t i = 9; i < f.size(); ++i) sample_ids.emplace_back(f[i].p, f[i].n);
+				if ((rc = header_done())) return rc;
 			}
 		}
+		if (in_header) {
+			regions.recycle();
+			continue;
+		}
+
+		// The data lines.  Parsing is per line and independent, so `threads` workers (opt::threads: the reference runs this
+		// loop under `omp parallel`, :99) parse batches of lines side by side; the batches are then handed on in file
+		// order, which -- unlike upstream with more than one thread -- keeps "the first writer of a cell wins" the
+		// one-thread result whatever `threads` is.
+		spans.clear();
+		{
+			const char *b = at;
+			uint32_t in_batch = 0;
+			while (at < end) {
+				const char *nl = (const char *)memchr(at, '\n', (size_t)(end - at));
+				if (!nl) break;                                    // :101-108: the getline that hits end of file leaves the stream not good(): that line is dropped
+				at = nl + 1;
+				if (++in_batch == batch_lines) {
+					spans.emplace_back(b, at);
+					b = at;
+					in_batch = 0;
+				}
+			}
+			if (in_batch) spans.emplace_back(b, at);
+		}
+		const ParseEnv env{ &chroms, &chr_ids, S, window, wstride, verbose };
+		if (batches.size() < std::min(round, spans.size())) batches.resize(std::min(round, spans.size()));
+		for (size_t r0 = 0; r0 < spans.size(); r0 += round) {
+			const size_t nb = std::min(round, spans.size() - r0);
+			parallel_for(nb, T, [&](size_t i) { parse_lines(env, spans[r0 + i].first, spans[r0 + i].second, batches[i]); });
+			for (size_t i = 0; i < nb; ++i) {
+				LineBatch &b = batches[i];
+				if (b.n && (rc = on_batch(b, wstride))) return rc; // the lines before a fatal one are handed on, as upstream inserts them before it dies
+				if (b.err) {
+					err = b.msg;
+					return b.err;
+				}
+			}
+		}
+		regions.recycle();
 	}
+	if (in_header && (rc = header_done())) return rc;              // no #CHROM line at all: no samples, no data lines (:71-98)
 	return NTSM_OK;
 }
 
@@ -806,4 +869,12 @@ extern "C" int ntsm_vcf_main(int argc, char **argv)
 	ntsm_ctx_destroy(ctx);
 	ntsm_sites_free(sites);
 	return 0;
+}
+
+// test knob: bytes per region when the VCF is not a plain regular file (default 64 MiB); returns the previous value
+extern "C" uint64_t ntsm_vcf_stream_chunk(uint64_t bytes)
+{
+	const uint64_t old = g_stream_chunk;
+	if (bytes) g_stream_chunk = (size_t)std::max<uint64_t>(bytes, 64);
+	return old;
 }

@@ -247,9 +247,26 @@ def test_gzipped_vcf_parses_like_plain(tmp_path):
     with open(tmp_path / "members.vcf.gz", "wb") as fh:
         for i in range(0, len(raw), 40000):
             fh.write(gzip.compress(raw[i:i + 40000]))
-    for f, threads in (("one.vcf.gz", 1), ("members.vcf.gz", 4)):
-        got = parse_vcf(ref, str(tmp_path / f), threads=threads)
-        assert got[:3] == want[:3] and np.array_equal(got[3], want[3])
+    import ntsm_b200
+    L = ntsm_b200.lib()
+    old = L.ntsm_vcf_stream_chunk(0)
+    try:
+        # such input is read in regions cut at line ends (64 MiB; here: smaller than a line, a few lines, the default)
+        for chunk in (64, 3000, 100000, old):
+            L.ntsm_vcf_stream_chunk(chunk)
+            for f, threads in (("one.vcf.gz", 1), ("members.vcf.gz", 4)):
+                got = parse_vcf(ref, str(tmp_path / f), threads=threads)
+                assert got[:3] == want[:3] and np.array_equal(got[3], want[3]), (chunk, f)
+        # every fixture, gzipped and read in small regions: the same lines, the same death
+        L.ntsm_vcf_stream_chunk(700)
+        for name in vcf_cases():
+            d2, a2, _ = _case(name)
+            open(tmp_path / "c.vcf.gz", "wb").write(gzip.compress(open(os.path.join(d2, "in.vcf"), "rb").read()))
+            w = parse_vcf(os.path.join(d2, a2["ref"]), os.path.join(d2, "in.vcf"), window=a2["window"])
+            g = parse_vcf(os.path.join(d2, a2["ref"]), str(tmp_path / "c.vcf.gz"), window=a2["window"], threads=3)
+            assert g[:3] == w[:3] and np.array_equal(g[3], w[3]), name
+    finally:
+        L.ntsm_vcf_stream_chunk(old)
     assert parse_vcf(ref, str(tmp_path / "missing.vcf"))[0] == -5
 
 
