@@ -302,6 +302,8 @@ int ntsm_count_files(ntsm_ctx *const *ctxs, uint32_t n_ctx, const char *const *p
  * loaded (ntsm_load_siteset = MultiCount::initCountsHash, which is FingerPrint's).  Results equal the
  * reference's classes run with one thread (tests/golden/vcf, made by tools/ref_vcf_harness.cpp).  Calls return
  * NTSM_ERR_NOKEY where the reference process dies (uncaught exception / failed assert, exit 134). */
+/* One caller at a time per ntsm_multi / ntsm_vcf (the library brings its own threads: `threads` arguments); the
+ * object works on the ctx's compute stream as it was when ntsm_multi_create ran. */
 typedef struct ntsm_multi ntsm_multi; /* MultiCount */
 typedef struct ntsm_vcf ntsm_vcf;     /* VCFConvert */
 int ntsm_multi_create(ntsm_multi **out, ntsm_ctx *ctx, uint32_t n_samples); /* MultiCount(sampleIDs) :43-49; the ctx must outlive it */

@@ -511,6 +511,9 @@ extern "C" int ntsm_multi_write_norm_matrix(ntsm_multi *m, const ntsm_sites *sit
 {
 	if (!m || !sites || !matrix_path || !center_path) return NTSM_ERR_ARG;
 	const uint32_t S = ntsm_sites_n_sites(sites), N = ntsm_multi_n_samples(m);
+	if (N && !sample_ids) return NTSM_ERR_ARG;
+	for (uint32_t j = 0; j < N; ++j)
+		if (!sample_ids[j]) return NTSM_ERR_ARG;
 	FILE *out = fopen(matrix_path, "wb");
 	FILE *cf = fopen(center_path, "wb");
 	if (!out || !cf) {
