@@ -351,7 +351,8 @@ int ntsm_vcf_convert(ntsm_vcf **out, ntsm_ctx *ctx, const ntsm_sites *s, const c
 void ntsm_vcf_destroy(ntsm_vcf *v);
 /* The host half of the above on its own, no device needed: the SNP lines of the VCF as ntsm_multi_insert_windows takes
  * them (windows [2 * count][wstride] + lens [2 * count], genotypes [count][n_samples]).  Returns the code
- * ntsm_vcf_convert would; *out is set even then and holds the lines in front of the fatal one. */
+ * ntsm_vcf_convert would; *out is set even then and holds the lines in front of the fatal one.  out == NULL: parse
+ * only, keep nothing (what the host half costs). */
 typedef struct ntsm_vcf_lines ntsm_vcf_lines;
 int ntsm_vcf_parse(ntsm_vcf_lines **out, const char *ref_path, const char *vcf_path, uint32_t window, uint32_t threads, int verbose);
 void ntsm_vcf_lines_free(ntsm_vcf_lines *l);
@@ -364,6 +365,9 @@ const uint16_t *ntsm_vcf_lines_lens(const ntsm_vcf_lines *l);
 const uint8_t *ntsm_vcf_lines_genotypes(const ntsm_vcf_lines *l);
 /* test knob: bytes per region in which a VCF that is not a plain regular file (gzip, pipe) is read; 0 = just ask */
 uint64_t ntsm_vcf_stream_chunk(uint64_t bytes);
+/* which genotype-column decoder the VCF parser uses: 0 byte-wise, 1 AVX2 (8 columns a step), 2 AVX-512 (16), picked from the
+ * CPU; force >= 0 sets it (capped at what the CPU has), -1 = back to automatic, -2 = just ask.  Same codes either way. */
+int ntsm_vcf_genotype_isa(int force);
 ntsm_multi *ntsm_vcf_multi(ntsm_vcf *v);
 uint32_t ntsm_vcf_n_samples(const ntsm_vcf *v);
 const char *ntsm_vcf_sample_id(const ntsm_vcf *v, uint32_t i);

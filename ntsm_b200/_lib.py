@@ -132,6 +132,7 @@ _SIGS = {
     "ntsm_vcf_lines_lens": (_P, [_P]),
     "ntsm_vcf_lines_genotypes": (_P, [_P]),
     "ntsm_vcf_stream_chunk": (C.c_uint64, [C.c_uint64]),
+    "ntsm_vcf_genotype_isa": (C.c_int, [C.c_int]),
     "ntsm_vcf_multi": (_P, [_P]),
     "ntsm_vcf_n_samples": (C.c_uint32, [_P]),
     "ntsm_vcf_sample_id": (C.c_char_p, [_P, C.c_uint32]),

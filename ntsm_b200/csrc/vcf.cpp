@@ -11,6 +11,7 @@
 // where it has undefined behaviour (a site closer than window/2 to the start of its chromosome, or past its end:
 // getSeqFromSite reads outside the sequence) they return NTSM_ERR_ARG.
 #include <errno.h>
+#include <immintrin.h>
 #include <getopt.h>
 #include <limits.h>
 #include <stdio.h>
@@ -152,6 +153,39 @@ inline uint8_t genotype_code(const char *g, size_t n)
 	return 0;
 }
 
+// The usual cohort VCF column is "a|b\t" with a, b in {0, 1}: four bytes whose code is simply a + b.  16 (AVX-512) or 8
+// (AVX2) columns are checked and decoded at once: as little-endian uint32 lanes, (lane & 0xFFFEFFFE) must equal
+// '0' '|' '0' '\t', and the low bits of bytes 0 and 2 are the two alleles.  Returns false (nothing consumed) when any of
+// the columns is something else -- "./.", "0/1", a multi-digit allele, the line's last column (it ends in '\n') -- and the
+// caller's byte-wise loop takes over, so the codes are genotype_code's either way.
+constexpr uint32_t kGtPattern = (uint32_t)'0' | (uint32_t)'|' << 8 | (uint32_t)'0' << 16 | (uint32_t)'\t' << 24;
+
+__attribute__((target("avx512f,avx512bw,bmi2"))) bool decode16_avx512(const char *q, uint32_t *codes32)
+{
+	const __m512i v = _mm512_loadu_si512((const void *)q);
+	if (_mm512_cmpeq_epi32_mask(_mm512_and_si512(v, _mm512_set1_epi32((int)0xFFFEFFFEu)), _mm512_set1_epi32((int)kGtPattern)) != 0xFFFF) return false;
+	const uint32_t a = _mm512_test_epi32_mask(v, _mm512_set1_epi32(1)), b = _mm512_test_epi32_mask(v, _mm512_set1_epi32(1 << 16));
+	*codes32 = (uint32_t)_pdep_u32(a ^ b, 0x55555555u) | (uint32_t)_pdep_u32(a & b, 0xAAAAAAAAu);   // a + b, two bits per column
+	return true;
+}
+
+__attribute__((target("avx2,bmi2"))) bool decode8_avx2(const char *q, uint32_t *codes16)
+{
+	const __m256i v = _mm256_loadu_si256((const __m256i *)q);
+	const __m256i ok = _mm256_cmpeq_epi32(_mm256_and_si256(v, _mm256_set1_epi32((int)0xFFFEFFFEu)), _mm256_set1_epi32((int)kGtPattern));
+	if (_mm256_movemask_ps(_mm256_castsi256_ps(ok)) != 0xFF) return false;
+	const uint32_t a = (uint32_t)_mm256_movemask_ps(_mm256_castsi256_ps(_mm256_slli_epi32(v, 31)));
+	const uint32_t b = (uint32_t)_mm256_movemask_ps(_mm256_castsi256_ps(_mm256_slli_epi32(v, 15)));
+	*codes16 = (uint32_t)_pdep_u32(a ^ b, 0x5555u) | (uint32_t)_pdep_u32(a & b, 0xAAAAu);
+	return true;
+}
+
+const int g_gt_isa = __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("bmi2") ? 2
+                     : __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2")                                       ? 1
+                                                                                                                                 : 0;
+int g_gt_isa_forced = -1;                                          // tests: 0 scalar, 1 AVX2, 2 AVX-512 (never above what the CPU has)
+inline int gt_isa() { return g_gt_isa_forced >= 0 && g_gt_isa_forced < g_gt_isa ? g_gt_isa_forced : g_gt_isa; }
+
 // n items over `threads` workers (an atomic counter hands them out); threads <= 1 runs inline
 template <class F> void parallel_for(size_t n, uint32_t threads, F fn)
 {
@@ -248,8 +282,27 @@ void parse_lines(const ParseEnv &E, const char *at, const char *end, LineBatch &
 		uint32_t *g = B.geno2.data() + (size_t)B.n * gwords;
 		for (uint32_t w = 0; w < gwords; ++w) g[w] = 0;
 		size_t n_cols = 0;
+		const int isa = gt_isa();
 		for (const char *q = cols; q;) {
-			// almost every column is three characters and a tab
+			// 16 / 8 regular columns at a time where the CPU can (appended at bit 2 * n_cols of the line's words)
+			uint32_t codes;
+			if (isa == 2 && n_cols + 16 <= S && q + 64 <= nl && decode16_avx512(q, &codes)) {
+				const uint64_t v = (uint64_t)codes << (2 * (n_cols & 15));
+				g[n_cols >> 4] |= (uint32_t)v;
+				if (v >> 32) g[(n_cols >> 4) + 1] |= (uint32_t)(v >> 32);
+				n_cols += 16;
+				q += 64;
+				continue;
+			}
+			if (isa == 1 && n_cols + 8 <= S && q + 32 <= nl && decode8_avx2(q, &codes)) {
+				const uint64_t v = (uint64_t)codes << (2 * (n_cols & 15));
+				g[n_cols >> 4] |= (uint32_t)v;
+				if (v >> 32) g[(n_cols >> 4) + 1] |= (uint32_t)(v >> 32);
+				n_cols += 8;
+				q += 32;
+				continue;
+			}
+			// almost every other column is three characters and a tab
 			const char *t = q + 3 < nl && q[3] == '\t' && q[0] != '\t' && q[1] != '\t' && q[2] != '\t' ? q + 3 : (const char *)memchr(q, '\t', (size_t)(nl - q));
 			const char *fe = t ? t : nl;
 			if (!t && fe == q) break;                              // the same `while (getline(...))` (:136): nothing after the line's last tab, no column
@@ -444,7 +497,14 @@ struct ntsm_vcf_lines {
 
 extern "C" int ntsm_vcf_parse(ntsm_vcf_lines **out, const char *ref_path, const char *vcf_path, uint32_t window, uint32_t threads, int verbose)
 {
-	if (!out || !ref_path || !vcf_path) return vfail(nullptr, NTSM_ERR_ARG, "ntsm_vcf_parse: null argument");
+	if (!ref_path || !vcf_path) return vfail(nullptr, NTSM_ERR_ARG, "ntsm_vcf_parse: null argument");
+	if (!out) {                                                    // parse only, nothing kept: what the host half costs (tools, timing)
+		std::string e;
+		const int r = vcf_stream(ref_path, vcf_path, window, threads, verbose, e, [](const std::vector<std::string> &) { return 0; },
+		                         [](const LineBatch &, uint32_t) { return 0; });
+		if (r) vfail(nullptr, r, e);
+		return r;
+	}
 	*out = nullptr;
 	ntsm_vcf_lines *L = new ntsm_vcf_lines();
 	std::string err;
@@ -880,4 +940,12 @@ extern "C" uint64_t ntsm_vcf_stream_chunk(uint64_t bytes)
 	const uint64_t old = g_stream_chunk;
 	if (bytes) g_stream_chunk = (size_t)std::max<uint64_t>(bytes, 64);
 	return old;
+}
+
+// which genotype decoder the VCF parser uses: 0 byte-wise, 1 AVX2 (8 columns a step), 2 AVX-512 (16); force >= 0 sets it
+// (capped at what the CPU has), -1 = back to automatic, -2 = just ask
+extern "C" int ntsm_vcf_genotype_isa(int force)
+{
+	if (force >= -1) g_gt_isa_forced = force;
+	return gt_isa();
 }

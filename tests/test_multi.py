@@ -270,6 +270,34 @@ def test_gzipped_vcf_parses_like_plain(tmp_path):
     assert parse_vcf(ref, str(tmp_path / "missing.vcf"))[0] == -5
 
 
+def test_genotype_decoders_agree(tmp_path):
+    """The VCF parser's column decoders -- byte-wise, AVX2 (8 columns a step), AVX-512 (16) -- give the same lines on every
+    fixture and on wide fuzzed VCFs whose odd columns fall at every offset of a step."""
+    import ntsm_b200
+    from ntsm_b200.multicount import parse_vcf
+    L = ntsm_b200.lib()
+    have = L.ntsm_vcf_genotype_isa(-1)
+    if have == 0:
+        pytest.skip("no AVX2 on this CPU: only the byte-wise decoder exists")
+    inputs = [(os.path.join(d, a["ref"]), os.path.join(d, "in.vcf"), a["window"]) for d, a, _ in map(_case, vcf_cases())]
+    rng = random.Random(77)
+    for i, n_samples in enumerate((7, 16, 33, 100, 257)):
+        d = tmp_path / ("f%d" % i)
+        os.makedirs(d)
+        _fuzz_inputs(rng, str(d), 30, n_samples, odd_gt=0.02 * i)
+        inputs.append((str(d / "ref.fa"), str(d / "in.vcf"), 31))
+    try:
+        for ref, vcf, window in inputs:
+            L.ntsm_vcf_genotype_isa(0)
+            want = parse_vcf(ref, vcf, window=window, threads=2)
+            for isa in range(1, have + 1):
+                assert L.ntsm_vcf_genotype_isa(isa) == isa
+                got = parse_vcf(ref, vcf, window=window, threads=2)
+                assert got[:3] == want[:3] and np.array_equal(got[3], want[3]), (vcf, isa)
+    finally:
+        L.ntsm_vcf_genotype_isa(-1)
+
+
 def test_ntsmvcf_binary_has_no_cpu_path():
     assert os.path.exists(NTSMVCF), "make -C ntsm_b200/csrc"
     try:
