@@ -180,9 +180,11 @@ __attribute__((target("avx2,bmi2"))) bool decode8_avx2(const char *q, uint32_t *
 	return true;
 }
 
-const int g_gt_isa = __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("bmi2") ? 2
-                     : __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2")                                       ? 1
-                                                                                                                                 : 0;
+const int g_gt_isa = [] {
+	__builtin_cpu_init();                                          // this runs as a static initialiser of a shared library
+	if (__builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("bmi2")) return 2;
+	return __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2") ? 1 : 0;
+}();
 int g_gt_isa_forced = -1;                                          // tests: 0 scalar, 1 AVX2, 2 AVX-512 (never above what the CPU has)
 inline int gt_isa() { return g_gt_isa_forced >= 0 && g_gt_isa_forced < g_gt_isa ? g_gt_isa_forced : g_gt_isa; }
 
