@@ -19,6 +19,8 @@ threads), `e2e_ascii*` (insertCount over ASCII reads in pinned host memory: host
 packer, or both), `e2e_packed` (already packed pinned stream: what PCIe alone allows).  At N > 1 also
 `strong_scaling` (one 100-Gbase job cut N ways) and `check.n_gpu_equals_1_gpu`.  `cpu_baseline` and
 `--impl reference`: the unmodified reference binary on 1.5 Gbases of the same workload, 16 host threads.
+`matrix_path` (rank 0): the multi-sample matrix path of `ntsmVCF -p` on its own workload and clock,
+measured by tools/bench_matrix.py next to the reference's MultiCount + VCFConvert classes on the host cores.
 """
 import argparse
 import json
